@@ -1,0 +1,132 @@
+// TEST INFRASTRUCTURE ONLY - never linked into or called from the product path.
+//
+// C wrappers around the UNMODIFIED reference sources, compiled from where they lie under
+// /root/reference by oracle/Makefile into oracle/_ref/libref_oracle.so:
+//   * third-party/libforest/src/{classifier,data,learning,tools}.cpp  (learner = model producer,
+//     RandomForest::read / multiClassLogPosterior / DecisionTree::findLeafNode = a9-a12 oracle)
+//   * third-party/densecrf/src/permutohedral.cpp (Permutohedral::init / compute = a16-a18 oracle)
+// No reference source is copied into this repository; this file only *calls* the reference.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <vector>
+
+#include "libforest/libforest.h"
+#include "permutohedral.h"
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// libforest: training (mirrors the learner set-up of reference src/train.cpp:225-249)
+// ---------------------------------------------------------------------------------------------
+// feats: [n][D] row-major; labels: [n][L].  Returns 0 on success.
+int ref_forest_train(const float* feats, int n, int D, const int* labels, int L, int num_trees,
+                     int max_depth, int min_split, int num_threads, const char* out_path) {
+    libf::DataStorage storage(L);
+    for (int i = 0; i < n; i++) {
+        libf::DataPoint* p = new libf::DataPoint(D);
+        for (int k = 0; k < D; k++) p->at(k) = feats[(size_t)i * D + k];
+        std::vector<int> lab(labels + (size_t)i * L, labels + (size_t)(i + 1) * L);
+        storage.addDataPointMulti(p, lab);
+    }
+    libf::DecisionTreeLearner treeLearner;
+    treeLearner.autoconf(&storage);
+    treeLearner.setUseBootstrap(true);
+    treeLearner.setMaxDepth(max_depth);
+    treeLearner.setMinSplitExamples(min_split);
+    treeLearner.setUseClassFrequency(false);
+    treeLearner.useMultiLabelLayers(true);
+    libf::RandomForestLearner forestLearner;
+    forestLearner.setTreeLearner(&treeLearner);
+    forestLearner.setNumTrees(num_trees);
+    forestLearner.setNumThreads(num_threads);
+    libf::RandomForest* forest = forestLearner.learn(&storage);
+    std::filebuf fb;
+    if (!fb.open(out_path, std::ios::out | std::ios::binary)) return 1;
+    std::ostream os(&fb);
+    forest->write(os);
+    fb.close();
+    delete forest;
+    return 0;
+}
+
+void* ref_forest_load(const char* path) {
+    std::filebuf fb;
+    if (!fb.open(path, std::ios::in | std::ios::binary)) return nullptr;
+    std::istream is(&fb);
+    libf::RandomForest* f = new libf::RandomForest();
+    f->read(is);
+    fb.close();
+    return f;
+}
+void ref_forest_free(void* f) { delete (libf::RandomForest*)f; }
+int ref_forest_num_trees(void* f) { return ((libf::RandomForest*)f)->getSize(); }
+
+// leaf_ids: [T][n] (may be NULL), logpost: [n][sumC] with the layers concatenated (may be NULL).
+// Returns sumC (floats per sample).
+int ref_forest_predict(void* fv, const float* feats, int n, int D, int* leaf_ids, float* logpost) {
+    libf::RandomForest* f = (libf::RandomForest*)fv;
+    const int T = f->getSize();
+    int sumC = 0;
+    for (int i = 0; i < n; i++) {
+        libf::DataPoint p(const_cast<float*>(feats + (size_t)i * D), D, false);
+        if (leaf_ids)
+            for (int t = 0; t < T; t++)
+                leaf_ids[(size_t)t * n + i] = ((libf::DecisionTree*)f->getTree(t))->findLeafNode(&p);
+        std::vector<std::vector<float> > post;
+        f->multiClassLogPosterior(&p, post);
+        if (i == 0)
+            for (size_t l = 0; l < post.size(); l++) sumC += (int)post[l].size();
+        if (logpost) {
+            float* o = logpost + (size_t)i * sumC;
+            for (size_t l = 0; l < post.size(); l++)
+                for (size_t c = 0; c < post[l].size(); c++) *o++ = post[l][c];
+        }
+    }
+    return sumC;
+}
+
+// ---------------------------------------------------------------------------------------------
+// permutohedral lattice, verbatim
+// ---------------------------------------------------------------------------------------------
+struct RefLattice : public Permutohedral {
+    int V() const { return M_; }
+    const int* offsets() const { return offset_.data(); }
+    const float* bary() const { return barycentric_.data(); }
+    const Neighbors* nbr() const { return blur_neighbors_.data(); }
+};
+
+// feats: d x N column-major (Eigen layout, reference segmenter.cpp:629-637)
+void* ref_lattice_init(const float* feats, int d, int N) {
+    Eigen::MatrixXf f(d, N);
+    memcpy(f.data(), feats, sizeof(float) * (size_t)d * N);
+    RefLattice* l = new RefLattice();
+    l->init(f);
+    return l;
+}
+int ref_lattice_vertices(void* l) { return ((RefLattice*)l)->V(); }
+// in/out: M x N column-major.  Dispatches like Permutohedral::compute (scalar path for M<=2).
+void ref_lattice_compute(void* l, const float* in, int M, int N, float* out) {
+    Eigen::MatrixXf i(M, N), o(M, N);
+    memcpy(i.data(), in, sizeof(float) * (size_t)M * N);
+    ((RefLattice*)l)->compute(o, i, false);
+    memcpy(out, o.data(), sizeof(float) * (size_t)M * N);
+}
+// offsets/bary: [(d+1)*N] in the reference's point-major order (permutohedral.cpp:268-275)
+void ref_lattice_get(void* l, int d, int N, int* offsets, float* bary) {
+    memcpy(offsets, ((RefLattice*)l)->offsets(), sizeof(int) * (size_t)(d + 1) * N);
+    memcpy(bary, ((RefLattice*)l)->bary(), sizeof(float) * (size_t)(d + 1) * N);
+}
+// neighbours: [(d+1)][V][2]
+void ref_lattice_neighbors(void* l, int d, int* nb) {
+    RefLattice* L = (RefLattice*)l;
+    const int V = L->V();
+    for (int j = 0; j <= d; j++)
+        for (int i = 0; i < V; i++) {
+            nb[((size_t)j * V + i) * 2 + 0] = L->nbr()[(size_t)j * V + i].n1;
+            nb[((size_t)j * V + i) * 2 + 1] = L->nbr()[(size_t)j * V + i].n2;
+        }
+}
+void ref_lattice_free(void* l) { delete (RefLattice*)l; }
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+"""CPU tests: pin the oracle (oracle/oracle.c) against
+  * cv2 4.13.0 outputs frozen in tests/golden/cv_golden.npz,
+  * outputs of the UNMODIFIED reference (libforest, permutohedral.cpp) frozen in ref_golden.npz,
+  * and, where oracle/_ref/libref_oracle.so is present, the reference itself run live.
+"""
+import numpy as np
+import pytest
+
+from conftest import FOREST
+
+
+def test_lab_matches_cv2(orc, cv_golden):
+    assert np.array_equal(orc.bgr2lab(cv_golden["lab_src"]), cv_golden["lab_dst"])
+
+
+def test_border_reflect_matches_cv2(orc, cv_golden):
+    for b in (5, 20):
+        assert np.array_equal(orc.border_reflect(cv_golden["border_src"], b), cv_golden["border_dst_%d" % b])
+
+
+def test_resize_u8_matches_cv2(orc, cv_golden):
+    big = cv_golden["resize_src"]
+    for S in cv_golden["resize_sizes"]:
+        win = np.ascontiguousarray(big[2:2 + S, 3:3 + S])
+        assert np.array_equal(orc.resize_u8c3(win, 11), cv_golden["resize_dst_%d" % S]), S
+        assert np.array_equal(orc.resize_u8c3(win, 5), cv_golden["resize5_dst_%d" % S]), S
+
+
+def test_resize_f32_matches_cv2(orc, cv_golden):
+    for C in (8, 9):
+        src = cv_golden["up_src_%d" % C]
+        assert np.array_equal(orc.resize_f32(src, 32, 24), cv_golden["up_dst_%d" % C])
+        assert np.array_equal(orc.resize_f32(src, 48, 36), cv_golden["up3_dst_%d" % C])
+
+
+def _rows(ref_golden):
+    return np.concatenate([ref_golden["rf_rows_color"].astype(np.float32), ref_golden["rf_rows_tail"]], axis=1)
+
+
+def test_forest_matches_reference_golden(orc, ref_golden):
+    f = orc.Forest(FOREST)
+    assert (f.T, f.L, f.classes) == (4, 2, [8, 9])
+    leaf, post = f.predict(_rows(ref_golden))
+    assert np.array_equal(leaf, ref_golden["rf_leaf"])
+    assert np.array_equal(post, ref_golden["rf_post"])  # bit-exact: same add order t=0..3
+
+
+@pytest.mark.parametrize("name", ["d6", "d5", "d3", "d2"])
+def test_lattice_matches_reference_golden(orc, ref_golden, name):
+    feats = ref_golden["lat_%s_feats" % name]
+    lat = orc.Lattice(feats)
+    assert lat.V == int(ref_golden["lat_%s_V" % name])
+    off, bary = lat.get()
+    assert np.array_equal(off, ref_golden["lat_%s_off" % name])  # same first-seen vertex numbering
+    assert np.array_equal(bary, ref_golden["lat_%s_bary" % name])
+    assert np.array_equal(lat.compute(ref_golden["lat_%s_in9" % name]), ref_golden["lat_%s_out9" % name])
+    ones = np.ones((feats.shape[0], 1), np.float32)
+    assert np.array_equal(lat.compute(ones), ref_golden["lat_%s_out1" % name])
+
+
+def test_live_reference_forest_and_lattice(orc):
+    """Where the compiled reference is available, compare on a fresh full-size frame too."""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    from rovinasemanticsegmentation_b200 import synth
+    Kinv, R, t = synth.calibration()
+    rgb, depth = synth.frame(77)
+    feats, xs, ys = orc.extract(orc.default_config(), 4, rgb, depth, Kinv, R, t, 0.5, 15.0)
+    mine, ref = orc.Forest(FOREST), orc.RefForest(FOREST)
+    l0, p0 = mine.predict(feats)
+    l1, p1 = ref.predict(feats, mine.sumC)
+    assert np.array_equal(l0, l1) and np.array_equal(p0, p1)
+    xyz, col = synth.local_map(seed=5, n_points=20001)
+    f6 = orc.features_xyzrgb(xyz, col, 0.5, 4.0)
+    a, b = orc.Lattice(f6), orc.RefLattice(f6)
+    assert a.V == b.V
+    x = np.random.default_rng(0).random((20001, 8), dtype=np.float32)
+    assert np.array_equal(a.compute(x), b.compute(x))
