@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 FOREST = os.path.join(GOLDEN, "forest_shared.dat")
-CONFIG = os.path.join(ROOT, "resources", "config.json")
+CONFIG = os.path.join(ROOT, "resources", "keyframe_config.json")
 
 
 def pytest_configure(config):
