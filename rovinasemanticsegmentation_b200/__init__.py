@@ -1,0 +1,299 @@
+"""B200-native per-keyframe inference path of RovinaSemanticSegmentation.
+
+This package is a thin ctypes binding of ``librss.so`` (hand-written sm_100a CUDA behind the C ABI declared in
+``include/rss.h``).  There is NO CPU fallback: importing works anywhere (so that the library can be built and its
+exported symbols checked on a machine without a GPU), but creating a :class:`Context` without the compiled
+library or without a CUDA device raises.  The package never imports ``oracle`` (the CPU checker).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librss.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "rss.h")
+DEFAULT_CONFIG = os.path.join(os.path.dirname(HERE), "resources", "keyframe_config.json")
+
+WITH_ANY_LABEL, WITH_POSITIVE_LABEL, NO_LABEL = 0, 1, 2
+NO_NORMALIZATION, NORMALIZE_BEFORE, NORMALIZE_AFTER, NORMALIZE_SYMMETRIC = 0, 1, 2, 3
+MAX_LAYERS = 8
+
+
+class RssError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("rss status %d: %s" % (status, message))
+        self.status = status
+
+
+class Info(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("feature_color_patch", "feature_depth", "feature_height", "feature_normal",
+                                        "patch_size", "patch_size_reduce", "feature_length", "num_trees", "total_nodes",
+                                        "total_leaves", "layer_count")] +
+                [("class_counts", C.c_int * MAX_LAYERS), ("total_classes", C.c_int),
+                 ("unknown_label", C.c_int * MAX_LAYERS), ("use_dense_crf", C.c_int), ("dcrf_iterations", C.c_int),
+                 ("rf_prediction_stride", C.c_int), ("dcrf_xyz_kernel", C.c_float), ("dcrf_rgb_kernel", C.c_float),
+                 ("dcrf_kernel_weight", C.c_float), ("depth_min", C.c_float), ("depth_max", C.c_float),
+                 ("cuda_device", C.c_int), ("sm_count", C.c_int)])
+
+
+class KeyframeParams(C.Structure):
+    _fields_ = [("sigma_xyz", C.c_float), ("w_gauss", C.c_float), ("sigma_px", C.c_float), ("sigma_rgb", C.c_float),
+                ("w_bilateral", C.c_float), ("iters", C.c_int), ("fill", C.c_float)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d_ms", "features_ms", "forest_ms", "upsample_ms", "lattice_ms",
+                                         "meanfield_ms", "d2h_ms", "total_ms")]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads librss.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RssError(-1, "librss.so is not built (run `python -m rovinasemanticsegmentation_b200.build`); "
+                               "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.rss_last_error.restype = C.c_char_p
+        L.rss_last_error.argtypes = [C.c_void_p]
+        L.rss_status_string.restype = C.c_char_p
+        L.rss_kernel_launches.restype = C.c_uint64
+        L.rss_kernel_launches.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _calib(Kinv, R, t):
+    return (np.ascontiguousarray(Kinv, np.float32).reshape(9), np.ascontiguousarray(R, np.float32).reshape(9),
+            np.ascontiguousarray(t, np.float32).reshape(3))
+
+
+class Context:
+    """One GPU context = the reference Segmenter's constructor state (config + forest), see rss_create."""
+
+    def __init__(self, config_path=DEFAULT_CONFIG, forest_path=None, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        st = self._lib.rss_create(config_path.encode(), forest_path.encode() if forest_path else None, int(device),
+                                  C.byref(h))
+        if st != 0:
+            raise RssError(st, self._lib.rss_last_error(None).decode())
+        self.h = h
+        self.info = Info()
+        self._check(self._lib.rss_get_info(self.h, C.byref(self.info)))
+        self.D = self.info.feature_length
+        self.classes = list(self.info.class_counts[:self.info.layer_count])
+        self.sumC = self.info.total_classes
+
+    def _check(self, st):
+        if st != 0:
+            raise RssError(st, self._lib.rss_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.rss_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.rss_kernel_launches(self.h))
+
+    def timings(self):
+        t = Timings()
+        self._check(self._lib.rss_get_timings(self.h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in Timings._fields_}
+
+    # ---- FeatureExtractor::extract
+    def extract_features(self, rgb, depth, Kinv, R, t, stride, dmin, dmax, extract_type=NO_LABEL, labels=None,
+                         want_feats=True):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        Kinv, R, t = _calib(Kinv, R, t)
+        cap = (-(-W // stride)) * (-(-H // stride))
+        feats = np.empty((cap, self.D), np.float32) if want_feats else None
+        xs = np.empty(cap, np.int32)
+        ys = np.empty(cap, np.int32)
+        nl, lab, out_lab = 0, None, None
+        if labels is not None:
+            lab = np.ascontiguousarray(labels, np.int8)
+            nl = lab.shape[0]
+            out_lab = np.empty((cap, nl), np.int32)
+        n = C.c_int(0)
+        self._check(self._lib.rss_extract_features(
+            self.h, _ptr(rgb, C.c_uint8), _ptr(depth, C.c_uint16), W, H, int(stride), _ptr(Kinv, C.c_float),
+            _ptr(R, C.c_float), _ptr(t, C.c_float), C.c_float(dmin), C.c_float(dmax), int(extract_type),
+            _ptr(lab, C.c_int8), nl, _ptr(feats, C.c_float), _ptr(xs, C.c_int32), _ptr(ys, C.c_int32),
+            _ptr(out_lab, C.c_int32), C.byref(n)))
+        n = n.value
+        out = [feats[:n] if want_feats else None, xs[:n], ys[:n]]
+        if out_lab is not None:
+            out.append(out_lab[:n])
+        return tuple(out)
+
+    def frame_intermediates(self, W, H, lab=True, xyz=True, normals=True):
+        P = self.info.patch_size
+        a = np.empty((H + 2 * P, W + 2 * P, 3), np.uint8) if lab else None
+        b = np.empty((H, W, 3), np.float32) if xyz else None
+        c = np.empty((H, W, 3), np.float32) if normals else None
+        self._check(self._lib.rss_frame_intermediates(self.h, _ptr(a, C.c_uint8), _ptr(b, C.c_float), _ptr(c, C.c_float)))
+        return a, b, c
+
+    # ---- RandomForest::multiClassLogPosterior
+    def forest_predict(self, feats=None, n=None):
+        if feats is not None:
+            feats = np.ascontiguousarray(feats, np.float32)
+            n = feats.shape[0]
+            assert feats.shape[1] == self.D
+        T = self.info.num_trees
+        leaf = np.empty((T, n), np.int32)
+        post = np.empty((n, self.sumC), np.float32)
+        self._check(self._lib.rss_forest_predict(self.h, _ptr(feats, C.c_float), int(n), _ptr(leaf, C.c_int32),
+                                                 _ptr(post, C.c_float)))
+        return leaf, post
+
+    # ---- Segmenter::processFramesFromQueueInternalRF body
+    def segment_frame(self, rgb, depth, Kinv, R, t, fill=0.0, want_host=True):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        Kinv, R, t = _calib(Kinv, R, t)
+        out = np.empty(self.sumC * H * W, np.float32) if want_host else None
+        self._check(self._lib.rss_segment_frame(self.h, _ptr(rgb, C.c_uint8), _ptr(depth, C.c_uint16), W, H,
+                                                _ptr(Kinv, C.c_float), _ptr(R, C.c_float), _ptr(t, C.c_float),
+                                                C.c_float(fill), _ptr(out, C.c_float)))
+        return out
+
+    def segment_keyframe(self, rgb, depth, Kinv, R, t, params, W=None, H=None, want_Q=False, want_labels=True):
+        """rgb/depth may be None to reuse the frame already resident on the device (then pass W, H)."""
+        if rgb is not None:
+            rgb = np.ascontiguousarray(rgb, np.uint8)
+            depth = np.ascontiguousarray(depth, np.uint16)
+            H, W = depth.shape
+        Kinv, R, t = _calib(Kinv, R, t)
+        L = self.info.layer_count
+        labels = np.empty((L, H * W), np.uint8) if want_labels else None
+        Q = np.empty(self.sumC * H * W, np.float32) if want_Q else None
+        self._check(self._lib.rss_segment_keyframe(self.h, _ptr(rgb, C.c_uint8), _ptr(depth, C.c_uint16), W, H,
+                                                   _ptr(Kinv, C.c_float), _ptr(R, C.c_float), _ptr(t, C.c_float),
+                                                   C.byref(params), _ptr(labels, C.c_uint8), _ptr(Q, C.c_float)))
+        return (labels, Q) if want_Q else labels
+
+    def crf(self, N, M):
+        return DenseCRF(self, N, M)
+
+
+class DenseCRF:
+    """DenseCRF (third-party/densecrf/include/densecrf.h) on the device.  M: int or list of per-layer label counts.
+    Matrices use the reference's column-major convention: a numpy array of shape (N, M)."""
+
+    def __init__(self, ctx, N, M):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self.N = int(N)
+        self.M = [int(M)] if np.isscalar(M) else [int(m) for m in M]
+        h = C.c_void_p()
+        arr = (C.c_int * len(self.M))(*self.M)
+        ctx._check(self._lib.rss_crf_create_layers(ctx.h, self.N, len(self.M), arr, C.byref(h)))
+        self.h = h
+        self.n_kernels = 0
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self._lib.rss_crf_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def set_unary(self, U, layer=0):
+        U = np.ascontiguousarray(U, np.float32)
+        assert U.shape == (self.N, self.M[layer])
+        self.ctx._check(self._lib.rss_crf_set_unary(self.h, layer, _ptr(U, C.c_float)))
+
+    def add_pairwise(self, feats, potts_w, norm_type=NORMALIZE_SYMMETRIC):
+        feats = np.ascontiguousarray(feats, np.float32)
+        assert feats.shape[0] == self.N
+        self.ctx._check(self._lib.rss_crf_add_pairwise(self.h, _ptr(feats, C.c_float), feats.shape[1],
+                                                       C.c_float(potts_w), int(norm_type)))
+        self.n_kernels += 1
+
+    def add_pairwise_gaussian(self, W, H, sx, sy, potts_w):
+        self.ctx._check(self._lib.rss_crf_add_pairwise_gaussian(self.h, W, H, C.c_float(sx), C.c_float(sy),
+                                                                C.c_float(potts_w)))
+        self.n_kernels += 1
+
+    def add_pairwise_bilateral(self, W, H, sx, sy, sr, sg, sb, im, potts_w):
+        im = np.ascontiguousarray(im, np.uint8)
+        self.ctx._check(self._lib.rss_crf_add_pairwise_bilateral(self.h, W, H, C.c_float(sx), C.c_float(sy),
+                                                                 C.c_float(sr), C.c_float(sg), C.c_float(sb),
+                                                                 _ptr(im, C.c_uint8), C.c_float(potts_w)))
+        self.n_kernels += 1
+
+    def add_pairwise_xyzrgb(self, xyz, rgb, wxyz, wrgb, potts_w):
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        self.ctx._check(self._lib.rss_crf_add_pairwise_xyzrgb(self.h, _ptr(xyz, C.c_float), _ptr(rgb, C.c_float),
+                                                              C.c_float(wxyz), C.c_float(wrgb), C.c_float(potts_w)))
+        self.n_kernels += 1
+
+    def lattice_size(self, k=0):
+        v = C.c_int(0)
+        self.ctx._check(self._lib.rss_crf_lattice_size(self.h, k, C.byref(v)))
+        return v.value
+
+    def filter(self, x, k=0):
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.shape == (self.N, sum(self.M))
+        out = np.empty_like(x)
+        self.ctx._check(self._lib.rss_crf_filter(self.h, k, _ptr(x, C.c_float), _ptr(out, C.c_float)))
+        return out
+
+    def inference(self, iters, layer=-1, unknown=None, want_Q=True, want_labels=False):
+        nl = len(self.M)
+        if layer < 0:
+            Q = [np.empty((self.N, m), np.float32) for m in self.M] if want_Q else None
+            Qbuf = np.empty(self.N * sum(self.M), np.float32) if want_Q else None
+            lab = np.empty((nl, self.N), np.uint8) if want_labels else None
+        else:
+            Qbuf = np.empty((self.N, self.M[layer]), np.float32) if want_Q else None
+            lab = np.empty(self.N, np.uint8) if want_labels else None
+        unk = None
+        if unknown is not None:
+            u = [unknown] if np.isscalar(unknown) else list(unknown)
+            unk = (C.c_int * len(u))(*u)
+        self.ctx._check(self._lib.rss_crf_inference(self.h, int(layer), int(iters), _ptr(Qbuf, C.c_float),
+                                                    _ptr(lab, C.c_uint8), unk))
+        if want_Q and layer < 0:
+            o = 0
+            for l, m in enumerate(self.M):
+                Q[l] = Qbuf[o:o + self.N * m].reshape(self.N, m)
+                o += self.N * m
+            Qbuf = Q[0] if nl == 1 else Q
+        if want_Q and want_labels:
+            return Qbuf, lab
+        return Qbuf if want_Q else lab
+
+    def unary_reset(self):
+        self.ctx._check(self._lib.rss_crf_unary_reset(self.h))
+
+    def unary_accumulate(self, index_image, posteriors=None):
+        idx = np.ascontiguousarray(index_image, np.int32).reshape(-1)
+        post = np.ascontiguousarray(posteriors, np.float32) if posteriors is not None else None
+        self.ctx._check(self._lib.rss_crf_unary_accumulate(self.h, self.ctx.h, _ptr(idx, C.c_int32), idx.size,
+                                                           _ptr(post, C.c_float)))

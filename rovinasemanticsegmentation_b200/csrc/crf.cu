@@ -1,0 +1,693 @@
+// DenseCRF mean-field inference on the device and the C ABI for it (include/rss.h, part 2).
+// Reference: third-party/densecrf/src/densecrf.cpp:98-131 (expAndNormalize, inference),
+// pairwise.cpp:40-80,173-178 (DenseKernel::initLattice/filter, PairwisePotential::apply),
+// labelcompatibility.cpp:46-48 (Potts), src/segmenter.cpp:561-657 (unary accumulation, gated argmax).
+//
+// All label layers of a CRF share every lattice: the channels of the layers are concatenated per point
+// ([N][Mtot]) and filtered together (the filter is channel-independent); the soft-max runs per layer.
+// One mean-field iteration = per lattice {zero, splat, d+1 blurs} on its own stream, then ONE fused
+// point-parallel kernel: slice of every lattice + post-scale by norm + Potts + unary + per-layer soft-max
+// (+ the gated argmax on the last iteration).  Q never leaves the device between iterations.
+#include <cmath>
+#include <cstring>
+
+#include "kernels.hpp"
+#include "lattice.cuh"
+
+namespace rss {
+float lattice_alpha(int d);
+rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp);
+float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
+                          int M, int Mp);
+void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
+                   int out_stride);
+rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch);
+
+constexpr int CRF_MAX_KERNELS = 4;
+constexpr int CRF_MAX_CH = 32;
+
+struct LayerSpec {
+    int n_layers;
+    int off[RSS_MAX_LAYERS + 1];
+    int unknown[RSS_MAX_LAYERS];  // < 0: plain argmax
+};
+struct SliceArgs {
+    int K;
+    const int* offsets[CRF_MAX_KERNELS];
+    const float* bary[CRF_MAX_KERNELS];
+    const float* values[CRF_MAX_KERNELS];
+    const float* norm[CRF_MAX_KERNELS];
+    const uint32_t* counts[CRF_MAX_KERNELS];
+    int d1[CRF_MAX_KERNELS];
+    float alpha[CRF_MAX_KERNELS];
+    float potts[CRF_MAX_KERNELS];
+};
+
+// expAndNormalize (densecrf.cpp:98-106) on one layer segment held in registers
+template <int MP>
+__device__ __forceinline__ void softmax_layers(float (&t)[MP], const LayerSpec& ls) {
+    for (int l = 0; l < ls.n_layers; l++) {
+        const int a = ls.off[l], b = ls.off[l + 1];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < MP; c++)
+            if (c >= a && c < b) mx = fmaxf(mx, t[c]);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < MP; c++)
+            if (c >= a && c < b) {
+                t[c] = expf(__fsub_rn(t[c], mx));
+                s = __fadd_rn(s, t[c]);
+            }
+#pragma unroll
+        for (int c = 0; c < MP; c++)
+            if (c >= a && c < b) t[c] = __fdiv_rn(t[c], s);
+    }
+}
+
+// Q0 = expAndNormalize(-unary)   (densecrf.cpp:120)
+template <int MP>
+__global__ void __launch_bounds__(256) softmax_init_kernel(const float* __restrict__ unary, int N, int M, LayerSpec ls,
+                                                           float* __restrict__ Q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float t[MP];
+#pragma unroll
+    for (int c = 0; c < MP; c++) t[c] = c < M ? -unary[(size_t)i * M + c] : 0.f;
+    softmax_layers<MP>(t, ls);
+#pragma unroll
+    for (int c = 0; c < MP; c++)
+        if (c < M) Q[(size_t)i * M + c] = t[c];
+}
+
+// gated argmax (segmenter.cpp:645-657) or plain argmax (DenseCRF::currentMap, densecrf.cpp:200-208)
+template <int MP>
+__device__ __forceinline__ void write_labels(const float (&q)[MP], const LayerSpec& ls, int i, int N,
+                                             uint8_t* __restrict__ labels) {
+    for (int l = 0; l < ls.n_layers; l++) {
+        const int a = ls.off[l], b = ls.off[l + 1];
+        int best;
+        float bv;
+        if (ls.unknown[l] >= 0) {
+            best = ls.unknown[l];
+            bv = (float)(2.0 / (double)(b - a));
+        } else {
+            best = 0;
+            bv = -INFINITY;
+        }
+#pragma unroll
+        for (int c = 0; c < MP; c++)
+            if (c >= a && c < b && q[c] > bv) {
+                bv = q[c];
+                best = c - a;
+            }
+        labels[(size_t)l * N + i] = (uint8_t)best;
+    }
+}
+
+// One mean-field update for point i (densecrf.cpp:123-128):
+//   tmp = -unary;  for each kernel: tmp -= -w * ((slice(values) ) * norm);  Q = expAndNormalize(tmp)
+template <int MP>
+__global__ void __launch_bounds__(128) slice_softmax_kernel(SliceArgs sa, const float* __restrict__ unary, int N, int M,
+                                                            int Mp, LayerSpec ls, float* __restrict__ Q,
+                                                            uint8_t* __restrict__ labels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float t[MP];
+#pragma unroll
+    for (int c = 0; c < MP; c++) t[c] = c < M ? -unary[(size_t)i * M + c] : 0.f;
+    for (int k = 0; k < sa.K; k++) {
+        if (sa.counts[k][1]) return;  // lattice overflow: the host re-runs with a larger table
+        float acc[MP];
+#pragma unroll
+        for (int c = 0; c < MP; c++) acc[c] = 0.f;
+        const int d1 = sa.d1[k];
+        const float alpha = sa.alpha[k];
+        for (int j = 0; j < d1; j++) {
+            const int v = __ldg(sa.offsets[k] + (size_t)i * d1 + j);
+            const float w = __fmul_rn(__ldg(sa.bary[k] + (size_t)i * d1 + j), alpha);
+            const float4* row = reinterpret_cast<const float4*>(sa.values[k] + (size_t)v * Mp);
+#pragma unroll
+            for (int g = 0; g < MP / 4; g++)
+                if (4 * g < M) {
+                    const float4 x = __ldg(row + g);
+                    acc[4 * g + 0] = __fadd_rn(acc[4 * g + 0], __fmul_rn(w, x.x));
+                    acc[4 * g + 1] = __fadd_rn(acc[4 * g + 1], __fmul_rn(w, x.y));
+                    acc[4 * g + 2] = __fadd_rn(acc[4 * g + 2], __fmul_rn(w, x.z));
+                    acc[4 * g + 3] = __fadd_rn(acc[4 * g + 3], __fmul_rn(w, x.w));
+                }
+        }
+        const float nv = sa.norm[k] ? sa.norm[k][i] : 1.f, negw = -sa.potts[k];
+#pragma unroll
+        for (int c = 0; c < MP; c++) {
+            const float o = __fmul_rn(negw, __fmul_rn(acc[c], nv));  // pairwise.cpp:78-79, labelcompatibility.cpp:46-48
+            t[c] = __fsub_rn(t[c], o);                               // densecrf.cpp:126
+        }
+    }
+    softmax_layers<MP>(t, ls);
+#pragma unroll
+    for (int c = 0; c < MP; c++)
+        if (c < M) Q[(size_t)i * M + c] = t[c];
+    if (labels) write_labels<MP>(t, ls, i, N, labels);
+}
+
+template <int MP>
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ Q, int N, int M, LayerSpec ls,
+                                                     uint8_t* __restrict__ labels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float q[MP];
+#pragma unroll
+    for (int c = 0; c < MP; c++) q[c] = c < M ? Q[(size_t)i * M + c] : 0.f;
+    write_labels<MP>(q, ls, i, N, labels);
+}
+
+// layout helpers between the reference's per-layer matrices ([N][M_l]) and the interleaved device layout ([N][Mtot])
+__global__ void __launch_bounds__(256) interleave_kernel(const float* __restrict__ src, int N, int Ml, int Mtot, int off,
+                                                         float scale, float* __restrict__ dst) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)N * Ml) return;
+    const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
+    dst[(size_t)i * Mtot + off + c] = scale * src[gid];
+}
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int N, int Ml, int Mtot, int off,
+                                                           float* __restrict__ dst) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)N * Ml) return;
+    const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
+    dst[gid] = src[(size_t)i * Mtot + off + c];
+}
+// segmenter.cpp:597-616: unaries(c, idx) += posterior[pixel*C + c] for idx >= 0.  The CRF stores ENERGIES
+// (= -unaries, segmenter.cpp:642), so the log-posterior is subtracted.
+__global__ void __launch_bounds__(256) unary_accumulate_kernel(const int* __restrict__ index_image, int npix,
+                                                               const float* __restrict__ post, int Ml, int Mtot, int off,
+                                                               int N, float* __restrict__ unary) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)npix * Ml) return;
+    const int p = (int)(gid / Ml), c = (int)(gid - (long long)p * Ml);
+    const int idx = index_image[p];
+    if (idx < 0 || idx >= N) return;
+    atomicAdd(unary + (size_t)idx * Mtot + off + c, -post[gid]);
+}
+// feature builders: DenseCRF2D::addPairwiseGaussian / Bilateral (densecrf.cpp:61-81), segmenter.cpp:629-637
+__global__ void __launch_bounds__(256) feat_gaussian_kernel(int W, int H, float sx, float sy, float* __restrict__ f) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int i = p % W, j = p / W;
+    f[2 * (size_t)p] = __fdiv_rn((float)i, sx);
+    f[2 * (size_t)p + 1] = __fdiv_rn((float)j, sy);
+}
+__global__ void __launch_bounds__(256) feat_bilateral_kernel(int W, int H, float sx, float sy, float sr, float sg, float sb,
+                                                             const uint8_t* __restrict__ im, float* __restrict__ f) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int i = p % W, j = p / W;
+    f[5 * (size_t)p] = __fdiv_rn((float)i, sx);
+    f[5 * (size_t)p + 1] = __fdiv_rn((float)j, sy);
+    f[5 * (size_t)p + 2] = __fdiv_rn((float)im[3 * (size_t)p], sr);
+    f[5 * (size_t)p + 3] = __fdiv_rn((float)im[3 * (size_t)p + 1], sg);
+    f[5 * (size_t)p + 4] = __fdiv_rn((float)im[3 * (size_t)p + 2], sb);
+}
+__global__ void __launch_bounds__(256) feat_xyzrgb_kernel(int N, const float* __restrict__ xyz, const float* __restrict__ rgb,
+                                                          float wxyz, float wrgb, float* __restrict__ f) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        f[6 * (size_t)p + k] = __fmul_rn(xyz[3 * (size_t)p + k], wxyz);
+        f[6 * (size_t)p + 3 + k] = __fmul_rn(rgb[3 * (size_t)p + k], wrgb);
+    }
+}
+// keyframe features from the frame's own buffers: back-projected points / sigma (invalid depth -> NaN is replaced
+// by the camera centre, i.e. depth 0), and (x, y, r, g, b) / sigma
+__global__ void __launch_bounds__(256) feat_frame_xyz_kernel(int N, const float4* __restrict__ xyz, float inv_sigma,
+                                                             float tx, float ty, float tz, float* __restrict__ f) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    float4 v = xyz[p];
+    if (isnan(v.x)) { v.x = tx; v.y = ty; v.z = tz; }
+    f[3 * (size_t)p] = __fmul_rn(v.x, inv_sigma);
+    f[3 * (size_t)p + 1] = __fmul_rn(v.y, inv_sigma);
+    f[3 * (size_t)p + 2] = __fmul_rn(v.z, inv_sigma);
+}
+// posteriors [layer][pixel][C_l] -> energies [pixel][Mtot] = -posterior (segmenter.cpp:642)
+__global__ void __launch_bounds__(256) unary_from_posteriors_kernel(const float* __restrict__ post, int N, int Mtot,
+                                                                    LayerSpec ls, float* __restrict__ unary) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)N * Mtot) return;
+    const int i = (int)(gid / Mtot), c = (int)(gid - (long long)i * Mtot);
+    int l = 0;
+    while (l + 1 < ls.n_layers && c >= ls.off[l + 1]) l++;
+    const int Ml = ls.off[l + 1] - ls.off[l];
+    unary[gid] = -post[(size_t)N * ls.off[l] + (size_t)i * Ml + (c - ls.off[l])];
+}
+
+template <template <int> class Launcher, typename... Args>
+static void dispatch_mp(int Mp, Args... args) {
+    switch (Mp) {
+        case 4: Launcher<4>::run(args...); break;
+        case 8: Launcher<8>::run(args...); break;
+        case 12: Launcher<12>::run(args...); break;
+        case 16: Launcher<16>::run(args...); break;
+        case 20: Launcher<20>::run(args...); break;
+        case 24: Launcher<24>::run(args...); break;
+        case 28: Launcher<28>::run(args...); break;
+        default: Launcher<32>::run(args...); break;
+    }
+}
+template <int MP> struct InitL {
+    static void run(rss_ctx* c, cudaStream_t st, const float* unary, int N, int M, LayerSpec ls, float* Q) {
+        RSS_LAUNCH(c, softmax_init_kernel<MP>, rss_div_up(N, 256), 256, 0, st, unary, N, M, ls, Q);
+    }
+};
+template <int MP> struct SliceL {
+    static void run(rss_ctx* c, cudaStream_t st, SliceArgs sa, const float* unary, int N, int M, int Mp, LayerSpec ls,
+                    float* Q, uint8_t* labels) {
+        RSS_LAUNCH(c, slice_softmax_kernel<MP>, rss_div_up(N, 128), 128, 0, st, sa, unary, N, M, Mp, ls, Q, labels);
+    }
+};
+template <int MP> struct ArgmaxL {
+    static void run(rss_ctx* c, cudaStream_t st, const float* Q, int N, int M, LayerSpec ls, uint8_t* labels) {
+        RSS_LAUNCH(c, argmax_kernel<MP>, rss_div_up(N, 256), 256, 0, st, Q, N, M, ls, labels);
+    }
+};
+
+static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
+    LayerSpec ls;
+    ls.n_layers = crf->n_layers;
+    for (int l = 0; l <= RSS_MAX_LAYERS; l++) ls.off[l] = l <= crf->n_layers ? crf->moff[l] : crf->Mtot;
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) ls.unknown[l] = (unknown && l < crf->n_layers) ? unknown[l] : -1;
+    return ls;
+}
+
+// the mean-field loop, fully enqueued (no host synchronisation).  labels_dev may be NULL.
+rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_dev) {
+    rss_ctx* ctx = crf->ctx;
+    cudaStream_t s0 = ctx->s0;
+    const int N = crf->N, M = crf->Mtot, Mp = crf->Mp, K = (int)crf->kernels.size();
+    const LayerSpec ls = make_layers(crf, unknown);
+    float* Q = crf->Q.as<float>();
+    const float* U = crf->unary.as<float>();
+    dispatch_mp<InitL>(Mp, ctx, s0, U, N, M, ls, Q);
+    if (iters <= 0 || K == 0) {
+        if (iters > 0) {  // no pairwise terms: every iteration reproduces expAndNormalize(-unary)
+        }
+        if (labels_dev) dispatch_mp<ArgmaxL>(Mp, ctx, s0, (const float*)Q, N, M, ls, labels_dev);
+        RSS_CU(ctx, cudaGetLastError());
+        return RSS_OK;
+    }
+    for (int it = 0; it < iters; it++) {
+        SliceArgs sa;
+        sa.K = K;
+        RSS_CU(ctx, cudaEventRecord(crf->ev_fork, s0));
+        for (int k = 0; k < K; k++) {
+            Lattice& L = *crf->kernels[k];
+            cudaStream_t sk = K > 1 ? crf->side[k] : s0;
+            if (K > 1) RSS_CU(ctx, cudaStreamWaitEvent(sk, crf->ev_fork, 0));
+            const bool pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
+            const bool post = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_AFTER;
+            float* vals = lattice_splat_blur(ctx, sk, L, Q, M, pre ? L.norm.as<float>() : nullptr, M, Mp);
+            if (K > 1) RSS_CU(ctx, cudaEventRecord(crf->ev_join[k], sk));
+            sa.offsets[k] = L.offsets.as<int>();
+            sa.bary[k] = L.bary.as<float>();
+            sa.values[k] = vals;
+            sa.norm[k] = post ? L.norm.as<float>() : nullptr;
+            sa.counts[k] = L.counts.as<uint32_t>();
+            sa.d1[k] = L.d + 1;
+            sa.alpha[k] = lattice_alpha(L.d);
+            sa.potts[k] = L.potts_w;
+        }
+        if (K > 1)
+            for (int k = 0; k < K; k++) RSS_CU(ctx, cudaStreamWaitEvent(s0, crf->ev_join[k], 0));
+        dispatch_mp<SliceL>(Mp, ctx, s0, sa, U, N, M, Mp, ls, Q, (it == iters - 1) ? labels_dev : (uint8_t*)nullptr);
+    }
+    RSS_CU(ctx, cudaGetLastError());
+    return RSS_OK;
+}
+
+static uint32_t next_pow2(uint64_t v) {
+    uint32_t p = 1;
+    while ((uint64_t)p < v && p < (1u << 30)) p <<= 1;
+    return p;
+}
+
+// builds lattice k from device-resident features; synchronises to detect overflow and grows the table
+rss_status crf_add_kernel_dev(rss_crf* crf, const float* feat_dev, int d, float potts_w, int norm_type, bool sync) {
+    rss_ctx* ctx = crf->ctx;
+    if ((int)crf->kernels.size() >= CRF_MAX_KERNELS) return ctx->fail(RSS_ERR_INVALID, "too many pairwise terms (max 4)");
+    if (norm_type < RSS_NORMALIZE_BEFORE || norm_type > RSS_NORMALIZE_SYMMETRIC)
+        return ctx->fail(RSS_ERR_INVALID, "unsupported normalization type");
+    Lattice* L;
+    if (!crf->pool.empty()) {  // rebuild in place: buffers (and the capacity that worked last time) are reused
+        L = crf->pool.back();
+        crf->pool.pop_back();
+    } else {
+        L = new Lattice();
+    }
+    L->potts_w = potts_w;
+    L->norm_type = norm_type;
+    crf->kernels.push_back(L);
+    const uint64_t maxv = (uint64_t)crf->N * (d + 1);
+    uint32_t hcap = next_pow2(std::min<uint64_t>(2 * maxv, 1u << 17));
+    if (L->hcap > hcap && L->d == d) hcap = L->hcap;
+    RSS_CU(ctx, crf->scratch.reserve((size_t)crf->N * crf->Mp * 4));
+    for (;;) {
+        rss_status st = lattice_build(ctx, ctx->s0, *L, feat_dev, crf->N, d, hcap, crf->Mp);
+        if (st != RSS_OK) return st;
+        st = lattice_normalization(ctx, ctx->s0, *L, crf->scratch.as<float>());
+        if (st != RSS_OK) return st;
+        if (!sync) return RSS_OK;
+        uint32_t h[8];
+        RSS_CU(ctx, cudaMemcpyAsync(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->s0));
+        RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+        if (!h[1]) {
+            L->V_host = (int)h[0];
+            return RSS_OK;
+        }
+        if ((uint64_t)hcap >= 2 * next_pow2(2 * maxv) || hcap >= (1u << 30))
+            return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
+        hcap *= 4;
+    }
+}
+
+void crf_free(rss_crf* crf) {
+    if (!crf) return;
+    for (Lattice* L : crf->kernels) { L->release(); delete L; }
+    for (Lattice* L : crf->pool) { L->release(); delete L; }
+    crf->kernels.clear();
+    crf->pool.clear();
+    crf->unary.release(); crf->Q.release(); crf->scratch.release(); crf->labels.release(); crf->feat_stage.release();
+    for (int k = 0; k < 4; k++) {
+        if (crf->side[k]) cudaStreamDestroy(crf->side[k]);
+        if (crf->ev_join[k]) cudaEventDestroy(crf->ev_join[k]);
+    }
+    if (crf->ev_fork) cudaEventDestroy(crf->ev_fork);
+    delete crf;
+}
+void crf_release_cached(rss_ctx* ctx) {
+    if (ctx->keyframe_crf) crf_free(ctx->keyframe_crf);
+    ctx->keyframe_crf = nullptr;
+}
+
+rss_status crf_new(rss_ctx* ctx, int N, int n_layers, const int* M, rss_crf** out) {
+    if (!ctx || !out) return RSS_ERR_INVALID;
+    if (N < 1 || n_layers < 1 || n_layers > RSS_MAX_LAYERS || !M) return ctx->fail(RSS_ERR_INVALID, "bad CRF dimensions");
+    rss_crf* crf = new rss_crf();
+    crf->ctx = ctx; crf->N = N; crf->n_layers = n_layers;
+    int off = 0;
+    for (int l = 0; l < n_layers; l++) {
+        if (M[l] < 1) { delete crf; return ctx->fail(RSS_ERR_INVALID, "layer with no labels"); }
+        crf->M[l] = M[l];
+        crf->moff[l] = off;
+        off += M[l];
+    }
+    for (int l = n_layers; l <= RSS_MAX_LAYERS; l++) crf->moff[l] = off;
+    crf->Mtot = off;
+    crf->Mp = (off + 3) / 4 * 4;
+    if (crf->Mp > CRF_MAX_CH) { delete crf; return ctx->fail(RSS_ERR_INVALID, "more than 32 labels in total are not supported"); }
+    cudaError_t e = crf->unary.reserve((size_t)N * off * 4);
+    if (e == cudaSuccess) e = crf->Q.reserve((size_t)N * off * 4);
+    if (e == cudaSuccess) e = crf->labels.reserve((size_t)N * n_layers);
+    if (e == cudaSuccess) e = crf->scratch.reserve((size_t)N * crf->Mp * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(crf->unary.ptr, 0, (size_t)N * off * 4, ctx->s0);
+    for (int k = 0; k < 4 && e == cudaSuccess; k++) {
+        e = cudaStreamCreateWithFlags(&crf->side[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&crf->ev_join[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&crf->ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        crf_free(crf);
+        return ctx->fail(RSS_ERR_CUDA, std::string("CRF allocation: ") + cudaGetErrorString(e));
+    }
+    *out = crf;
+    return RSS_OK;
+}
+
+}  // namespace rss
+
+using namespace rss;
+
+extern "C" rss_status rss_crf_create_layers(rss_ctx* ctx, int N, int n_layers, const int* M, rss_crf** out) {
+    if (!ctx) return RSS_ERR_INVALID;
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    return crf_new(ctx, N, n_layers, M, out);
+}
+extern "C" rss_status rss_crf_create(rss_ctx* ctx, int N, int M, rss_crf** out) { return rss_crf_create_layers(ctx, N, 1, &M, out); }
+
+extern "C" rss_status rss_crf_destroy(rss_crf* crf) {
+    if (!crf) return RSS_ERR_INVALID;
+    cudaSetDevice(crf->ctx->device);
+    cudaStreamSynchronize(crf->ctx->s0);
+    crf_free(crf);
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_set_unary(rss_crf* crf, int layer, const float* U) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (layer < 0 || layer >= crf->n_layers || !U) return ctx->fail(RSS_ERR_INVALID, "bad layer or null unary");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    const int Ml = crf->M[layer];
+    RSS_CU(ctx, cudaMemcpyAsync(crf->scratch.ptr, U, (size_t)crf->N * Ml * 4, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)crf->N * Ml, 256), 256, 0, ctx->s0, crf->scratch.as<float>(),
+               crf->N, Ml, crf->Mtot, crf->moff[layer], 1.0f, crf->unary.as<float>());
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    crf->unary_set = true;
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_add_pairwise(rss_crf* crf, const float* feats, int d, float potts_w, int norm_type) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (!feats || d < 1 || d > LAT_MAX_D) return ctx->fail(RSS_ERR_INVALID, "null features or dimension outside [1, 7]");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * d * 4));
+    RSS_CU(ctx, cudaMemcpyAsync(crf->feat_stage.ptr, feats, (size_t)crf->N * d * 4, cudaMemcpyHostToDevice, ctx->s0));
+    return crf_add_kernel_dev(crf, crf->feat_stage.as<float>(), d, potts_w, norm_type, true);
+}
+
+extern "C" rss_status rss_crf_add_pairwise_gaussian(rss_crf* crf, int W, int H, float sx, float sy, float potts_w) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if ((long long)W * H != crf->N) return ctx->fail(RSS_ERR_INVALID, "W*H must equal the CRF's point count");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * 2 * 4));
+    RSS_LAUNCH(ctx, feat_gaussian_kernel, rss_div_up(crf->N, 256), 256, 0, ctx->s0, W, H, sx, sy, crf->feat_stage.as<float>());
+    return crf_add_kernel_dev(crf, crf->feat_stage.as<float>(), 2, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
+}
+
+extern "C" rss_status rss_crf_add_pairwise_bilateral(rss_crf* crf, int W, int H, float sx, float sy, float sr, float sg,
+                                                     float sb, const uint8_t* im, float potts_w) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if ((long long)W * H != crf->N || !im) return ctx->fail(RSS_ERR_INVALID, "W*H must equal the CRF's point count; image required");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * 5 * 4));
+    uint8_t* im_dev = reinterpret_cast<uint8_t*>(crf->scratch.ptr);  // N*Mp*4 >= N*3 bytes
+    RSS_CU(ctx, cudaMemcpyAsync(im_dev, im, (size_t)crf->N * 3, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(crf->N, 256), 256, 0, ctx->s0, W, H, sx, sy, sr, sg, sb, im_dev,
+               crf->feat_stage.as<float>());
+    return crf_add_kernel_dev(crf, crf->feat_stage.as<float>(), 5, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
+}
+
+extern "C" rss_status rss_crf_add_pairwise_xyzrgb(rss_crf* crf, const float* xyz, const float* rgb, float wxyz, float wrgb,
+                                                  float potts_w) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (!xyz || !rgb) return ctx->fail(RSS_ERR_INVALID, "null point cloud");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = crf->N;
+    RSS_CU(ctx, crf->feat_stage.reserve(N * 12 * 4));
+    float* stage = crf->feat_stage.as<float>();  // [0,6N): features, [6N,9N): xyz, [9N,12N): rgb
+    RSS_CU(ctx, cudaMemcpyAsync(stage + 6 * N, xyz, N * 12, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_CU(ctx, cudaMemcpyAsync(stage + 9 * N, rgb, N * 12, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_LAUNCH(ctx, feat_xyzrgb_kernel, rss_div_up((long long)N, 256), 256, 0, ctx->s0, (int)N, stage + 6 * N, stage + 9 * N,
+               wxyz, wrgb, stage);
+    return crf_add_kernel_dev(crf, stage, 6, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
+}
+
+extern "C" rss_status rss_crf_lattice_size(rss_crf* crf, int k, int* vertices) {
+    if (!crf || !vertices) return RSS_ERR_INVALID;
+    if (k < 0 || k >= (int)crf->kernels.size()) return crf->ctx->fail(RSS_ERR_INVALID, "no such pairwise term");
+    *vertices = crf->kernels[k]->V_host;
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float* out) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (k < 0 || k >= (int)crf->kernels.size() || !in || !out) return ctx->fail(RSS_ERR_INVALID, "bad filter arguments");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    Lattice& L = *crf->kernels[k];
+    const int N = crf->N, M = crf->Mtot, Mp = crf->Mp;
+    float* buf = crf->scratch.as<float>();
+    RSS_CU(ctx, cudaMemcpyAsync(buf, in, (size_t)N * M * 4, cudaMemcpyHostToDevice, ctx->s0));
+    float* vals = lattice_splat_blur(ctx, ctx->s0, L, buf, M, nullptr, M, Mp);
+    lattice_slice(ctx, ctx->s0, L, vals, M, Mp, M <= 2 ? 1 : 0, buf, M);
+    RSS_CU(ctx, cudaMemcpyAsync(out, buf, (size_t)N * M * 4, cudaMemcpyDeviceToHost, ctx->s0));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_inference(rss_crf* crf, int layer, int iters, float* Q, uint8_t* labels,
+                                        const int* unknown_label) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (layer < -1 || layer >= crf->n_layers || iters < 0) return ctx->fail(RSS_ERR_INVALID, "bad layer or iteration count");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    int unk[RSS_MAX_LAYERS];
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = -1;
+    if (unknown_label) {
+        if (layer < 0) for (int l = 0; l < crf->n_layers; l++) unk[l] = unknown_label[l];
+        else unk[layer] = unknown_label[0];
+    }
+    cudaEventRecord(ctx->ev[6], ctx->s0);
+    rss_status st = crf_run(crf, iters, unk, labels ? crf->labels.as<uint8_t>() : nullptr);
+    if (st != RSS_OK) return st;
+    cudaEventRecord(ctx->ev[7], ctx->s0);
+    const int N = crf->N;
+    if (Q) {
+        if (layer < 0 && crf->n_layers == 1) layer = 0;
+        if (layer < 0) {
+            float* dstQ = Q;
+            for (int l = 0; l < crf->n_layers; l++) {
+                RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0,
+                           crf->Q.as<float>(), N, crf->M[l], crf->Mtot, crf->moff[l], crf->scratch.as<float>());
+                RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
+                RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+                dstQ += (size_t)N * crf->M[l];
+            }
+        } else if (crf->n_layers == 1) {
+            RSS_CU(ctx, cudaMemcpyAsync(Q, crf->Q.ptr, (size_t)N * crf->Mtot * 4, cudaMemcpyDeviceToHost, ctx->s0));
+        } else {
+            RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[layer], 256), 256, 0, ctx->s0,
+                       crf->Q.as<float>(), N, crf->M[layer], crf->Mtot, crf->moff[layer], crf->scratch.as<float>());
+            RSS_CU(ctx, cudaMemcpyAsync(Q, crf->scratch.ptr, (size_t)N * crf->M[layer] * 4, cudaMemcpyDeviceToHost, ctx->s0));
+        }
+    }
+    if (labels) {
+        if (layer < 0) RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.ptr, (size_t)N * crf->n_layers, cudaMemcpyDeviceToHost, ctx->s0));
+        else RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.as<uint8_t>() + (size_t)layer * N, (size_t)N, cudaMemcpyDeviceToHost, ctx->s0));
+    }
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+    ctx->tim.meanfield_ms = ms;
+    for (Lattice* L : crf->kernels) {
+        uint32_t h[2];
+        RSS_CU(ctx, cudaMemcpy(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+        if (h[1]) return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
+    }
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_unary_reset(rss_crf* crf) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, cudaMemsetAsync(crf->unary.ptr, 0, (size_t)crf->N * crf->Mtot * 4, ctx->s0));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx, const int32_t* index_image, int npix,
+                                               const float* posteriors) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (!index_image || npix < 1) return ctx->fail(RSS_ERR_INVALID, "null index image");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    const float* post_dev = nullptr;
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)npix * 4 + (posteriors ? (size_t)npix * crf->Mtot * 4 : 0)));
+    int* idx_dev = crf->feat_stage.as<int>();
+    RSS_CU(ctx, cudaMemcpyAsync(idx_dev, index_image, (size_t)npix * 4, cudaMemcpyHostToDevice, ctx->s0));
+    if (posteriors) {
+        float* p = crf->feat_stage.as<float>() + npix;
+        RSS_CU(ctx, cudaMemcpyAsync(p, posteriors, (size_t)npix * crf->Mtot * 4, cudaMemcpyHostToDevice, ctx->s0));
+        post_dev = p;
+    } else {
+        if (!frame_ctx || frame_ctx != ctx) return ctx->fail(RSS_ERR_INVALID, "frame context must be the CRF's context");
+        if (!ctx->fr.have_post || ctx->fr.W * ctx->fr.H != npix || ctx->forest.sumC != crf->Mtot)
+            return ctx->fail(RSS_ERR_STATE, "no resident posteriors matching this index image");
+        post_dev = ctx->fr.posteriors.as<float>();
+    }
+    for (int l = 0; l < crf->n_layers; l++) {
+        RSS_LAUNCH(ctx, unary_accumulate_kernel, rss_div_up((long long)npix * crf->M[l], 256), 256, 0, ctx->s0, idx_dev, npix,
+                   post_dev + (size_t)npix * crf->moff[l], crf->M[l], crf->Mtot, crf->moff[l], crf->N, crf->unary.as<float>());
+    }
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    crf->unary_set = true;
+    return RSS_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// fused keyframe (configs[1]/[2] of BASELINE.json)
+// --------------------------------------------------------------------------------------------------------------------
+namespace rss {
+rss_status frame_segment(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth, int W, int H, const float* Kinv,
+                         const float* R, const float* t, float fill);
+void frame_collect_timings(rss_ctx* ctx, bool with_d2h);
+}
+
+extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth_mm, int W, int H,
+                                           const float Kinv[9], const float R[9], const float t[3],
+                                           const rss_keyframe_params* prm, uint8_t* labels, float* Qout) {
+    if (!ctx) return RSS_ERR_INVALID;
+    if (!Kinv || !R || !t || !prm) return ctx->fail(RSS_ERR_INVALID, "null calibration or parameters");
+    if (!(ctx->cfg.use_height || ctx->cfg.use_normal))
+        return ctx->fail(RSS_ERR_STATE, "the keyframe CRF needs the point cloud (feature_height or feature_normal)");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    rss_status st = frame_segment(ctx, rgb, depth_mm, W, H, Kinv, R, t, prm->fill);
+    if (st != RSS_OK) return st;
+    const ForestDev& F = ctx->forest;
+    const int N = W * H;
+    rss_crf* crf = ctx->keyframe_crf;
+    if (!crf || crf->N != N || crf->n_layers != F.L || crf->Mtot != F.sumC) {
+        crf_release_cached(ctx);
+        st = crf_new(ctx, N, F.L, F.C, &crf);
+        if (st != RSS_OK) return st;
+        ctx->keyframe_crf = crf;
+    }
+    // previous lattices are rebuilt in place (their buffers are reused): the 5-D one first so that pops match
+    while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
+    LayerSpec ls = make_layers(crf, nullptr);
+    RSS_LAUNCH(ctx, unary_from_posteriors_kernel, rss_div_up((long long)N * crf->Mtot, 256), 256, 0, ctx->s0,
+               ctx->fr.posteriors.as<float>(), N, crf->Mtot, ls, crf->unary.as<float>());
+    cudaEventRecord(ctx->ev[8], ctx->s0);
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * 8 * 4));
+    float* f3 = crf->feat_stage.as<float>();
+    float* f5 = f3 + (size_t)N * 3;
+    RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, ctx->s0, N, ctx->fr.xyz.as<float4>(),
+               1.0f / prm->sigma_xyz, t[0], t[1], t[2], f3);
+    RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(N, 256), 256, 0, ctx->s0, W, H, prm->sigma_px, prm->sigma_px,
+               prm->sigma_rgb, prm->sigma_rgb, prm->sigma_rgb, ctx->fr.rgb.as<uint8_t>(), f5);
+    st = crf_add_kernel_dev(crf, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, true);
+    if (st != RSS_OK) return st;
+    st = crf_add_kernel_dev(crf, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, true);
+    if (st != RSS_OK) return st;
+    cudaEventRecord(ctx->ev[9], ctx->s0);
+    int unk[RSS_MAX_LAYERS];
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = l < ctx->cfg.layer_count ? ctx->cfg.unknown_label[l] : 0;
+    st = crf_run(crf, prm->iters, unk, crf->labels.as<uint8_t>());
+    if (st != RSS_OK) return st;
+    cudaEventRecord(ctx->ev[10], ctx->s0);
+    if (labels) RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.ptr, (size_t)N * F.L, cudaMemcpyDeviceToHost, ctx->s0));
+    if (Qout) {
+        float* dstQ = Qout;
+        for (int l = 0; l < crf->n_layers; l++) {
+            RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, crf->Q.as<float>(),
+                       N, crf->M[l], crf->Mtot, crf->moff[l], crf->scratch.as<float>());
+            RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
+            RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+            dstQ += (size_t)N * crf->M[l];
+        }
+    }
+    cudaEventRecord(ctx->ev[5], ctx->s0);
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    frame_collect_timings(ctx, false);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]); ctx->tim.lattice_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]); ctx->tim.meanfield_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[5]); ctx->tim.d2h_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]); ctx->tim.total_ms = ms;
+    return RSS_OK;
+}

@@ -1,0 +1,503 @@
+// Permutohedral lattice on the device: construction (embedding, hash table with 128-bit CAS, vertex
+// numbering, blur neighbours, vertex-major CSR of the splat matrix) and the three filter stages
+// splat / blur / slice.  Reference: third-party/densecrf/src/permutohedral.cpp:54-131 (hash table),
+// :140-321 (init, SSE build), :476-589 (seqCompute / sseCompute).
+//
+// Design notes (B200):
+//  * Embedding arithmetic mirrors the SSE code operation by operation (separate float multiplies and adds,
+//    round-half-even), so every point lands in the same simplex with the same barycentric weights as in the
+//    reference.  The vertex NUMBERING differs (it is not observable); the partition of points is identical.
+//  * Keys (d x int16) are packed into one 128-bit word and claimed with a single ATOMG.CAS.128.  A slot goes
+//    EMPTY -> key exactly once, so plain cached loads are safe for the fast "already there" path.
+//  * Splat is a gather, not a scatter: the (point, corner) pairs are counting-sorted by vertex once per
+//    lattice, rows are cut into segments of SPLAT_SEG nonzeros, and each iteration every (segment, float4
+//    channel group) work item sums its w * Q rows and issues one vector RED.ADD.F32x4 per item.  This removes
+//    the atomic hot spot of the few-vertices regime (a 640x480 frame at the node's kernel widths has ~10^3
+//    vertices for 2*10^6 adds per channel) while staying load-balanced in the many-vertices regime.
+//  * No kernel needs the vertex count on the host: V lives in device memory, launches are sized by capacity.
+#include "lattice.cuh"
+#include "scan.cuh"
+
+namespace rss {
+
+// ---------------------------------------------------------------------------------------------- keys
+__device__ __forceinline__ bool key_eq(const Key128& a, const Key128& b) { return a.lo == b.lo && a.hi == b.hi; }
+__device__ __forceinline__ Key128 key_empty() { return Key128{~0ull, ~0ull}; }
+__device__ __forceinline__ uint32_t key_hash(const Key128& k) {
+    unsigned long long h = k.lo * 0x9E3779B97F4A7C15ull;
+    h ^= (k.hi + 0x7F4A7C159E3779B9ull) * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    return (uint32_t)h;
+}
+template <int D>
+__device__ __forceinline__ Key128 key_pack(const int* k) {  // int16 wrap like the reference's short keys
+    Key128 r{0ull, 0ull};
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const unsigned long long v = (unsigned long long)(k[i] & 0xFFFF);
+        if (i < 4) r.lo |= v << (16 * i);
+        else r.hi |= v << (16 * (i - 4));
+    }
+    return r;
+}
+template <int D>
+__device__ __forceinline__ void key_unpack(const Key128& r, int* k) {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const unsigned long long v = i < 4 ? (r.lo >> (16 * i)) : (r.hi >> (16 * (i - 4)));
+        k[i] = (int)(short)(v & 0xFFFF);
+    }
+}
+__device__ __forceinline__ Key128 load_key(const Key128* p) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    return Key128{v.x, v.y};
+}
+// returns the slot of `key`, inserting it if absent; -1 when the table is full.
+// A slot goes EMPTY -> key exactly once.  A plain (cached, possibly stale or torn) 128-bit load may only be trusted
+// when it shows OUR key (then the slot was fully written); every other outcome is confirmed with the CAS itself,
+// whose return value is the authoritative content of the slot.
+__device__ __forceinline__ int hash_insert(Key128* table, uint32_t mask, const Key128& key, uint32_t* counts) {
+    uint32_t h = key_hash(key) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+        if (key_eq(load_key(table + h), key)) return (int)h;
+        const Key128 old = atomicCAS(table + h, key_empty(), key);
+        if (key_eq(old, key_empty())) {
+            atomicAdd(counts + 3, 1u);
+            return (int)h;
+        }
+        if (key_eq(old, key)) return (int)h;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+__device__ __forceinline__ int hash_find(const Key128* table, uint32_t mask, const Key128& key) {
+    uint32_t h = key_hash(key) & mask;
+    for (uint32_t probes = 0; probes <= mask; probes++) {
+        const Key128 cur = load_key(table + h);
+        if (key_eq(cur, key)) return (int)h;
+        if (key_eq(cur, key_empty())) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------------------------------------- embedding
+struct ScaleFactors {
+    float s[LAT_MAX_D];
+};
+
+// Permutohedral::init, SSE build (permutohedral.cpp:192-277), one thread per point.
+template <int D>
+__global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restrict__ feat, int N, ScaleFactors sf,
+                                                            Key128* __restrict__ table, uint32_t mask,
+                                                            int* __restrict__ offsets, float* __restrict__ bary_out,
+                                                            uint32_t* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float invdplus1 = __fdiv_rn(1.0f, (float)(D + 1)), dplus1 = (float)(D + 1);
+    float elevated[D + 1], rem0[D + 1], rank[D + 1], bary[D + 2];
+    // elevate (:203-209)
+    float sm = 0.f;
+#pragma unroll
+    for (int j = D; j > 0; j--) {
+        const float cf = __fmul_rn(feat[(size_t)i * D + (j - 1)], sf.s[j - 1]);
+        elevated[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
+        sm = __fadd_rn(sm, cf);
+    }
+    elevated[0] = sm;
+    // closest 0-coloured simplex (:212-222), cvtps_epi32 = round-half-even
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k <= D; k++) {
+        const float v = rintf(__fmul_rn(invdplus1, elevated[k]));
+        rem0[k] = __fmul_rn(v, dplus1);
+        sum = __fadd_rn(sum, v);
+    }
+    // rank (:225-235)
+#pragma unroll
+    for (int k = 0; k <= D; k++) rank[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+        const float da = __fsub_rn(elevated[a], rem0[a]);
+#pragma unroll
+        for (int b = a + 1; b <= D; b++) {
+            const float db = __fsub_rn(elevated[b], rem0[b]);
+            const float c = da < db ? 1.f : 0.f;
+            rank[a] = __fadd_rn(rank[a], c);
+            rank[b] = __fadd_rn(rank[b], __fsub_rn(1.f, c));
+        }
+    }
+    // bring the point back onto the plane (:238-244)
+#pragma unroll
+    for (int k = 0; k <= D; k++) {
+        rank[k] = __fadd_rn(rank[k], sum);
+        const float add = rank[k] < 0.f ? dplus1 : 0.f, sub = rank[k] >= dplus1 ? dplus1 : 0.f;
+        const float adj = __fsub_rn(add, sub);
+        rank[k] = __fadd_rn(rank[k], adj);
+        rem0[k] = __fadd_rn(rem0[k], adj);
+    }
+    // barycentric coordinates (:247-265)
+#pragma unroll
+    for (int k = 0; k < D + 2; k++) bary[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k <= D; k++) {
+        const float v = __fmul_rn(__fsub_rn(elevated[k], rem0[k]), invdplus1);
+        const int q = D - (int)rank[k];
+#pragma unroll
+        for (int z = 0; z < D + 2; z++) {  // register-resident scatter
+            if (z == q) bary[z] = __fadd_rn(bary[z], v);
+            if (z == q + 1) bary[z] = __fsub_rn(bary[z], v);
+        }
+    }
+    bary[0] = __fadd_rn(bary[0], __fadd_rn(1.f, bary[D + 1]));
+    // vertices of the simplex (:270-277): key = rem0 + canonical[remainder][rank]
+    int irank[D + 1], irem[D + 1];
+#pragma unroll
+    for (int k = 0; k <= D; k++) {
+        irank[k] = (int)rank[k];
+        irem[k] = __float2int_rz(rem0[k]);
+    }
+#pragma unroll
+    for (int rem = 0; rem <= D; rem++) {
+        int key[D];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            // canonical[rem][r] = rem if r <= D - rem else rem - (D+1)   (:171-177)
+            const int canon = irank[k] <= D - rem ? rem : rem - (D + 1);
+            key[k] = irem[k] + canon;
+        }
+        const int slot = hash_insert(table, mask, key_pack<D>(key), counts);
+        if (slot < 0) counts[1] = 1u;
+        offsets[(size_t)i * (D + 1) + rem] = slot;
+        bary_out[(size_t)i * (D + 1) + rem] = bary[rem];
+    }
+}
+
+// occupancy flags -> (scan) -> slot_id; then compact the keys and rewrite offsets from slots to vertex ids
+__global__ void __launch_bounds__(256) table_flags_kernel(const Key128* __restrict__ table, uint32_t hcap,
+                                                          uint32_t* __restrict__ flags) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= hcap) return;
+    flags[h] = key_eq(load_key(table + h), key_empty()) ? 0u : 1u;
+}
+__global__ void __launch_bounds__(256) table_compact_kernel(const Key128* __restrict__ table, uint32_t hcap,
+                                                            const uint32_t* __restrict__ slot_id, uint32_t vcap,
+                                                            Key128* __restrict__ vkeys, uint32_t* __restrict__ counts) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= hcap) return;
+    const Key128 k = load_key(table + h);
+    if (key_eq(k, key_empty())) return;
+    const uint32_t id = slot_id[h];
+    if (id >= vcap) { counts[1] = 1u; return; }  // load factor above 1/2: ask the host for a bigger table
+    vkeys[id] = k;
+}
+__global__ void __launch_bounds__(256) remap_offsets_kernel(int* __restrict__ offsets, size_t n,
+                                                            const uint32_t* __restrict__ slot_id,
+                                                            uint32_t* __restrict__ deg, const uint32_t* __restrict__ counts,
+                                                            uint32_t vcap) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || counts[1]) return;
+    const int slot = offsets[k];
+    const uint32_t id = slot_id[slot];
+    offsets[k] = (int)id;
+    if (id < vcap) atomicAdd(deg + id, 1u);
+}
+
+// blur neighbours (:303-318): along axis j, n1 = key - 1 with coordinate j set to key[j] + d, n2 the opposite
+template <int D>
+__global__ void __launch_bounds__(256) neighbors_kernel(const Key128* __restrict__ vkeys, const Key128* __restrict__ table,
+                                                        uint32_t mask, const uint32_t* __restrict__ slot_id,
+                                                        const uint32_t* __restrict__ counts, uint32_t vcap,
+                                                        int2* __restrict__ nbr) {
+    const uint32_t V = counts[0];
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts[1] || gid >= V * (D + 1)) return;
+    const uint32_t j = gid / V, v = gid - j * V;
+    int key[D], n1[D], n2[D];
+    key_unpack<D>(vkeys[v], key);
+#pragma unroll
+    for (int k = 0; k < D; k++) { n1[k] = key[k] - 1; n2[k] = key[k] + 1; }
+#pragma unroll
+    for (int k = 0; k < D; k++)
+        if ((uint32_t)k == j) { n1[k] = key[k] + D; n2[k] = key[k] - D; }
+    const int s1 = hash_find(table, mask, key_pack<D>(n1)), s2 = hash_find(table, mask, key_pack<D>(n2));
+    nbr[(size_t)j * vcap + v] = make_int2(s1 < 0 ? (int)vcap : (int)slot_id[s1], s2 < 0 ? (int)vcap : (int)slot_id[s2]);
+}
+
+// vertex-major CSR of the splat matrix + segment list
+__global__ void __launch_bounds__(256) seg_count_kernel(const uint32_t* __restrict__ deg, const uint32_t* __restrict__ counts,
+                                                        uint32_t* __restrict__ nseg, uint32_t vcap) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > vcap) return;
+    const uint32_t V = counts[1] ? 0u : counts[0];
+    nseg[v] = v < V ? (deg[v] + SPLAT_SEG - 1) / SPLAT_SEG : 0u;
+}
+__global__ void __launch_bounds__(256) csr_fill_kernel(const int* __restrict__ offsets, const float* __restrict__ bary,
+                                                       size_t n, int d1, const uint32_t* __restrict__ row_start,
+                                                       uint32_t* __restrict__ cursor, const uint32_t* __restrict__ counts,
+                                                       int* __restrict__ csr_pt, float* __restrict__ csr_w) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || counts[1]) return;
+    const int v = offsets[k];
+    const uint32_t pos = row_start[v] + atomicAdd(cursor + v, 1u);
+    csr_pt[pos] = (int)(k / d1);
+    csr_w[pos] = bary[k];
+}
+__global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restrict__ row_start,
+                                                       const uint32_t* __restrict__ seg_off,
+                                                       const uint32_t* __restrict__ counts, uint32_t maxseg,
+                                                       int* __restrict__ seg_v, uint32_t* __restrict__ seg_begin,
+                                                       uint32_t* __restrict__ seg_end) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts[1] || v >= counts[0]) return;
+    const uint32_t b = row_start[v], e = row_start[v + 1];
+    uint32_t s = seg_off[v];
+    for (uint32_t p = b; p < e && s < maxseg; p += SPLAT_SEG, s++) {
+        seg_v[s] = (int)v;
+        seg_begin[s] = p;
+        seg_end[s] = min(e, p + SPLAT_SEG);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- filter stages
+// splat (:545-553): values[v] += w * in[p] for every (p, corner) pair of vertex v.  `in` is Q, optionally scaled by
+// norm[p] first (DenseKernel::filter pre-scaling, pairwise.cpp:65-66).  One thread per (segment, float4 group).
+__global__ void __launch_bounds__(256) splat_kernel(const int* __restrict__ seg_v, const uint32_t* __restrict__ seg_begin,
+                                                    const uint32_t* __restrict__ seg_end, const uint32_t* __restrict__ counts,
+                                                    const int* __restrict__ csr_pt, const float* __restrict__ csr_w,
+                                                    const float* __restrict__ in, int in_stride,
+                                                    const float* __restrict__ norm, int M, int Mp,
+                                                    float* __restrict__ values) {
+    const int G = Mp >> 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nseg = counts[2];
+    if (counts[1] || gid >= (long long)nseg * G) return;
+    const uint32_t s = (uint32_t)(gid / G);
+    const int g = (int)(gid - (long long)s * G);
+    const int c0 = 4 * g;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t b = seg_begin[s], e = seg_end[s];
+    for (uint32_t k = b; k < e; k++) {
+        const int p = __ldg(csr_pt + k);
+        const float w = __ldg(csr_w + k);
+        const float nv = norm ? __ldg(norm + p) : 1.f;
+        const float* row = in + (size_t)p * in_stride + c0;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (c0 + c < M) {
+                float x = __ldg(row + c);
+                if (norm) x = __fmul_rn(x, nv);
+                acc[c] = __fadd_rn(acc[c], __fmul_rn(w, x));
+            }
+    }
+    float* dst = values + (size_t)seg_v[s] * Mp + c0;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]),
+                 "f"(acc[3])
+                 : "memory");
+}
+
+// blur along one axis (:555-569): new[v] = old[v] + 0.5 * (old[n1] + old[n2]); a missing neighbour is the zero row
+__global__ void __launch_bounds__(256) blur_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
+                                                   const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
+                                                   int G) {
+    const uint32_t V = counts[0];
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts[1] || gid >= (long long)V * G) return;
+    const uint32_t v = (uint32_t)(gid / G);
+    const int g = (int)(gid - (long long)v * G);
+    const int2 nb = __ldg(nbr + v);
+    const float4 o = src[(size_t)v * G + g], a = src[(size_t)nb.x * G + g], b = src[(size_t)nb.y * G + g];
+    float4 r;
+    r.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(a.x, b.x)));
+    r.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(a.y, b.y)));
+    r.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(a.z, b.z)));
+    r.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(a.w, b.w)));
+    dst[(size_t)v * G + g] = r;
+}
+
+// plain slice (:571-584) for rss_crf_filter and the normalisation pass; seq selects the scalar path's
+// (w * value) * alpha association (seqCompute :518-521) instead of (w * alpha) * value.
+__global__ void __launch_bounds__(256) slice_kernel(const int* __restrict__ offsets, const float* __restrict__ bary, int N,
+                                                    int d1, float alpha, const float* __restrict__ values, int M, int Mp,
+                                                    int seq, const uint32_t* __restrict__ counts,
+                                                    float* __restrict__ out, int out_stride) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts[1] || gid >= (long long)N * M) return;
+    const int i = (int)(gid / M), c = (int)(gid - (long long)i * M);
+    float acc = 0.f;
+    for (int j = 0; j < d1; j++) {
+        const int v = offsets[(size_t)i * d1 + j];
+        const float w = bary[(size_t)i * d1 + j];
+        const float val = values[(size_t)v * Mp + c];
+        const float p = seq ? __fmul_rn(__fmul_rn(w, val), alpha) : __fmul_rn(__fmul_rn(w, alpha), val);
+        acc = __fadd_rn(acc, p);
+    }
+    out[(size_t)i * out_stride + c] = acc;
+}
+
+// DenseKernel::initLattice (pairwise.cpp:44-61): norm from the filter response to all-ones
+__global__ void __launch_bounds__(256) norm_kernel(float* __restrict__ norm, int N, int norm_type) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float v = norm[i];
+    if (norm_type == RSS_NORMALIZE_SYMMETRIC) norm[i] = (float)(1.0 / sqrt((double)v + 1e-20));
+    else norm[i] = (float)(1.0 / ((double)v + 1e-20));
+}
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void __launch_bounds__(256) finalize_counts_kernel(uint32_t* counts, const uint32_t* seg_total,
+                                                              uint32_t vcap, uint32_t maxseg) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (counts[0] > vcap) counts[1] = 1u;
+        uint32_t s = *seg_total;
+        if (s > maxseg) { counts[1] = 1u; s = 0; }
+        counts[2] = counts[1] ? 0u : s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static ScaleFactors make_scale_factors(int d) {
+    ScaleFactors sf;
+    const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (d + 1));                     // permutohedral.cpp:180
+    for (int i = 0; i < LAT_MAX_D; i++)
+        sf.s[i] = i < d ? (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev) : 0.f;  // :183
+    return sf;
+}
+
+template <int D>
+static void launch_embed(rss_ctx* c, cudaStream_t st, const float* feat, int N, Lattice& L) {
+    RSS_LAUNCH(c, lattice_embed_kernel<D>, rss_div_up(N, 256), 256, 0, st, feat, N, make_scale_factors(D),
+               L.table.as<Key128>(), L.hcap - 1, L.offsets.as<int>(), L.bary.as<float>(), L.counts.as<uint32_t>());
+}
+template <int D>
+static void launch_neighbors(rss_ctx* c, cudaStream_t st, Lattice& L) {
+    RSS_LAUNCH(c, neighbors_kernel<D>, rss_div_up((long long)L.vcap * (D + 1), 256), 256, 0, st, L.vkeys.as<Key128>(),
+               L.table.as<Key128>(), L.hcap - 1, L.slot_id.as<uint32_t>(), L.counts.as<uint32_t>(), L.vcap,
+               L.nbr.as<int2>());
+}
+
+float lattice_alpha(int d) { return 1.0f / (1 + powf(2, -(float)d)); }  // :571
+
+// Allocates for capacity hcap and enqueues the whole construction on `st`.  feat: device [N][d].  Mp = padded
+// channel count of the value tables.  No host synchronisation; overflow is reported in counts[1].
+rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp) {
+    if (d < 1 || d > LAT_MAX_D) return ctx->fail(RSS_ERR_INVALID, "pairwise feature dimension must be in [1, 7]");
+    L.d = d; L.N = N; L.hcap = hcap; L.vcap = hcap / 2;
+    const int d1 = d + 1;
+    const size_t nnz = (size_t)N * d1;
+    L.maxseg = (uint32_t)(nnz / SPLAT_SEG + L.vcap + 1);
+    RSS_CU(ctx, L.table.reserve((size_t)hcap * sizeof(Key128)));
+    RSS_CU(ctx, L.slot_id.reserve((size_t)hcap * 4));
+    RSS_CU(ctx, L.vkeys.reserve((size_t)L.vcap * sizeof(Key128)));
+    RSS_CU(ctx, L.offsets.reserve(nnz * 4));
+    RSS_CU(ctx, L.bary.reserve(nnz * 4));
+    RSS_CU(ctx, L.nbr.reserve((size_t)d1 * L.vcap * sizeof(int2)));
+    RSS_CU(ctx, L.norm.reserve((size_t)N * 4));
+    RSS_CU(ctx, L.counts.reserve(64));
+    RSS_CU(ctx, L.deg.reserve((size_t)(L.vcap + 2) * 4));
+    RSS_CU(ctx, L.cursor.reserve((size_t)(L.vcap + 1) * 4));
+    RSS_CU(ctx, L.nseg.reserve((size_t)(L.vcap + 2) * 4));
+    RSS_CU(ctx, L.csr_pt.reserve(nnz * 4));
+    RSS_CU(ctx, L.csr_w.reserve(nnz * 4));
+    RSS_CU(ctx, L.seg_v.reserve((size_t)L.maxseg * 4));
+    RSS_CU(ctx, L.seg_begin.reserve((size_t)L.maxseg * 4));
+    RSS_CU(ctx, L.seg_end.reserve((size_t)L.maxseg * 4));
+    RSS_CU(ctx, L.val_a.reserve((size_t)(L.vcap + 1) * Mp * 4));
+    RSS_CU(ctx, L.val_b.reserve((size_t)(L.vcap + 1) * Mp * 4));
+    RSS_CU(ctx, L.scan_tmp.reserve((scan_tmp_elems(hcap) + 8) * 4));
+    uint32_t* counts = L.counts.as<uint32_t>();
+    RSS_CU(ctx, cudaMemsetAsync(L.table.ptr, 0xFF, (size_t)hcap * sizeof(Key128), st));
+    RSS_CU(ctx, cudaMemsetAsync(counts, 0, 64, st));
+    RSS_CU(ctx, cudaMemsetAsync(L.deg.ptr, 0, (size_t)(L.vcap + 2) * 4, st));
+    RSS_CU(ctx, cudaMemsetAsync(L.cursor.ptr, 0, (size_t)(L.vcap + 1) * 4, st));
+    RSS_CU(ctx, cudaMemsetAsync(L.val_b.ptr, 0, (size_t)(L.vcap + 1) * Mp * 4, st));
+    switch (d) {
+        case 1: launch_embed<1>(ctx, st, feat, N, L); break;
+        case 2: launch_embed<2>(ctx, st, feat, N, L); break;
+        case 3: launch_embed<3>(ctx, st, feat, N, L); break;
+        case 4: launch_embed<4>(ctx, st, feat, N, L); break;
+        case 5: launch_embed<5>(ctx, st, feat, N, L); break;
+        case 6: launch_embed<6>(ctx, st, feat, N, L); break;
+        default: launch_embed<7>(ctx, st, feat, N, L); break;
+    }
+    // vertex numbering: slot -> id by an exclusive scan of the occupancy flags; counts[0] = V
+    RSS_LAUNCH(ctx, table_flags_kernel, rss_div_up(hcap, 256), 256, 0, st, L.table.as<Key128>(), hcap,
+               L.slot_id.as<uint32_t>());
+    exclusive_scan_u32(L.slot_id.as<uint32_t>(), L.slot_id.as<uint32_t>(), hcap, L.scan_tmp.as<uint32_t>(), counts, st,
+                       &ctx->launches);
+    RSS_LAUNCH(ctx, table_compact_kernel, rss_div_up(hcap, 256), 256, 0, st, L.table.as<Key128>(), hcap,
+               L.slot_id.as<uint32_t>(), L.vcap, L.vkeys.as<Key128>(), counts);
+    RSS_LAUNCH(ctx, remap_offsets_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
+               L.slot_id.as<uint32_t>(), L.deg.as<uint32_t>(), counts, L.vcap);
+    switch (d) {
+        case 1: launch_neighbors<1>(ctx, st, L); break;
+        case 2: launch_neighbors<2>(ctx, st, L); break;
+        case 3: launch_neighbors<3>(ctx, st, L); break;
+        case 4: launch_neighbors<4>(ctx, st, L); break;
+        case 5: launch_neighbors<5>(ctx, st, L); break;
+        case 6: launch_neighbors<6>(ctx, st, L); break;
+        default: launch_neighbors<7>(ctx, st, L); break;
+    }
+    // CSR: segments per row, row_start = scan(deg), seg_off = scan(nseg)
+    RSS_LAUNCH(ctx, seg_count_kernel, rss_div_up((long long)L.vcap + 1, 256), 256, 0, st, L.deg.as<uint32_t>(), counts,
+               L.nseg.as<uint32_t>(), L.vcap);
+    exclusive_scan_u32(L.deg.as<uint32_t>(), L.deg.as<uint32_t>(), (size_t)L.vcap + 1, L.scan_tmp.as<uint32_t>(), nullptr,
+                       st, &ctx->launches);
+    exclusive_scan_u32(L.nseg.as<uint32_t>(), L.nseg.as<uint32_t>(), (size_t)L.vcap + 1, L.scan_tmp.as<uint32_t>(),
+                       counts + 4, st, &ctx->launches);
+    RSS_LAUNCH(ctx, finalize_counts_kernel, 1, 32, 0, st, counts, counts + 4, L.vcap, L.maxseg);
+    RSS_LAUNCH(ctx, csr_fill_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), L.bary.as<float>(),
+               nnz, d1, L.deg.as<uint32_t>(), L.cursor.as<uint32_t>(), counts, L.csr_pt.as<int>(), L.csr_w.as<float>());
+    RSS_LAUNCH(ctx, seg_fill_kernel, rss_div_up(L.vcap, 256), 256, 0, st, L.deg.as<uint32_t>(), L.nseg.as<uint32_t>(),
+               counts, L.maxseg, L.seg_v.as<int>(), L.seg_begin.as<uint32_t>(), L.seg_end.as<uint32_t>());
+    RSS_CU(ctx, cudaGetLastError());
+    return RSS_OK;
+}
+
+// splat -> (d+1) blurs; returns the table holding the blurred values.  in: [N][in_stride], M live channels.
+float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
+                          int M, int Mp) {
+    const int G = Mp / 4;
+    float* a = L.val_a.as<float>();
+    float* b = L.val_b.as<float>();
+    cudaMemsetAsync(a, 0, (size_t)(L.vcap + 1) * Mp * 4, st);
+    const long long items = (long long)L.maxseg * G;
+    RSS_LAUNCH(ctx, splat_kernel, rss_div_up(items, 256), 256, 0, st, L.seg_v.as<int>(), L.seg_begin.as<uint32_t>(),
+               L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_pt.as<int>(), L.csr_w.as<float>(), in, in_stride,
+               norm, M, Mp, a);
+    for (int j = 0; j <= L.d; j++) {
+        RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st, reinterpret_cast<const float4*>(a),
+                   reinterpret_cast<float4*>(b), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), G);
+        float* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
+                   int out_stride) {
+    RSS_LAUNCH(ctx, slice_kernel, rss_div_up((long long)L.N * M, 256), 256, 0, st, L.offsets.as<int>(), L.bary.as<float>(),
+               L.N, L.d + 1, lattice_alpha(L.d), values, M, Mp, seq, L.counts.as<uint32_t>(), out, out_stride);
+}
+
+// norm_ = 1/sqrt(K 1 + 1e-20) through the scalar path (pairwise.cpp:44,54-57; permutohedral.cpp:600-601)
+rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch /* [N] */) {
+    const int N = L.N;
+    float* norm = L.norm.as<float>();
+    if (L.norm_type == RSS_NO_NORMALIZATION) {
+        return ctx->fail(RSS_ERR_INVALID, "NO_NORMALIZATION is not supported on the device path");
+    }
+    RSS_LAUNCH(ctx, fill_f32_kernel, rss_div_up(N, 256), 256, 0, st, ones_scratch, (size_t)N, 1.0f);
+    // value tables were allocated for the CRF's Mp >= 4; run the one-channel filter with Mp = 4
+    float* vals = lattice_splat_blur(ctx, st, L, ones_scratch, 1, nullptr, 1, 4);
+    lattice_slice(ctx, st, L, vals, 1, 4, 1, norm, 1);
+    RSS_LAUNCH(ctx, norm_kernel, rss_div_up(N, 256), 256, 0, st, norm, N, L.norm_type);
+    // the ping-pong partner must have a zero "missing neighbour" row again for the CRF's own Mp
+    RSS_CU(ctx, cudaGetLastError());
+    return RSS_OK;
+}
+
+}  // namespace rss

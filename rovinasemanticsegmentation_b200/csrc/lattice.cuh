@@ -1,0 +1,67 @@
+// Device data structures of the permutohedral lattice (reference third-party/densecrf/src/permutohedral.cpp).
+#pragma once
+#include "common.cuh"
+
+namespace rss {
+
+constexpr int LAT_MAX_D = 7;   // feature dimensions; keys are d int16 packed into 128 bits (one spare lane)
+constexpr int SPLAT_SEG = 32;  // nonzeros per splat work item
+
+struct __align__(16) Key128 {
+    unsigned long long lo, hi;
+};
+
+// One pairwise term = one lattice.  Vertex-count dependent sizes are allocated for vcap (= hash capacity / 2)
+// and the true count lives on the device (counts[0]) so that no host synchronisation is needed to launch.
+struct Lattice {
+    int d = 0, N = 0;
+    float potts_w = 0.f;
+    int norm_type = RSS_NORMALIZE_SYMMETRIC;
+    uint32_t hcap = 0;   // hash capacity (power of two)
+    uint32_t vcap = 0;   // vertex capacity = hcap / 2
+    int V_host = -1;     // vertex count once read back (diagnostics)
+    DevBuf table;        // Key128[hcap]
+    DevBuf slot_id;      // uint32[hcap]   slot -> vertex id (exclusive scan of occupancy)
+    DevBuf vkeys;        // Key128[vcap]   vertex id -> key
+    DevBuf offsets;      // int  [N][d+1]  vertex id of each enclosing-simplex corner
+    DevBuf bary;         // float[N][d+1]
+    DevBuf nbr;          // int2 [d+1][vcap]  blur neighbours (n1, n2); missing -> zero row (index = vcap)
+    DevBuf norm;         // float[N]
+    DevBuf counts;       // uint32[8]: [0] V, [1] overflow flag, [2] segments, [3] inserted
+    DevBuf deg;          // uint32[vcap+1]  row degree, then row_start (in-place scan)
+    DevBuf cursor;       // uint32[vcap]
+    DevBuf nseg;         // uint32[vcap+1]  segments per row, then segment offsets
+    DevBuf csr_pt;       // int  [N*(d+1)]
+    DevBuf csr_w;        // float[N*(d+1)]
+    DevBuf seg_v;        // int  [maxseg]   vertex of each splat segment
+    DevBuf seg_begin;    // uint32[maxseg]
+    DevBuf seg_end;      // uint32[maxseg]
+    DevBuf val_a, val_b; // float[(vcap+1)][Mp] ping-pong value tables (row vcap stays zero)
+    DevBuf scan_tmp;
+    uint32_t maxseg = 0;
+    void release() {
+        DevBuf* b[] = {&table, &slot_id, &vkeys, &offsets, &bary, &nbr, &norm, &counts, &deg, &cursor, &nseg,
+                       &csr_pt, &csr_w, &seg_v, &seg_begin, &seg_end, &val_a, &val_b, &scan_tmp};
+        for (DevBuf* p : b) p->release();
+    }
+};
+
+}  // namespace rss
+
+struct rss_crf {
+    rss_ctx* ctx = nullptr;
+    int N = 0, n_layers = 0;
+    int M[RSS_MAX_LAYERS] = {0};
+    int moff[RSS_MAX_LAYERS + 1] = {0};
+    int Mtot = 0, Mp = 0;          // total labels, padded to a multiple of 4
+    rss::DevBuf unary;             // float[N][Mtot]  energies (layers concatenated per point)
+    rss::DevBuf Q;                 // float[N][Mtot]
+    rss::DevBuf scratch;           // float[N][Mp] staging for host-layout conversions / filter tests
+    rss::DevBuf labels;            // uint8[n_layers][N]
+    rss::DevBuf feat_stage;        // float[N][d] staging for feature upload
+    std::vector<rss::Lattice*> kernels;
+    std::vector<rss::Lattice*> pool;  // released lattices whose device buffers are reused by the next build
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // per-lattice streams
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool unary_set = false;
+};

@@ -1,0 +1,289 @@
+// Preparation kernels for PCL-style integral-image normals (see normals.cuh), sm_100a.
+//
+// Three data products per frame:
+//   (1) gradient planes g[6][H][W] (float): central differences of the organised cloud, 0 where PCL skips
+//       the element (non-finite), plus finite flags fin[2][H][W];
+//   (2) two 3-channel DOUBLE integral images + finite counts, built with PCL's serial recurrence
+//       I[r][c+1] = (I[r-1][c+1] + I[r][c]) - I[r-1][c] + e.  Floating-point rounding makes the result depend
+//       on that exact evaluation order, so the kernel keeps it and parallelises along anti-diagonals:
+//       one CTA per (image, channel) plane, one thread per row, thread r handles column s-r at step s
+//       and hands its value to thread r+1 through double-buffered shared memory;
+//   (3) PCL's two-pass 1.0/1.4 chamfer distance map over the depth-change mask.  Only min(dist, 10) is
+//       ever consumed, and a value < 10 is reached through at most 9 steps, so each pass is computed
+//       exactly in independent row bands with a 10-row run-in; within a row the serial dependency
+//       cur[c] = min(m[c], cur[c-1] + 1.0f) is resolved by a log-step min-plus scan (x -> x + 1.0f is
+//       monotone, so min commutes with it and the float additions happen in the reference order).
+#include "kernels.hpp"
+#include "normals.cuh"
+
+namespace rss {
+
+size_t integral_elems(int W, int H) { return (size_t)(W + 1) * (H + 1); }
+
+// ------------------------------------------------------------------------------------------------
+// (1) gradients (initAverage3DGradientMethod) + depth-change mask -> initial distance map
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool depth_change(float z, float zn) {
+    const float thr = __fmul_rn(__fmul_rn(0.02f, __fadd_rn(fabsf(z), 1.0f)), 2.0f);
+    return fabsf(__fsub_rn(z, zn)) > thr || !isfinite(z) || !isfinite(zn);
+}
+
+__global__ void __launch_bounds__(256) gradient_mask_kernel(const float4* __restrict__ xyz, int W, int H,
+                                                            float* __restrict__ grad, uint8_t* __restrict__ fin,
+                                                            float* __restrict__ dist_init) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= W) return;
+    const size_t i = (size_t)r * W + c, NP = (size_t)W * H;
+    float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f};
+    if (r >= 1 && r < H - 1 && c >= 1 && c < W - 1) {
+        const float4 L = xyz[i - 1], Rr = xyz[i + 1], U = xyz[i - W], Dn = xyz[i + W];
+        gx[0] = __fsub_rn(Rr.x, L.x); gx[1] = __fsub_rn(Rr.y, L.y); gx[2] = __fsub_rn(Rr.z, L.z);
+        gy[0] = __fsub_rn(Dn.x, U.x); gy[1] = __fsub_rn(Dn.y, U.y); gy[2] = __fsub_rn(Dn.z, U.z);
+    }
+    const bool fx = isfinite(__fadd_rn(__fadd_rn(gx[0], gx[1]), gx[2]));
+    const bool fy = isfinite(__fadd_rn(__fadd_rn(gy[0], gy[1]), gy[2]));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        grad[(size_t)k * NP + i] = fx ? gx[k] : 0.f;
+        grad[(size_t)(3 + k) * NP + i] = fy ? gy[k] : 0.f;
+    }
+    fin[i] = fx ? 1 : 0;
+    fin[NP + i] = fy ? 1 : 0;
+    // depth-change map, gathered: a pixel is cleared by its own tests and by its left / upper neighbour's
+    const float z = xyz[i].z;
+    bool cleared = false;
+    if (r < H - 1 && c < W - 1) cleared = depth_change(z, xyz[i + 1].z) || depth_change(z, xyz[i + W].z);
+    if (!cleared && c >= 1 && r < H - 1) cleared = depth_change(xyz[i - 1].z, z);
+    if (!cleared && r >= 1 && c < W - 1) cleared = depth_change(xyz[i - W].z, z);
+    dist_init[i] = cleared ? 0.0f : (float)(W + H);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (3) chamfer passes.  One CTA per band of rows; shared arrays hold the previous row and the scan buffers.
+// ------------------------------------------------------------------------------------------------
+constexpr int DIST_RUNIN = 10;
+constexpr int DIST_PAD = 16;
+constexpr float DIST_BIG = 1.0e30f;
+
+// min-plus scan along a row: v[c] = min_{0<=j<=15} (m[c -/+ j] (+1.0f) j times).  dir = +1 looks left.
+// a/b: padded buffers (DIST_PAD entries of DIST_BIG on both sides); result ends in the returned buffer.
+template <int DIR>
+__device__ __forceinline__ float* minplus_scan(float* a, float* b, int W) {
+    float* src = a;
+    float* dst = b;
+#pragma unroll
+    for (int step = 1; step <= 8; step <<= 1) {
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            float o = src[DIST_PAD + c - DIR * step];
+            for (int k = 0; k < step; k++) o = __fadd_rn(o, 1.0f);
+            dst[DIST_PAD + c] = fminf(src[DIST_PAD + c], o);
+        }
+        __syncthreads();
+        float* t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+__global__ void __launch_bounds__(1024) dist_forward_kernel(const float* __restrict__ init, int W, int H, int band,
+                                                            float* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* prev = sm;                        // W
+    float* va = prev + W;                    // W + 2*PAD
+    float* vb = va + W + 2 * DIST_PAD;       // W + 2*PAD
+    const int y0 = blockIdx.x * band, y1 = min(y0 + band, H);
+    const int ys = max(y0 - DIST_RUNIN, 0);
+    for (int c = threadIdx.x; c < W + 2 * DIST_PAD; c += blockDim.x) va[c] = vb[c] = DIST_BIG;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        const float v = init[(size_t)ys * W + c];
+        prev[c] = v;
+        if (ys >= y0) out[(size_t)ys * W + c] = v;  // row 0 is never updated by the forward pass
+    }
+    __syncthreads();
+    for (int r = ys + 1; r < y1; r++) {
+        const float* irow = init + (size_t)r * W;
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            const float ce = irow[c];
+            float m = ce;  // column 0 is never updated
+            if (c >= 1) {
+                const float ul = __fadd_rn(prev[c - 1], 1.4f), up = __fadd_rn(prev[c], 1.0f);
+                // previous_row[ci+1] at ci = W-1 is the first element of the current row (PCL quirk)
+                const float ur = __fadd_rn(c + 1 < W ? prev[c + 1] : irow[0], 1.4f);
+                m = fminf(ce, fminf(fminf(ul, up), ur));
+            }
+            va[DIST_PAD + c] = m;
+        }
+        __syncthreads();
+        float* res = minplus_scan<+1>(va, vb, W);
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            const float v = res[DIST_PAD + c];
+            prev[c] = v;
+            if (r >= y0) out[(size_t)r * W + c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) dist_backward_kernel(const float* __restrict__ fwd, int W, int H, int band,
+                                                             float* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* next = sm;
+    float* va = next + W;
+    float* vb = va + W + 2 * DIST_PAD;
+    const int y0 = blockIdx.x * band, y1 = min(y0 + band, H);
+    const int ye = min(y1 - 1 + DIST_RUNIN, H - 1);
+    for (int c = threadIdx.x; c < W + 2 * DIST_PAD; c += blockDim.x) va[c] = vb[c] = DIST_BIG;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        const float v = fwd[(size_t)ye * W + c];
+        next[c] = v;
+        if (ye < y1) out[(size_t)ye * W + c] = v;  // row H-1 is never updated by the backward pass
+    }
+    __syncthreads();
+    for (int r = ye - 1; r >= y0; r--) {
+        const float* frow = fwd + (size_t)r * W;
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            const float ce = frow[c];
+            float m = ce;  // column W-1 is never updated
+            if (c < W - 1) {
+                // next_row[ci-1] at ci = 0 is the last element of the current row (PCL quirk)
+                const float ll = __fadd_rn(c >= 1 ? next[c - 1] : frow[W - 1], 1.4f);
+                const float lo = __fadd_rn(next[c], 1.0f), lr = __fadd_rn(next[c + 1], 1.4f);
+                m = fminf(ce, fminf(fminf(ll, lo), lr));
+            }
+            va[DIST_PAD + c] = m;
+        }
+        __syncthreads();
+        float* res = minplus_scan<-1>(va, vb, W);
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            const float v = res[DIST_PAD + c];
+            next[c] = v;
+            if (r < y1) out[(size_t)r * W + c] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2) integral images along anti-diagonals.  grid = 6 CTAs (image x channel), block = H threads (<= 1024).
+// Thread r owns integral row r+1.  At step s it computes column c = s - r:
+//     v = ((I[r][c+1] + I[r+1][c]) - I[r][c]) + g      (g = 0 where PCL skips the element)
+// "up" comes from thread r-1 (shared memory, written one step earlier), "left"/"upleft" stay in registers.
+// Gradient values are prefetched 8 columns ahead (two float4 per thread) so that the global-load latency is
+// off the critical path; the recurrence itself is three dependent DADDs per step.
+// ------------------------------------------------------------------------------------------------
+constexpr int PF = 8;
+__global__ void __launch_bounds__(1024) integral_wavefront_kernel(const float* __restrict__ grad,
+                                                                  const uint8_t* __restrict__ fin, int W, int H,
+                                                                  double* __restrict__ integ, int* __restrict__ cnt) {
+    extern __shared__ double smd[];  // [2][H+1] doubles, then [2][H+1] ints
+    double* sval = smd;
+    int* scnt = reinterpret_cast<int*>(smd + 2 * (H + 1));
+    const int plane_id = blockIdx.x;  // img*3 + ch
+    const int img = plane_id / 3, ch = plane_id - img * 3;
+    const bool do_cnt = ch == 0;
+    const int r = threadIdx.x;
+    const int W1 = W + 1;
+    const size_t NP = (size_t)W * H, IP = (size_t)W1 * (H + 1);
+    double* I = integ + (size_t)plane_id * IP;
+    int* Cn = cnt + (size_t)img * IP;
+    const float* g = grad + (size_t)plane_id * NP + (size_t)r * W;
+    const uint8_t* f = fin + (size_t)img * NP + (size_t)r * W;
+    // zero row / column of the integral image
+    for (int c = threadIdx.x; c < W1; c += blockDim.x) {
+        I[c] = 0.0;
+        if (do_cnt) Cn[c] = 0;
+    }
+    if (r < H) {
+        I[(size_t)(r + 1) * W1] = 0.0;
+        if (do_cnt) Cn[(size_t)(r + 1) * W1] = 0;
+    }
+    for (int k = threadIdx.x; k < 2 * (H + 1); k += blockDim.x) {
+        sval[k] = 0.0;
+        scnt[k] = 0;
+    }
+    __syncthreads();
+    double left = 0.0, upleft = 0.0;
+    int cleft = 0, cupleft = 0;
+    float buf[2][PF];
+    uint8_t fbuf[2][PF];
+    auto load_chunk = [&](int which, int c0) {
+#pragma unroll
+        for (int k = 0; k < PF; k++) {
+            const bool in = r < H && c0 + k < W;
+            buf[which][k] = in ? __ldg(g + c0 + k) : 0.f;
+            fbuf[which][k] = (in && do_cnt) ? __ldg(f + c0 + k) : 0;
+        }
+    };
+    load_chunk(0, 0);
+    load_chunk(1, PF);
+    const int steps = W + H - 1;
+    for (int s = 0; s < steps; s++) {
+        const int c = s - r;
+        const int rb = (s + 1) & 1, wb = s & 1;  // read the buffer written at step s-1
+        if (r < H && c >= 0 && c < W) {
+            const int q = c / PF, k = c - q * PF, which = q & 1;
+            const double up = sval[rb * (H + 1) + r];
+            float gv = 0.f;
+            uint8_t fv = 0;
+#pragma unroll
+            for (int kk = 0; kk < PF; kk++)
+                if (kk == k) { gv = buf[0][kk]; fv = fbuf[0][kk]; }
+            if (which) {
+#pragma unroll
+                for (int kk = 0; kk < PF; kk++)
+                    if (kk == k) { gv = buf[1][kk]; fv = fbuf[1][kk]; }
+            }
+            const double v = __dadd_rn(__dsub_rn(__dadd_rn(up, left), upleft), (double)gv);
+            I[(size_t)(r + 1) * W1 + c + 1] = v;
+            sval[wb * (H + 1) + r + 1] = v;
+            upleft = up;
+            left = v;
+            if (do_cnt) {
+                const int cu = scnt[rb * (H + 1) + r];
+                const int cv = cu + cleft - cupleft + (int)fv;
+                Cn[(size_t)(r + 1) * W1 + c + 1] = cv;
+                scnt[wb * (H + 1) + r + 1] = cv;
+                cupleft = cu;
+                cleft = cv;
+            }
+            if (k == PF - 1) {  // chunk consumed: refill it with the chunk after next
+                if (which == 0) load_chunk(0, (q + 2) * PF);
+                else load_chunk(1, (q + 2) * PF);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int W, int H, float* dist_a,
+                            float* dist_b, double* integ, int* integ_cnt, float* grad, uint8_t* fin) {
+    dim3 grid(rss_div_up(W, 256), H);
+    RSS_LAUNCH(c, gradient_mask_kernel, grid, 256, 0, st, xyz, W, H, grad, fin, dist_b);
+    // distance map: init (dist_b) -> forward (dist_a) -> backward (dist_b)
+    const int band = 8;
+    const int threads = min(1024, rss_div_up(W, 32) * 32);
+    const size_t smem = (size_t)(3 * W + 4 * DIST_PAD) * sizeof(float);
+    RSS_LAUNCH(c, dist_forward_kernel, rss_div_up(H, band), threads, smem, st, dist_b, W, H, band, dist_a);
+    RSS_LAUNCH(c, dist_backward_kernel, rss_div_up(H, band), threads, smem, st, dist_a, W, H, band, dist_b);
+    const int wt = min(1024, rss_div_up(H, 32) * 32);
+    const size_t wsmem = (size_t)2 * (H + 1) * (sizeof(double) + sizeof(int));
+    RSS_LAUNCH(c, integral_wavefront_kernel, 6, wt, wsmem, st, grad, fin, W, H, integ, integ_cnt);
+}
+
+__global__ void __launch_bounds__(256) normals_full_kernel(const float4* __restrict__ xyz,
+                                                           const float* __restrict__ dist,
+                                                           const double* __restrict__ integ,
+                                                           const int* __restrict__ cnt, int W, int H,
+                                                           float* __restrict__ normals) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const float3 n = pcl_normal_at(xyz, dist, integ, cnt, W, H, x, y);
+    float* o = normals + ((size_t)y * W + x) * 3;
+    o[0] = n.x; o[1] = n.y; o[2] = n.z;
+}
+void launch_normals_full(rss_ctx* c, cudaStream_t st, const float4* xyz, const float* dist, const double* integ,
+                         const int* integ_cnt, int W, int H, float* normals) {
+    dim3 grid(rss_div_up(W, 256), H);
+    RSS_LAUNCH(c, normals_full_kernel, grid, 256, 0, st, xyz, dist, integ, integ_cnt, W, H, normals);
+}
+
+}  // namespace rss
