@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the per-keyframe inference path (BASELINE.json metric: keyframes/sec, RF + DenseCRF, 640x480).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one synthetic 640x480 RGB-D keyframe through the whole hot path: Lab + patch features + depth/height/
+normal features -> multi-label forest (4 trees, 17 classes in 2 layers) -> 2x upsample -> DenseCRF over the 307 200
+pixels with a 3-D Gaussian kernel on the back-projected points and a 5-D bilateral kernel, 10 mean-field iterations,
+both label layers, gated argmax (BASELINE.json configs[1], with configs[2]'s second layer included).
+
+  value : keyframes/s with the frame already resident in HBM (device time, CUDA events on the library's stream)
+  e2e   : keyframes/s through the C ABI with HOST buffers: pinned rgb/depth in, label maps out, copies timed
+N > 1 (torchrun): every rank owns one GPU and its own keyframes (weak scaling, no collective on the data path);
+the timed region is bracketed by a barrier + synchronize and the slowest rank's time is used.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+FOREST = os.path.join(ROOT, "tests", "golden", "forest_shared.dat")
+W, H = 640, 480
+METRIC = "keyframes/sec RF+DenseCRF 640x480"
+WORKLOAD = ("single-frame RF + DenseCRF: 640x480 RGB-D, stride-2 forest (4 trees, 366 features, 8+9 classes), "
+            "Gaussian 3-D (5 cm, w=3) + bilateral 5-D (80 px / 13, w=10) kernels, 10 mean-field iterations, "
+            "both label layers")
+KF = dict(sigma_xyz=0.05, w_gauss=3.0, sigma_px=80.0, sigma_rgb=13.0, w_bilateral=10.0, iters=10, fill=0.0)
+N_FRAMES = 8  # distinct synthetic frames cycled through
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_keyframe(seed):
+    """The oracle's single-thread restatement of one keyframe (how the reference runs inference)."""
+    import oracle
+    from rovinasemanticsegmentation_b200 import synth
+    oracle.set_threads(1)
+    rgb, depth = synth.frame(seed)
+    Kinv, R, t = synth.calibration()
+    forest = oracle.Forest(FOREST)
+    t0 = time.perf_counter()
+    post = oracle.segment_frame(oracle.default_config(), forest, 2, rgb, depth, Kinv, R, t, 0.5, 15.0, KF["fill"])
+    xyz = oracle.cloud(depth, Kinv, R, t, 0.5, 15.0).reshape(-1, 3)
+    xyz[np.isnan(xyz[:, 0])] = t
+    f3 = (xyz * np.float32(1.0 / KF["sigma_xyz"])).astype(np.float32)
+    f5 = oracle.features_bilateral2d(W, H, KF["sigma_px"], KF["sigma_px"], KF["sigma_rgb"], KF["sigma_rgb"],
+                                     KF["sigma_rgb"], rgb)
+    off, N = 0, W * H
+    for M, unk in ((8, 7), (9, 8)):
+        Q = oracle.crf_inference(-post[off:off + N * M].reshape(N, M), [(f3, KF["w_gauss"]), (f5, KF["w_bilateral"])],
+                                 KF["iters"])
+        oracle.gated_argmax(Q, unk)
+        off += N * M
+    return time.perf_counter() - t0
+
+
+def _cpu_worker(seed):
+    return cpu_keyframe(seed)
+
+
+def cpu_throughput(procs, rounds):
+    """`procs` independent single-thread pipelines side by side (keyframes are independent), `rounds` times."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, range(procs))  # warm-up: page in libraries, build LUTs
+        t0 = time.perf_counter()
+        for r in range(rounds):
+            pool.map(_cpu_worker, range(100 + r * procs, 100 + (r + 1) * procs))
+        dt = time.perf_counter() - t0
+    return procs * rounds / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    oracle.build(ref=False)
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    steps = max(1, min(args.steps, 3))
+    for _ in range(0):
+        pass
+    val, dt = cpu_throughput(procs, steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "keyframes/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "CPU run"},
+        "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": procs, "kind": "port",
+                         "sample": "%d rounds of %d full 640x480 keyframes, one single-thread oracle pipeline per core "
+                                   "(oracle/oracle.c, validated bit-exact against the compiled reference)" % (steps, procs)},
+        "e2e": {"value": val, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+ALGO_BYTES = {
+    # algorithmic (compulsory) bytes per launch, SURVEY.md 8(d) / DESIGN.md "Kernels"; N = W*H points, M = 17 labels
+    # slice of both lattices + soft-max: offsets+bary 8(d+1)N per lattice, unary 4MN, Q write 4MN, norm 4N per lattice
+    "slice_softmax_kernel<20>": lambda N, M: 8 * (4 + 6) * N + 4 * M * N * 2 + 4 * 2 * N,
+}
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import rovinasemanticsegmentation_b200 as rss
+    from rovinasemanticsegmentation_b200 import synth
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank)
+    Kinv, R, t = synth.calibration()
+    frames = []
+    for k in range(N_FRAMES):
+        rgb, depth = synth.frame(10_000 + rank * N_FRAMES + k)
+        prgb = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
+        pdep = torch.empty((H, W), dtype=torch.int16, pin_memory=True)
+        prgb.numpy()[...] = rgb
+        pdep.numpy().view(np.uint16)[...] = depth
+        frames.append((prgb.numpy(), pdep.numpy().view(np.uint16)))
+    plabels = torch.empty((2, H * W), dtype=torch.uint8, pin_memory=True)
+    labels_np = plabels.numpy()
+    prm = rss.KeyframeParams(KF["sigma_xyz"], KF["w_gauss"], KF["sigma_px"], KF["sigma_rgb"], KF["w_bilateral"],
+                             KF["iters"], KF["fill"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    import ctypes as C
+    lib = ctx._lib
+    Kp, Rp, tp = (np.ascontiguousarray(a, np.float32).reshape(-1) for a in (Kinv, R, t))
+
+    def call(rgb, depth, labels):
+        st = lib.rss_segment_keyframe(ctx.h, rss._ptr(rgb, C.c_uint8), rss._ptr(depth, C.c_uint16), W, H,
+                                      rss._ptr(Kp, C.c_float), rss._ptr(Rp, C.c_float), rss._ptr(tp, C.c_float),
+                                      C.byref(prm), rss._ptr(labels, C.c_uint8), None)
+        ctx._check(st)
+
+    # ---- warm-up (untimed)
+    for k in range(args.warmup):
+        call(frames[k % N_FRAMES][0], frames[k % N_FRAMES][1], labels_np)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---- device-resident throughput: frame k resident before the step, L2 flushed, device time from CUDA events
+    ctx.profile_enable(True)
+    launches0 = ctx.kernel_launches
+    dev_ms = 0.0
+    stage = {}
+    barrier()
+    for k in range(args.steps):
+        ctx.upload_frame(*frames[k % N_FRAMES])
+        flush.zero_()
+        torch.cuda.synchronize()
+        call(None, None, None)
+        tm = ctx.timings()
+        dev_ms += tm["total_ms"]
+        for n, v in tm.items():
+            stage[n] = stage.get(n, 0.0) + v
+    barrier()
+    launches = ctx.kernel_launches - launches0
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+
+    # ---- end to end through the C ABI with host buffers (pinned), wall clock over K synchronous calls
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        call(frames[k % N_FRAMES][0], frames[k % N_FRAMES][1], labels_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # slowest rank decides
+    times = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = times.tolist()
+
+    if rank == 0:
+        total_kf = args.steps * world
+        value = total_kf / (dev_ms_max / 1000.0)
+        e2e = total_kf / (e2e_ms_max / 1000.0)
+        peak, peak_src = peaks()
+        # dominant kernel = largest accumulated device time in the timed region
+        top = sorted(prof.items(), key=lambda kv: -kv[1][0])
+        kernel_table = [{"kernel": n, "ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
+                         "us_per_launch": 1000.0 * ms / max(cnt, 1)} for n, (ms, cnt) in top[:12]]
+        dom_name, (dom_ms, dom_cnt) = top[0]
+        N, M = W * H, 17
+        algo = ALGO_BYTES.get(dom_name)
+        roof = None
+        if algo is not None:
+            ach = algo(N, M) / (dom_ms / dom_cnt / 1000.0) / 1e9
+            roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo(N, M),
+                    "us_per_launch": 1000.0 * dom_ms / dom_cnt}
+        else:
+            roof = {"bound": "hbm", "kernel": dom_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                    "traffic": None, "peak_source": peak_src, "us_per_launch": 1000.0 * dom_ms / dom_cnt}
+        line = {
+            "metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "l2": "flushed with a 256 MiB write before every timed step",
+                       "frames": "%d distinct synthetic frames per rank" % N_FRAMES},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": W * H * 3 + W * H * 2,
+                    "d2h_bytes_per_step": 2 * W * H, "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "stages_ms_per_step": {n: v / args.steps for n, v in stage.items()},
+            "kernels": kernel_table,
+            "ms_per_meanfield_iter": stage.get("meanfield_ms", 0.0) / args.steps / KF["iters"],
+        }
+        if world == 1 and not args.no_cpu:
+            import oracle
+            oracle.build(ref=False)
+            procs = max(1, min(os.cpu_count() or 1, 32))
+            cv, cdt = cpu_throughput(procs, 1)
+            line["cpu_baseline"] = {"value": cv, "unit": "keyframes/s", "cores": procs, "kind": "port",
+                                    "sample": "%d full 640x480 keyframes, one single-thread oracle pipeline per core "
+                                              "(%.1f s)" % (procs, cdt)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu"] if args.no_cpu else [])
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -172,6 +172,10 @@ rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, const uint16_t
                                 const float Kinv[9], const float R[9], const float t[3],
                                 const rss_keyframe_params* params, uint8_t* labels, float* Q);
 
+/* Makes a frame resident on the device (H2D copy only).  Every call that takes rgb/depth_mm accepts NULL for
+ * both to work on the resident frame instead: that is how the device-resident throughput is measured. */
+rss_status rss_upload_frame(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth_mm, int W, int H);
+
 /* ---------------------------------------------------------------------------------------------------
  * Instrumentation: device time (CUDA events on the context's stream) of the stages of the last call,
  * in milliseconds, and the number of kernels this library launched since the context was created.
@@ -181,6 +185,11 @@ typedef struct {
 } rss_timings;
 rss_status rss_get_timings(const rss_ctx* ctx, rss_timings* out);
 uint64_t rss_kernel_launches(const rss_ctx* ctx);
+/* Per-kernel device times: when enabled, every launch is bracketed by CUDA events on its own stream.
+ * rss_profile_get returns entry `index` (0 .. count-1): kernel name, accumulated milliseconds, launch count;
+ * RSS_ERR_INVALID past the end.  rss_profile_enable(ctx, x) also clears the accumulated numbers. */
+rss_status rss_profile_enable(rss_ctx* ctx, int enable);
+rss_status rss_profile_get(rss_ctx* ctx, int index, char* name, int name_cap, double* total_ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

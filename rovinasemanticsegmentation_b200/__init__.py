@@ -119,6 +119,27 @@ class Context:
         self._check(self._lib.rss_get_timings(self.h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in Timings._fields_}
 
+    def upload_frame(self, rgb, depth):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        self._check(self._lib.rss_upload_frame(self.h, _ptr(rgb, C.c_uint8), _ptr(depth, C.c_uint16), W, H))
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.rss_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        """{kernel name: (total device ms, launches)} accumulated since profile_enable."""
+        out = {}
+        name = C.create_string_buffer(128)
+        ms = C.c_double(0)
+        n = C.c_uint64(0)
+        i = 0
+        while self._lib.rss_profile_get(self.h, i, name, 128, C.byref(ms), C.byref(n)) == 0:
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
+        return out
+
     # ---- FeatureExtractor::extract
     def extract_features(self, rgb, depth, Kinv, R, t, stride, dmin, dmax, extract_type=NO_LABEL, labels=None,
                          want_feats=True):

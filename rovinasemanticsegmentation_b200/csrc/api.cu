@@ -294,6 +294,8 @@ static void free_ctx(rss_ctx* ctx) {
     ctx->pin_small.release();
     for (cudaEvent_t& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    ctx->prof_collect();
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->s0) cudaStreamDestroy(ctx->s0);
@@ -384,6 +386,33 @@ extern "C" rss_status rss_get_timings(const rss_ctx* ctx, rss_timings* out) {
     return RSS_OK;
 }
 extern "C" uint64_t rss_kernel_launches(const rss_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" rss_status rss_profile_enable(rss_ctx* ctx, int enable) {
+    if (!ctx) return RSS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->prof_collect();
+    ctx->prof_acc.clear();
+    ctx->profile = enable != 0;
+    return RSS_OK;
+}
+extern "C" rss_status rss_profile_get(rss_ctx* ctx, int index, char* name, int name_cap, double* total_ms,
+                                      uint64_t* launches) {
+    if (!ctx) return RSS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->prof_collect();
+    if (index < 0 || index >= (int)ctx->prof_acc.size()) return RSS_ERR_INVALID;
+    auto it = ctx->prof_acc.begin();
+    std::advance(it, index);
+    if (name && name_cap > 0) {
+        strncpy(name, it->first.c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (total_ms) *total_ms = it->second.first;
+    if (launches) *launches = it->second.second;
+    return RSS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // frame pipeline
@@ -605,6 +634,16 @@ extern "C" rss_status rss_extract_features(rss_ctx* ctx, const uint8_t* rgb, con
         if (out_labels && labels)
             RSS_CU(ctx, cudaMemcpyAsync(out_labels, f.slabels.ptr, (size_t)n * n_label_layers * 4, cudaMemcpyDeviceToHost, ctx->s0));
     }
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_upload_frame(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth_mm, int W, int H) {
+    if (!ctx) return RSS_ERR_INVALID;
+    if (!rgb || !depth_mm) return ctx->fail(RSS_ERR_INVALID, "null frame");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    rss_status st = frame_upload(ctx, rgb, depth_mm, W, H);
+    if (st != RSS_OK) return st;
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     return RSS_OK;
 }

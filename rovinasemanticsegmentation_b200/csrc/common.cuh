@@ -4,7 +4,9 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/rss.h"
@@ -138,6 +140,31 @@ struct rss_ctx {
     uint64_t launches = 0;
     std::string err;
     rss_crf* keyframe_crf = nullptr;  // cached CRF of rss_segment_keyframe
+    // optional per-kernel timing (rss_profile_enable)
+    bool profile = false;
+    struct Pending { const char* name; cudaEvent_t a, b; };
+    std::vector<Pending> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    std::map<std::string, std::pair<double, uint64_t>> prof_acc;
+    cudaEvent_t prof_event() {
+        if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_collect() {  // call after the streams have been synchronised
+        for (Pending& p : prof_pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+                auto& acc = prof_acc[p.name];
+                acc.first += ms;
+                acc.second += 1;
+            }
+            prof_pool.push_back(p.a);
+            prof_pool.push_back(p.b);
+        }
+        prof_pending.clear();
+    }
     rss_status fail(rss_status s, const std::string& m) {
         err = m;
         return s;
@@ -152,10 +179,20 @@ struct rss_ctx {
     } while (0)
 
 // every kernel launch of the library goes through this so that rss_kernel_launches() is a real count
-#define RSS_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)   \
-    do {                                                          \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
-        (ctx)->launches++;                                        \
+#define RSS_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                  \
+    do {                                                                         \
+        cudaEvent_t pa__ = nullptr, pb__ = nullptr;                              \
+        if ((ctx)->profile) {                                                    \
+            pa__ = (ctx)->prof_event();                                          \
+            pb__ = (ctx)->prof_event();                                          \
+            cudaEventRecord(pa__, (stream));                                     \
+        }                                                                        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        (ctx)->launches++;                                                       \
+        if ((ctx)->profile) {                                                    \
+            cudaEventRecord(pb__, (stream));                                     \
+            (ctx)->prof_pending.push_back(rss_ctx::Pending{#kernel, pa__, pb__}); \
+        }                                                                        \
     } while (0)
 
 static inline int rss_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
