@@ -463,8 +463,8 @@ rss_status frame_prepare(rss_ctx* ctx, const float* Kinv, const float* R, const 
         if (cfg.use_normal) {
             RSS_CU(ctx, f.dist_a.reserve(NP * 4));
             RSS_CU(ctx, f.dist_b.reserve(NP * 4));
-            RSS_CU(ctx, f.grad.reserve(NP * 6 * 4));
-            RSS_CU(ctx, f.fin.reserve(NP * 2));
+            RSS_CU(ctx, f.grad.reserve(integral_elems(W, H) * 6 * 4));
+            RSS_CU(ctx, f.fin.reserve(integral_elems(W, H) * 2));
             RSS_CU(ctx, f.integ.reserve(integral_elems(W, H) * 6 * sizeof(double)));
             RSS_CU(ctx, f.integ_cnt.reserve(integral_elems(W, H) * 2 * sizeof(int)));
             launch_normals_prepare(ctx, ctx->s1, f.xyz.as<float4>(), W, H, f.dist_a.as<float>(), f.dist_b.as<float>(),

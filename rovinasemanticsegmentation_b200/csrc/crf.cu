@@ -18,7 +18,7 @@ namespace rss {
 float lattice_alpha(int d);
 rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp);
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
-                          int M, int Mp);
+                          int Mp);
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
                    int out_stride);
 rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch);
@@ -43,9 +43,99 @@ struct SliceArgs {
     float potts[CRF_MAX_KERNELS];
 };
 
-// expAndNormalize (densecrf.cpp:98-106) on one layer segment held in registers
+// ---------------------------------------------------------------------------------------------------------------
+// Point-parallel kernels.  Q and the unary energies are stored [N][Mp] (Mp = labels padded to a multiple of 4, pad
+// channels = 0) so that every row is 16-byte aligned.  A point is handled by a GROUP OF 8 LANES; lane g of the group
+// owns the float4 channel group g (channels 4g..4g+3).  All row accesses of a group are one contiguous 16*G-byte
+// read, and the per-layer soft-max / argmax reductions are three xor-shuffles inside the group.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float group_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ float group_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v + __shfl_xor_sync(0xffffffffu, v, 4);
+}
+// expAndNormalize (densecrf.cpp:98-106) per layer; t = this lane's four channels, c0 = 4g.  Pad channels become 0.
+__device__ __forceinline__ void softmax_layers(float (&t)[4], int c0, const LayerSpec& ls) {
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int l = 0; l < ls.n_layers; l++) {
+        const int a = ls.off[l], b = ls.off[l + 1];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (c0 + q >= a && c0 + q < b) mx = fmaxf(mx, t[q]);
+        mx = group_max(mx);
+        float e[4], s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool in = c0 + q >= a && c0 + q < b;
+            e[q] = in ? __expf(__fsub_rn(t[q], mx)) : 0.f;  // ex2.approx: |rel err| < 2e-6, tolerance is 1e-4 abs
+            s += e[q];
+        }
+        s = group_sum(s);
+        const float rs = __fdividef(1.0f, s);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (c0 + q >= a && c0 + q < b) out[q] = e[q] * rs;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) t[q] = out[q];
+}
+// gated argmax (segmenter.cpp:645-657: first label whose Q exceeds 2/M and every earlier candidate, else the layer's
+// "Unknown") or plain argmax (DenseCRF::currentMap, densecrf.cpp:200-208).  Ties resolve to the lower label, like the
+// reference's strict '>' scan.
+__device__ __forceinline__ void write_labels(const float (&q)[4], int c0, int g, const LayerSpec& ls, int i, int N,
+                                             uint8_t* __restrict__ labels) {
+    for (int l = 0; l < ls.n_layers; l++) {
+        const int a = ls.off[l], b = ls.off[l + 1];
+        const bool gated = ls.unknown[l] >= 0;
+        float bv = gated ? (float)(2.0 / (double)(b - a)) : -INFINITY;
+        int best = 1 << 20;  // "no label passed the gate"
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (c0 + k >= a && c0 + k < b && q[k] > bv) {
+                bv = q[k];
+                best = c0 + k - a;
+            }
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (ob < (1 << 20) && (best >= (1 << 20) || ov > bv || (ov == bv && ob < best))) {
+                bv = ov;
+                best = ob;
+            }
+        }
+        if (g == 0) labels[(size_t)l * N + i] = (uint8_t)(best < (1 << 20) ? best : (gated ? ls.unknown[l] : 0));
+    }
+}
+
+// Q0 = expAndNormalize(-unary)   (densecrf.cpp:120)
+__global__ void __launch_bounds__(256) softmax_init_kernel(const float* __restrict__ unary, int N, int G, int Mp,
+                                                           LayerSpec ls, float* __restrict__ Q) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(gid >> 3), g = (int)(gid & 7);
+    const bool live = i < N && g < G;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(unary + (size_t)i * Mp) + g);
+        t[0] = -u.x; t[1] = -u.y; t[2] = -u.z; t[3] = -u.w;
+    }
+    softmax_layers(t, 4 * g, ls);
+    if (live) reinterpret_cast<float4*>(Q + (size_t)i * Mp)[g] = make_float4(t[0], t[1], t[2], t[3]);
+}
+
+// One mean-field update (densecrf.cpp:123-128), ONE THREAD PER POINT:
+//   tmp = -unary;  for each kernel: tmp -= -w * (slice(values) * norm);  Q = expAndNormalize(tmp)
+// With first-appearance vertex numbering neighbouring pixels reference the same few value rows, so the 32 row
+// gathers of a warp hit a handful of cache lines (L1 resident).  All label channels of the point live in registers
+// (MP = padded channel count, compile time), rows are read as float4.
 template <int MP>
-__device__ __forceinline__ void softmax_layers(float (&t)[MP], const LayerSpec& ls) {
+__device__ __forceinline__ void softmax_regs(float (&t)[MP], const LayerSpec& ls) {
     for (int l = 0; l < ls.n_layers; l++) {
         const int a = ls.off[l], b = ls.off[l + 1];
         float mx = -INFINITY;
@@ -56,138 +146,140 @@ __device__ __forceinline__ void softmax_layers(float (&t)[MP], const LayerSpec& 
 #pragma unroll
         for (int c = 0; c < MP; c++)
             if (c >= a && c < b) {
-                t[c] = expf(__fsub_rn(t[c], mx));
-                s = __fadd_rn(s, t[c]);
+                t[c] = __expf(__fsub_rn(t[c], mx));  // ex2.approx: |rel err| < 2e-6, the tolerance is 1e-4 abs
+                s += t[c];
             }
+        const float rs = __fdividef(1.0f, s);
 #pragma unroll
         for (int c = 0; c < MP; c++)
-            if (c >= a && c < b) t[c] = __fdiv_rn(t[c], s);
+            if (c >= a && c < b) t[c] *= rs;
     }
 }
-
-// Q0 = expAndNormalize(-unary)   (densecrf.cpp:120)
-template <int MP>
-__global__ void __launch_bounds__(256) softmax_init_kernel(const float* __restrict__ unary, int N, int M, LayerSpec ls,
-                                                           float* __restrict__ Q) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float t[MP];
+template <int MP, int D1>
+__device__ __forceinline__ void slice_one(const SliceArgs& sa, int k, int i, int Mp, float (&t)[MP]) {
+    float acc[MP];
 #pragma unroll
-    for (int c = 0; c < MP; c++) t[c] = c < M ? -unary[(size_t)i * M + c] : 0.f;
-    softmax_layers<MP>(t, ls);
+    for (int c = 0; c < MP; c++) acc[c] = 0.f;
+    const int* offp = sa.offsets[k] + (size_t)i * D1;
+    const float* bp = sa.bary[k] + (size_t)i * D1;
+    const float alpha = sa.alpha[k];
+    int v[D1];
+    float w[D1];
 #pragma unroll
-    for (int c = 0; c < MP; c++)
-        if (c < M) Q[(size_t)i * M + c] = t[c];
-}
-
-// gated argmax (segmenter.cpp:645-657) or plain argmax (DenseCRF::currentMap, densecrf.cpp:200-208)
-template <int MP>
-__device__ __forceinline__ void write_labels(const float (&q)[MP], const LayerSpec& ls, int i, int N,
-                                             uint8_t* __restrict__ labels) {
-    for (int l = 0; l < ls.n_layers; l++) {
-        const int a = ls.off[l], b = ls.off[l + 1];
-        int best;
-        float bv;
-        if (ls.unknown[l] >= 0) {
-            best = ls.unknown[l];
-            bv = (float)(2.0 / (double)(b - a));
-        } else {
-            best = 0;
-            bv = -INFINITY;
+    for (int j = 0; j < D1; j++) {
+        v[j] = __ldg(offp + j);
+        w[j] = __fmul_rn(__ldg(bp + j), alpha);
+    }
+#pragma unroll
+    for (int j = 0; j < D1; j++) {
+        const float4* row = reinterpret_cast<const float4*>(sa.values[k] + (size_t)v[j] * Mp);
+#pragma unroll
+        for (int g = 0; g < MP / 4; g++) {
+            const float4 x = __ldg(row + g);
+            acc[4 * g + 0] = __fadd_rn(acc[4 * g + 0], __fmul_rn(w[j], x.x));
+            acc[4 * g + 1] = __fadd_rn(acc[4 * g + 1], __fmul_rn(w[j], x.y));
+            acc[4 * g + 2] = __fadd_rn(acc[4 * g + 2], __fmul_rn(w[j], x.z));
+            acc[4 * g + 3] = __fadd_rn(acc[4 * g + 3], __fmul_rn(w[j], x.w));
         }
+    }
+    const float nv = sa.norm[k] ? __ldg(sa.norm[k] + i) : 1.f, negw = -sa.potts[k];
 #pragma unroll
-        for (int c = 0; c < MP; c++)
-            if (c >= a && c < b && q[c] > bv) {
-                bv = q[c];
-                best = c - a;
-            }
-        labels[(size_t)l * N + i] = (uint8_t)best;
+    for (int c = 0; c < MP; c++) {
+        const float o = __fmul_rn(negw, __fmul_rn(acc[c], nv));  // pairwise.cpp:78-79, labelcompatibility.cpp:46-48
+        t[c] = __fsub_rn(t[c], o);                               // densecrf.cpp:126
     }
 }
-
-// One mean-field update for point i (densecrf.cpp:123-128):
-//   tmp = -unary;  for each kernel: tmp -= -w * ((slice(values) ) * norm);  Q = expAndNormalize(tmp)
 template <int MP>
 __global__ void __launch_bounds__(128) slice_softmax_kernel(SliceArgs sa, const float* __restrict__ unary, int N, int M,
-                                                            int Mp, LayerSpec ls, float* __restrict__ Q,
+                                                            LayerSpec ls, float* __restrict__ Q,
                                                             uint8_t* __restrict__ labels) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float t[MP];
+    const float4* up = reinterpret_cast<const float4*>(unary + (size_t)i * MP);
 #pragma unroll
-    for (int c = 0; c < MP; c++) t[c] = c < M ? -unary[(size_t)i * M + c] : 0.f;
+    for (int g = 0; g < MP / 4; g++) {
+        const float4 u = __ldg(up + g);
+        t[4 * g] = -u.x; t[4 * g + 1] = -u.y; t[4 * g + 2] = -u.z; t[4 * g + 3] = -u.w;
+    }
     for (int k = 0; k < sa.K; k++) {
         if (sa.counts[k][1]) return;  // lattice overflow: the host re-runs with a larger table
-        float acc[MP];
-#pragma unroll
-        for (int c = 0; c < MP; c++) acc[c] = 0.f;
-        const int d1 = sa.d1[k];
-        const float alpha = sa.alpha[k];
-        for (int j = 0; j < d1; j++) {
-            const int v = __ldg(sa.offsets[k] + (size_t)i * d1 + j);
-            const float w = __fmul_rn(__ldg(sa.bary[k] + (size_t)i * d1 + j), alpha);
-            const float4* row = reinterpret_cast<const float4*>(sa.values[k] + (size_t)v * Mp);
-#pragma unroll
-            for (int g = 0; g < MP / 4; g++)
-                if (4 * g < M) {
-                    const float4 x = __ldg(row + g);
-                    acc[4 * g + 0] = __fadd_rn(acc[4 * g + 0], __fmul_rn(w, x.x));
-                    acc[4 * g + 1] = __fadd_rn(acc[4 * g + 1], __fmul_rn(w, x.y));
-                    acc[4 * g + 2] = __fadd_rn(acc[4 * g + 2], __fmul_rn(w, x.z));
-                    acc[4 * g + 3] = __fadd_rn(acc[4 * g + 3], __fmul_rn(w, x.w));
-                }
-        }
-        const float nv = sa.norm[k] ? sa.norm[k][i] : 1.f, negw = -sa.potts[k];
-#pragma unroll
-        for (int c = 0; c < MP; c++) {
-            const float o = __fmul_rn(negw, __fmul_rn(acc[c], nv));  // pairwise.cpp:78-79, labelcompatibility.cpp:46-48
-            t[c] = __fsub_rn(t[c], o);                               // densecrf.cpp:126
+        switch (sa.d1[k]) {
+            case 2: slice_one<MP, 2>(sa, k, i, MP, t); break;
+            case 3: slice_one<MP, 3>(sa, k, i, MP, t); break;
+            case 4: slice_one<MP, 4>(sa, k, i, MP, t); break;
+            case 5: slice_one<MP, 5>(sa, k, i, MP, t); break;
+            case 6: slice_one<MP, 6>(sa, k, i, MP, t); break;
+            case 7: slice_one<MP, 7>(sa, k, i, MP, t); break;
+            default: slice_one<MP, 8>(sa, k, i, MP, t); break;
         }
     }
-    softmax_layers<MP>(t, ls);
+    softmax_regs<MP>(t, ls);
+    float4* qp = reinterpret_cast<float4*>(Q + (size_t)i * MP);
 #pragma unroll
-    for (int c = 0; c < MP; c++)
-        if (c < M) Q[(size_t)i * M + c] = t[c];
-    if (labels) write_labels<MP>(t, ls, i, N, labels);
+    for (int g = 0; g < MP / 4; g++)
+        qp[g] = make_float4(4 * g < M ? t[4 * g] : 0.f, 4 * g + 1 < M ? t[4 * g + 1] : 0.f, 4 * g + 2 < M ? t[4 * g + 2] : 0.f,
+                            4 * g + 3 < M ? t[4 * g + 3] : 0.f);
+    if (labels) {
+        for (int l = 0; l < ls.n_layers; l++) {
+            const int a = ls.off[l], b = ls.off[l + 1];
+            const bool gated = ls.unknown[l] >= 0;
+            float bv = gated ? (float)(2.0 / (double)(b - a)) : -INFINITY;  // segmenter.cpp:647
+            int best = gated ? ls.unknown[l] : 0;
+#pragma unroll
+            for (int c = 0; c < MP; c++)
+                if (c >= a && c < b && t[c] > bv) {
+                    bv = t[c];
+                    best = c - a;
+                }
+            labels[(size_t)l * N + i] = (uint8_t)best;
+        }
+    }
 }
-
 template <int MP>
-__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ Q, int N, int M, LayerSpec ls,
-                                                     uint8_t* __restrict__ labels) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float q[MP];
-#pragma unroll
-    for (int c = 0; c < MP; c++) q[c] = c < M ? Q[(size_t)i * M + c] : 0.f;
-    write_labels<MP>(q, ls, i, N, labels);
+static void launch_slice_softmax(rss_ctx* c, cudaStream_t st, const SliceArgs& sa, const float* unary, int N, int M,
+                                 const LayerSpec& ls, float* Q, uint8_t* labels) {
+    RSS_LAUNCH(c, slice_softmax_kernel<MP>, rss_div_up(N, 128), 128, 0, st, sa, unary, N, M, ls, Q, labels);
 }
 
-// layout helpers between the reference's per-layer matrices ([N][M_l]) and the interleaved device layout ([N][Mtot])
-__global__ void __launch_bounds__(256) interleave_kernel(const float* __restrict__ src, int N, int Ml, int Mtot, int off,
+__global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ Q, int N, int G, int Mp, LayerSpec ls,
+                                                     uint8_t* __restrict__ labels) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(gid >> 3), g = (int)(gid & 7);
+    float q[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (i < N && g < G) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(Q + (size_t)i * Mp) + g);
+        q[0] = u.x; q[1] = u.y; q[2] = u.z; q[3] = u.w;
+    }
+    if (i < N) write_labels(q, 4 * g, g, ls, i, N, labels);
+}
+
+// layout helpers between the reference's per-layer matrices ([N][M_l]) and the padded interleaved device layout
+__global__ void __launch_bounds__(256) interleave_kernel(const float* __restrict__ src, int N, int Ml, int Mp, int off,
                                                          float scale, float* __restrict__ dst) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)N * Ml) return;
     const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
-    dst[(size_t)i * Mtot + off + c] = scale * src[gid];
+    dst[(size_t)i * Mp + off + c] = scale * src[gid];
 }
-__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int N, int Ml, int Mtot, int off,
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int N, int Ml, int Mp, int off,
                                                            float* __restrict__ dst) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)N * Ml) return;
     const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
-    dst[gid] = src[(size_t)i * Mtot + off + c];
+    dst[gid] = src[(size_t)i * Mp + off + c];
 }
 // segmenter.cpp:597-616: unaries(c, idx) += posterior[pixel*C + c] for idx >= 0.  The CRF stores ENERGIES
 // (= -unaries, segmenter.cpp:642), so the log-posterior is subtracted.
 __global__ void __launch_bounds__(256) unary_accumulate_kernel(const int* __restrict__ index_image, int npix,
-                                                               const float* __restrict__ post, int Ml, int Mtot, int off,
+                                                               const float* __restrict__ post, int Ml, int Mp, int off,
                                                                int N, float* __restrict__ unary) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)npix * Ml) return;
     const int p = (int)(gid / Ml), c = (int)(gid - (long long)p * Ml);
     const int idx = index_image[p];
     if (idx < 0 || idx >= N) return;
-    atomicAdd(unary + (size_t)idx * Mtot + off + c, -post[gid]);
+    atomicAdd(unary + (size_t)idx * Mp + off + c, -post[gid]);
 }
 // feature builders: DenseCRF2D::addPairwiseGaussian / Bilateral (densecrf.cpp:61-81), segmenter.cpp:629-637
 __global__ void __launch_bounds__(256) feat_gaussian_kernel(int W, int H, float sx, float sy, float* __restrict__ f) {
@@ -230,47 +322,18 @@ __global__ void __launch_bounds__(256) feat_frame_xyz_kernel(int N, const float4
     f[3 * (size_t)p + 1] = __fmul_rn(v.y, inv_sigma);
     f[3 * (size_t)p + 2] = __fmul_rn(v.z, inv_sigma);
 }
-// posteriors [layer][pixel][C_l] -> energies [pixel][Mtot] = -posterior (segmenter.cpp:642)
-__global__ void __launch_bounds__(256) unary_from_posteriors_kernel(const float* __restrict__ post, int N, int Mtot,
+// posteriors [layer][pixel][C_l] -> energies [pixel][Mp] = -posterior (segmenter.cpp:642); pad channels = 0
+__global__ void __launch_bounds__(256) unary_from_posteriors_kernel(const float* __restrict__ post, int N, int Mtot, int Mp,
                                                                     LayerSpec ls, float* __restrict__ unary) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)N * Mtot) return;
-    const int i = (int)(gid / Mtot), c = (int)(gid - (long long)i * Mtot);
+    if (gid >= (long long)N * Mp) return;
+    const int i = (int)(gid / Mp), c = (int)(gid - (long long)i * Mp);
+    if (c >= Mtot) { unary[gid] = 0.f; return; }
     int l = 0;
     while (l + 1 < ls.n_layers && c >= ls.off[l + 1]) l++;
     const int Ml = ls.off[l + 1] - ls.off[l];
     unary[gid] = -post[(size_t)N * ls.off[l] + (size_t)i * Ml + (c - ls.off[l])];
 }
-
-template <template <int> class Launcher, typename... Args>
-static void dispatch_mp(int Mp, Args... args) {
-    switch (Mp) {
-        case 4: Launcher<4>::run(args...); break;
-        case 8: Launcher<8>::run(args...); break;
-        case 12: Launcher<12>::run(args...); break;
-        case 16: Launcher<16>::run(args...); break;
-        case 20: Launcher<20>::run(args...); break;
-        case 24: Launcher<24>::run(args...); break;
-        case 28: Launcher<28>::run(args...); break;
-        default: Launcher<32>::run(args...); break;
-    }
-}
-template <int MP> struct InitL {
-    static void run(rss_ctx* c, cudaStream_t st, const float* unary, int N, int M, LayerSpec ls, float* Q) {
-        RSS_LAUNCH(c, softmax_init_kernel<MP>, rss_div_up(N, 256), 256, 0, st, unary, N, M, ls, Q);
-    }
-};
-template <int MP> struct SliceL {
-    static void run(rss_ctx* c, cudaStream_t st, SliceArgs sa, const float* unary, int N, int M, int Mp, LayerSpec ls,
-                    float* Q, uint8_t* labels) {
-        RSS_LAUNCH(c, slice_softmax_kernel<MP>, rss_div_up(N, 128), 128, 0, st, sa, unary, N, M, Mp, ls, Q, labels);
-    }
-};
-template <int MP> struct ArgmaxL {
-    static void run(rss_ctx* c, cudaStream_t st, const float* Q, int N, int M, LayerSpec ls, uint8_t* labels) {
-        RSS_LAUNCH(c, argmax_kernel<MP>, rss_div_up(N, 256), 256, 0, st, Q, N, M, ls, labels);
-    }
-};
 
 static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
     LayerSpec ls;
@@ -284,15 +347,17 @@ static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
 rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_dev) {
     rss_ctx* ctx = crf->ctx;
     cudaStream_t s0 = ctx->s0;
-    const int N = crf->N, M = crf->Mtot, Mp = crf->Mp, K = (int)crf->kernels.size();
+    const int N = crf->N, Mp = crf->Mp, K = (int)crf->kernels.size();
     const LayerSpec ls = make_layers(crf, unknown);
     float* Q = crf->Q.as<float>();
     const float* U = crf->unary.as<float>();
-    dispatch_mp<InitL>(Mp, ctx, s0, U, N, M, ls, Q);
+    const int G = Mp / 4;
+    RSS_LAUNCH(ctx, softmax_init_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, U, N, G, Mp, ls, Q);
     if (iters <= 0 || K == 0) {
         if (iters > 0) {  // no pairwise terms: every iteration reproduces expAndNormalize(-unary)
         }
-        if (labels_dev) dispatch_mp<ArgmaxL>(Mp, ctx, s0, (const float*)Q, N, M, ls, labels_dev);
+        if (labels_dev)
+            RSS_LAUNCH(ctx, argmax_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, (const float*)Q, N, G, Mp, ls, labels_dev);
         RSS_CU(ctx, cudaGetLastError());
         return RSS_OK;
     }
@@ -306,7 +371,7 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
             if (K > 1) RSS_CU(ctx, cudaStreamWaitEvent(sk, crf->ev_fork, 0));
             const bool pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
             const bool post = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_AFTER;
-            float* vals = lattice_splat_blur(ctx, sk, L, Q, M, pre ? L.norm.as<float>() : nullptr, M, Mp);
+            float* vals = lattice_splat_blur(ctx, sk, L, Q, Mp, pre ? L.norm.as<float>() : nullptr, Mp);
             if (K > 1) RSS_CU(ctx, cudaEventRecord(crf->ev_join[k], sk));
             sa.offsets[k] = L.offsets.as<int>();
             sa.bary[k] = L.bary.as<float>();
@@ -319,7 +384,17 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
         }
         if (K > 1)
             for (int k = 0; k < K; k++) RSS_CU(ctx, cudaStreamWaitEvent(s0, crf->ev_join[k], 0));
-        dispatch_mp<SliceL>(Mp, ctx, s0, sa, U, N, M, Mp, ls, Q, (it == iters - 1) ? labels_dev : (uint8_t*)nullptr);
+        uint8_t* lab = (it == iters - 1) ? labels_dev : (uint8_t*)nullptr;
+        switch (Mp) {
+            case 4: launch_slice_softmax<4>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            case 8: launch_slice_softmax<8>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            case 12: launch_slice_softmax<12>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            case 16: launch_slice_softmax<16>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            case 20: launch_slice_softmax<20>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            case 24: launch_slice_softmax<24>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            case 28: launch_slice_softmax<28>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+            default: launch_slice_softmax<32>(ctx, s0, sa, U, N, crf->Mtot, ls, Q, lab); break;
+        }
     }
     RSS_CU(ctx, cudaGetLastError());
     return RSS_OK;
@@ -350,7 +425,7 @@ rss_status crf_add_kernel_dev(rss_crf* crf, const float* feat_dev, int d, float 
     const uint64_t maxv = (uint64_t)crf->N * (d + 1);
     uint32_t hcap = next_pow2(std::min<uint64_t>(2 * maxv, 1u << 17));
     if (L->hcap > hcap && L->d == d) hcap = L->hcap;
-    RSS_CU(ctx, crf->scratch.reserve((size_t)crf->N * crf->Mp * 4));
+    RSS_CU(ctx, crf->scratch.reserve((size_t)crf->N * (crf->Mp + 4) * 4));
     for (;;) {
         rss_status st = lattice_build(ctx, ctx->s0, *L, feat_dev, crf->N, d, hcap, crf->Mp);
         if (st != RSS_OK) return st;
@@ -405,11 +480,11 @@ rss_status crf_new(rss_ctx* ctx, int N, int n_layers, const int* M, rss_crf** ou
     crf->Mtot = off;
     crf->Mp = (off + 3) / 4 * 4;
     if (crf->Mp > CRF_MAX_CH) { delete crf; return ctx->fail(RSS_ERR_INVALID, "more than 32 labels in total are not supported"); }
-    cudaError_t e = crf->unary.reserve((size_t)N * off * 4);
-    if (e == cudaSuccess) e = crf->Q.reserve((size_t)N * off * 4);
+    cudaError_t e = crf->unary.reserve((size_t)N * crf->Mp * 4);
+    if (e == cudaSuccess) e = crf->Q.reserve((size_t)N * crf->Mp * 4);
     if (e == cudaSuccess) e = crf->labels.reserve((size_t)N * n_layers);
-    if (e == cudaSuccess) e = crf->scratch.reserve((size_t)N * crf->Mp * 4);
-    if (e == cudaSuccess) e = cudaMemsetAsync(crf->unary.ptr, 0, (size_t)N * off * 4, ctx->s0);
+    if (e == cudaSuccess) e = crf->scratch.reserve((size_t)N * (crf->Mp + 4) * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(crf->unary.ptr, 0, (size_t)N * crf->Mp * 4, ctx->s0);
     for (int k = 0; k < 4 && e == cudaSuccess; k++) {
         e = cudaStreamCreateWithFlags(&crf->side[k], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&crf->ev_join[k], cudaEventDisableTiming);
@@ -450,7 +525,7 @@ extern "C" rss_status rss_crf_set_unary(rss_crf* crf, int layer, const float* U)
     const int Ml = crf->M[layer];
     RSS_CU(ctx, cudaMemcpyAsync(crf->scratch.ptr, U, (size_t)crf->N * Ml * 4, cudaMemcpyHostToDevice, ctx->s0));
     RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)crf->N * Ml, 256), 256, 0, ctx->s0, crf->scratch.as<float>(),
-               crf->N, Ml, crf->Mtot, crf->moff[layer], 1.0f, crf->unary.as<float>());
+               crf->N, Ml, crf->Mp, crf->moff[layer], 1.0f, crf->unary.as<float>());
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     crf->unary_set = true;
     return RSS_OK;
@@ -520,11 +595,16 @@ extern "C" rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     Lattice& L = *crf->kernels[k];
     const int N = crf->N, M = crf->Mtot, Mp = crf->Mp;
-    float* buf = crf->scratch.as<float>();
-    RSS_CU(ctx, cudaMemcpyAsync(buf, in, (size_t)N * M * 4, cudaMemcpyHostToDevice, ctx->s0));
-    float* vals = lattice_splat_blur(ctx, ctx->s0, L, buf, M, nullptr, M, Mp);
-    lattice_slice(ctx, ctx->s0, L, vals, M, Mp, M <= 2 ? 1 : 0, buf, M);
-    RSS_CU(ctx, cudaMemcpyAsync(out, buf, (size_t)N * M * 4, cudaMemcpyDeviceToHost, ctx->s0));
+    // scratch: [N][Mp] padded input, followed by the [N][M] host-layout staging area
+    float* padded = crf->scratch.as<float>();
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * M * 4));
+    float* stage = crf->feat_stage.as<float>();
+    RSS_CU(ctx, cudaMemsetAsync(padded, 0, (size_t)N * Mp * 4, ctx->s0));
+    RSS_CU(ctx, cudaMemcpyAsync(stage, in, (size_t)N * M * 4, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)N * M, 256), 256, 0, ctx->s0, stage, N, M, Mp, 0, 1.0f, padded);
+    float* vals = lattice_splat_blur(ctx, ctx->s0, L, padded, Mp, nullptr, Mp);
+    lattice_slice(ctx, ctx->s0, L, vals, M, Mp, M <= 2 ? 1 : 0, stage, M);
+    RSS_CU(ctx, cudaMemcpyAsync(out, stage, (size_t)N * M * 4, cudaMemcpyDeviceToHost, ctx->s0));
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     return RSS_OK;
 }
@@ -552,16 +632,14 @@ extern "C" rss_status rss_crf_inference(rss_crf* crf, int layer, int iters, floa
             float* dstQ = Q;
             for (int l = 0; l < crf->n_layers; l++) {
                 RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0,
-                           crf->Q.as<float>(), N, crf->M[l], crf->Mtot, crf->moff[l], crf->scratch.as<float>());
+                           crf->Q.as<float>(), N, crf->M[l], crf->Mp, crf->moff[l], crf->scratch.as<float>());
                 RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
                 RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
                 dstQ += (size_t)N * crf->M[l];
             }
-        } else if (crf->n_layers == 1) {
-            RSS_CU(ctx, cudaMemcpyAsync(Q, crf->Q.ptr, (size_t)N * crf->Mtot * 4, cudaMemcpyDeviceToHost, ctx->s0));
         } else {
             RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[layer], 256), 256, 0, ctx->s0,
-                       crf->Q.as<float>(), N, crf->M[layer], crf->Mtot, crf->moff[layer], crf->scratch.as<float>());
+                       crf->Q.as<float>(), N, crf->M[layer], crf->Mp, crf->moff[layer], crf->scratch.as<float>());
             RSS_CU(ctx, cudaMemcpyAsync(Q, crf->scratch.ptr, (size_t)N * crf->M[layer] * 4, cudaMemcpyDeviceToHost, ctx->s0));
         }
     }
@@ -585,7 +663,7 @@ extern "C" rss_status rss_crf_unary_reset(rss_crf* crf) {
     if (!crf) return RSS_ERR_INVALID;
     rss_ctx* ctx = crf->ctx;
     RSS_CU(ctx, cudaSetDevice(ctx->device));
-    RSS_CU(ctx, cudaMemsetAsync(crf->unary.ptr, 0, (size_t)crf->N * crf->Mtot * 4, ctx->s0));
+    RSS_CU(ctx, cudaMemsetAsync(crf->unary.ptr, 0, (size_t)crf->N * crf->Mp * 4, ctx->s0));
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     return RSS_OK;
 }
@@ -612,7 +690,7 @@ extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx,
     }
     for (int l = 0; l < crf->n_layers; l++) {
         RSS_LAUNCH(ctx, unary_accumulate_kernel, rss_div_up((long long)npix * crf->M[l], 256), 256, 0, ctx->s0, idx_dev, npix,
-                   post_dev + (size_t)npix * crf->moff[l], crf->M[l], crf->Mtot, crf->moff[l], crf->N, crf->unary.as<float>());
+                   post_dev + (size_t)npix * crf->moff[l], crf->M[l], crf->Mp, crf->moff[l], crf->N, crf->unary.as<float>());
     }
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     crf->unary_set = true;
@@ -650,8 +728,8 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     // previous lattices are rebuilt in place (their buffers are reused): the 5-D one first so that pops match
     while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
     LayerSpec ls = make_layers(crf, nullptr);
-    RSS_LAUNCH(ctx, unary_from_posteriors_kernel, rss_div_up((long long)N * crf->Mtot, 256), 256, 0, ctx->s0,
-               ctx->fr.posteriors.as<float>(), N, crf->Mtot, ls, crf->unary.as<float>());
+    RSS_LAUNCH(ctx, unary_from_posteriors_kernel, rss_div_up((long long)N * crf->Mp, 256), 256, 0, ctx->s0,
+               ctx->fr.posteriors.as<float>(), N, crf->Mtot, crf->Mp, ls, crf->unary.as<float>());
     cudaEventRecord(ctx->ev[8], ctx->s0);
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * 8 * 4));
     float* f3 = crf->feat_stage.as<float>();
@@ -675,7 +753,7 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
         float* dstQ = Qout;
         for (int l = 0; l < crf->n_layers; l++) {
             RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, crf->Q.as<float>(),
-                       N, crf->M[l], crf->Mtot, crf->moff[l], crf->scratch.as<float>());
+                       N, crf->M[l], crf->Mp, crf->moff[l], crf->scratch.as<float>());
             RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
             RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
             dstQ += (size_t)N * crf->M[l];

@@ -93,6 +93,7 @@ template <int D>
 __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restrict__ feat, int N, ScaleFactors sf,
                                                             Key128* __restrict__ table, uint32_t mask,
                                                             int* __restrict__ offsets, float* __restrict__ bary_out,
+                                                            uint32_t* __restrict__ first_ref,
                                                             uint32_t* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -170,28 +171,37 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
         }
         const int slot = hash_insert(table, mask, key_pack<D>(key), counts);
         if (slot < 0) counts[1] = 1u;
+        else atomicMin(first_ref + slot, (uint32_t)i * (D + 1) + rem);  // first (point, corner) pair that touches the vertex
         offsets[(size_t)i * (D + 1) + rem] = slot;
         bary_out[(size_t)i * (D + 1) + rem] = bary[rem];
     }
 }
 
-// occupancy flags -> (scan) -> slot_id; then compact the keys and rewrite offsets from slots to vertex ids
-__global__ void __launch_bounds__(256) table_flags_kernel(const Key128* __restrict__ table, uint32_t hcap,
-                                                          uint32_t* __restrict__ flags) {
-    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= hcap) return;
-    flags[h] = key_eq(load_key(table + h), key_empty()) ? 0u : 1u;
+// Vertex numbering in order of first appearance in the point sequence - the numbering the reference's serial hash
+// table produces (permutohedral.cpp:118-120).  Besides making offsets comparable with the reference one to one, it
+// is what makes the filter cache friendly: consecutive points (neighbouring pixels) share vertices, so vertices that
+// are close in the lattice get close ids, and the value rows a warp gathers sit in a few cache lines.
+//   flag[k] = 1 iff pair k is the first to touch its vertex;  id = exclusive_scan(flag)[k] for those pairs.
+__global__ void __launch_bounds__(256) first_flags_kernel(const int* __restrict__ offsets, size_t n,
+                                                          const uint32_t* __restrict__ first_ref,
+                                                          const uint32_t* __restrict__ counts, uint32_t* __restrict__ flags) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    flags[k] = (!counts[1] && first_ref[offsets[k]] == (uint32_t)k) ? 1u : 0u;
 }
-__global__ void __launch_bounds__(256) table_compact_kernel(const Key128* __restrict__ table, uint32_t hcap,
-                                                            const uint32_t* __restrict__ slot_id, uint32_t vcap,
-                                                            Key128* __restrict__ vkeys, uint32_t* __restrict__ counts) {
-    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= hcap) return;
-    const Key128 k = load_key(table + h);
-    if (key_eq(k, key_empty())) return;
-    const uint32_t id = slot_id[h];
-    if (id >= vcap) { counts[1] = 1u; return; }  // load factor above 1/2: ask the host for a bigger table
-    vkeys[id] = k;
+__global__ void __launch_bounds__(256) assign_ids_kernel(const int* __restrict__ offsets, size_t n,
+                                                         const uint32_t* __restrict__ first_ref,
+                                                         const uint32_t* __restrict__ rank, const Key128* __restrict__ table,
+                                                         uint32_t vcap, uint32_t* __restrict__ slot_id,
+                                                         Key128* __restrict__ vkeys, uint32_t* __restrict__ counts) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || counts[1]) return;
+    const int slot = offsets[k];
+    if (first_ref[slot] != (uint32_t)k) return;
+    const uint32_t id = rank[k];
+    slot_id[slot] = id;
+    if (id < vcap) vkeys[id] = load_key(table + slot);
+    else counts[1] = 1u;  // load factor above 1/2: the host retries with a bigger table
 }
 __global__ void __launch_bounds__(256) remap_offsets_kernel(int* __restrict__ offsets, size_t n,
                                                             const uint32_t* __restrict__ slot_id,
@@ -262,43 +272,81 @@ __global__ void __launch_bounds__(256) seg_fill_kernel(const uint32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- filter stages
-// splat (:545-553): values[v] += w * in[p] for every (p, corner) pair of vertex v.  `in` is Q, optionally scaled by
-// norm[p] first (DenseKernel::filter pre-scaling, pairwise.cpp:65-66).  One thread per (segment, float4 group).
-__global__ void __launch_bounds__(256) splat_kernel(const int* __restrict__ seg_v, const uint32_t* __restrict__ seg_begin,
+// splat (:545-553): values[v] += w * in[p] for every (p, corner) pair of vertex v.  `in` rows are in_stride floats
+// (a multiple of 4, 16-byte aligned), optionally scaled by norm[p] first (DenseKernel::filter, pairwise.cpp:65-66).
+// One warp per segment of <= 32 nonzeros: the lanes first load the segment's (point, weight, norm) triples with
+// three coalesced loads, then the warp walks the nonzeros four at a time - 8 lanes per nonzero, lane g of a group
+// reading the float4 channel group g of that point's row, i.e. one contiguous 16*G-byte read per nonzero.
+// Partial sums are combined with two xor-shuffles and leave as one RED.ADD.F32x4 per channel group.
+__global__ void __launch_bounds__(512) splat_kernel(const int* __restrict__ seg_v, const uint32_t* __restrict__ seg_begin,
                                                     const uint32_t* __restrict__ seg_end, const uint32_t* __restrict__ counts,
                                                     const int* __restrict__ csr_pt, const float* __restrict__ csr_w,
                                                     const float* __restrict__ in, int in_stride,
-                                                    const float* __restrict__ norm, int M, int Mp,
+                                                    const float* __restrict__ norm, int G, int Mp,
                                                     float* __restrict__ values) {
-    const int G = Mp >> 2;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // Persistent CTAs, each sweeping one CONTIGUOUS range of segments: consecutive segments belong to consecutive
+    // vertices (numbered by first appearance = spatially coherent), which reference the same points, so the Q rows
+    // fetched for one vertex are still in this SM's L1 when the neighbouring vertices need them.
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (counts[1]) return;
     const uint32_t nseg = counts[2];
-    if (counts[1] || gid >= (long long)nseg * G) return;
-    const uint32_t s = (uint32_t)(gid / G);
-    const int g = (int)(gid - (long long)s * G);
-    const int c0 = 4 * g;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t b = seg_begin[s], e = seg_end[s];
-    for (uint32_t k = b; k < e; k++) {
-        const int p = __ldg(csr_pt + k);
-        const float w = __ldg(csr_w + k);
-        const float nv = norm ? __ldg(norm + p) : 1.f;
-        const float* row = in + (size_t)p * in_stride + c0;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-            if (c0 + c < M) {
-                float x = __ldg(row + c);
-                if (norm) x = __fmul_rn(x, nv);
-                acc[c] = __fadd_rn(acc[c], __fmul_rn(w, x));
-            }
+    const uint32_t per = (nseg + gridDim.x - 1) / gridDim.x;
+    const uint32_t s_begin = blockIdx.x * per, s_end = min(nseg, s_begin + per);
+    const int sub = lane >> 3, g = lane & 7;
+    for (uint32_t warp = s_begin + wib; warp < s_end; warp += wpb) {
+    const uint32_t b = seg_begin[warp], e = seg_end[warp];
+    const int n = (int)(e - b);
+    int p = 0;
+    float w = 0.f, nv = 1.f;
+    if (lane < n) {
+        p = __ldg(csr_pt + b + lane);
+        w = __ldg(csr_w + b + lane);
+        if (norm) nv = __ldg(norm + p);
     }
-    float* dst = values + (size_t)seg_v[s] * Mp + c0;
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]),
-                 "f"(acc[3])
-                 : "memory");
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < SPLAT_SEG / 4; it++) {
+        const int idx = it * 4 + sub;
+        const int pp = __shfl_sync(0xffffffffu, p, idx);
+        const float ww = __shfl_sync(0xffffffffu, w, idx);
+        const float nn = __shfl_sync(0xffffffffu, nv, idx);
+        if (idx < n && g < G) {
+            float4 x = __ldg(reinterpret_cast<const float4*>(in + (size_t)pp * in_stride) + g);
+            if (norm) {
+                x.x = __fmul_rn(x.x, nn); x.y = __fmul_rn(x.y, nn); x.z = __fmul_rn(x.z, nn); x.w = __fmul_rn(x.w, nn);
+            }
+            acc.x = __fadd_rn(acc.x, __fmul_rn(ww, x.x));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(ww, x.y));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(ww, x.z));
+            acc.w = __fadd_rn(acc.w, __fmul_rn(ww, x.w));
+        }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane < G) {
+        float* dst = values + (size_t)seg_v[warp] * Mp + 4 * lane;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z),
+                     "f"(acc.w)
+                     : "memory");
+    }
+    }
 }
 
 // blur along one axis (:555-569): new[v] = old[v] + 0.5 * (old[n1] + old[n2]); a missing neighbour is the zero row
+__device__ __forceinline__ float4 blur_item(const float4 o, const float4 a, const float4 b) {
+    float4 r;
+    r.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(a.x, b.x)));
+    r.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(a.y, b.y)));
+    r.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(a.z, b.z)));
+    r.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(a.w, b.w)));
+    return r;
+}
+// one launch per axis: the large-lattice path (value tables beyond L2 reach of one cluster)
 __global__ void __launch_bounds__(256) blur_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                                    const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
                                                    int G) {
@@ -308,13 +356,53 @@ __global__ void __launch_bounds__(256) blur_kernel(const float4* __restrict__ sr
     const uint32_t v = (uint32_t)(gid / G);
     const int g = (int)(gid - (long long)v * G);
     const int2 nb = __ldg(nbr + v);
-    const float4 o = src[(size_t)v * G + g], a = src[(size_t)nb.x * G + g], b = src[(size_t)nb.y * G + g];
-    float4 r;
-    r.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(a.x, b.x)));
-    r.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(a.y, b.y)));
-    r.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(a.z, b.z)));
-    r.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(a.w, b.w)));
-    dst[(size_t)v * G + g] = r;
+    dst[(size_t)v * G + g] = blur_item(src[(size_t)v * G + g], src[(size_t)nb.x * G + g], src[(size_t)nb.y * G + g]);
+}
+__global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p, const uint32_t* __restrict__ counts, int G) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < (long long)counts[0] * G) p[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// All d+1 axes in ONE launch for lattices whose value table is L2 resident (the single-frame regime: 10^3..10^5
+// vertices, where a per-axis launch is pure launch latency).  A persistent grid of co-resident CTAs (cooperative
+// launch, one CTA per SM) walks the table; between axes the CTAs meet at a grid barrier built on one L2 counter
+// (monotonic target, so it never needs resetting).  Value reads use ld.global.cg: the rows were written by other SMs
+// one axis earlier and must come from L2, not from a stale L1 line.  After the last axis the table that does NOT hold
+// the result is zeroed: it is the next iteration's splat target, so an iteration needs no memset launch.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(512) blur_coop_kernel(float4* __restrict__ a, float4* __restrict__ b,
+                                                        const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
+                                                        int G, int d1, uint32_t vcap, unsigned int* barrier,
+                                                        unsigned int barrier_base) {
+    const uint32_t V = counts[1] ? 0u : counts[0];
+    const uint32_t items = V * (uint32_t)G;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    float4* src = a;
+    float4* dst = b;
+    for (int j = 0; j < d1; j++) {
+        const int2* nb_j = nbr + (size_t)j * vcap;
+        for (uint32_t it = tid; it < items; it += nthr) {
+            const uint32_t v = it / (uint32_t)G, g = it - v * (uint32_t)G;
+            const int2 nb = __ldg(nb_j + v);
+            const float4 o = __ldcg(src + it), x = __ldcg(src + (size_t)nb.x * G + g), y = __ldcg(src + (size_t)nb.y * G + g);
+            __stcg(dst + it, blur_item(o, x, y));
+        }
+        grid_barrier(barrier, barrier_base + (unsigned int)(j + 1) * gridDim.x);
+        float4* t = src; src = dst; dst = t;
+    }
+    // src holds the result; dst becomes the next splat target
+    for (uint32_t it = tid; it < items; it += nthr) __stcg(dst + it, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 // plain slice (:571-584) for rss_crf_filter and the normalisation pass; seq selects the scalar path's
@@ -371,7 +459,8 @@ static ScaleFactors make_scale_factors(int d) {
 template <int D>
 static void launch_embed(rss_ctx* c, cudaStream_t st, const float* feat, int N, Lattice& L) {
     RSS_LAUNCH(c, lattice_embed_kernel<D>, rss_div_up(N, 256), 256, 0, st, feat, N, make_scale_factors(D),
-               L.table.as<Key128>(), L.hcap - 1, L.offsets.as<int>(), L.bary.as<float>(), L.counts.as<uint32_t>());
+               L.table.as<Key128>(), L.hcap - 1, L.offsets.as<int>(), L.bary.as<float>(), L.first_ref.as<uint32_t>(),
+               L.counts.as<uint32_t>());
 }
 template <int D>
 static void launch_neighbors(rss_ctx* c, cudaStream_t st, Lattice& L) {
@@ -392,6 +481,8 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     L.maxseg = (uint32_t)(nnz / SPLAT_SEG + L.vcap + 1);
     RSS_CU(ctx, L.table.reserve((size_t)hcap * sizeof(Key128)));
     RSS_CU(ctx, L.slot_id.reserve((size_t)hcap * 4));
+    RSS_CU(ctx, L.first_ref.reserve((size_t)hcap * 4));
+    RSS_CU(ctx, L.rank.reserve((nnz + 8) * 4));
     RSS_CU(ctx, L.vkeys.reserve((size_t)L.vcap * sizeof(Key128)));
     RSS_CU(ctx, L.offsets.reserve(nnz * 4));
     RSS_CU(ctx, L.bary.reserve(nnz * 4));
@@ -408,13 +499,17 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     RSS_CU(ctx, L.seg_end.reserve((size_t)L.maxseg * 4));
     RSS_CU(ctx, L.val_a.reserve((size_t)(L.vcap + 1) * Mp * 4));
     RSS_CU(ctx, L.val_b.reserve((size_t)(L.vcap + 1) * Mp * 4));
-    RSS_CU(ctx, L.scan_tmp.reserve((scan_tmp_elems(hcap) + 8) * 4));
+    RSS_CU(ctx, L.scan_tmp.reserve((scan_tmp_elems(nnz > hcap ? nnz : hcap) + 8) * 4));
     uint32_t* counts = L.counts.as<uint32_t>();
     RSS_CU(ctx, cudaMemsetAsync(L.table.ptr, 0xFF, (size_t)hcap * sizeof(Key128), st));
+    RSS_CU(ctx, cudaMemsetAsync(L.first_ref.ptr, 0xFF, (size_t)hcap * 4, st));
     RSS_CU(ctx, cudaMemsetAsync(counts, 0, 64, st));
     RSS_CU(ctx, cudaMemsetAsync(L.deg.ptr, 0, (size_t)(L.vcap + 2) * 4, st));
     RSS_CU(ctx, cudaMemsetAsync(L.cursor.ptr, 0, (size_t)(L.vcap + 1) * 4, st));
+    RSS_CU(ctx, cudaMemsetAsync(L.val_a.ptr, 0, (size_t)(L.vcap + 1) * Mp * 4, st));
     RSS_CU(ctx, cudaMemsetAsync(L.val_b.ptr, 0, (size_t)(L.vcap + 1) * Mp * 4, st));
+    L.splat_target = 0;
+    L.barrier_base = 0;
     switch (d) {
         case 1: launch_embed<1>(ctx, st, feat, N, L); break;
         case 2: launch_embed<2>(ctx, st, feat, N, L); break;
@@ -424,13 +519,14 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
         case 6: launch_embed<6>(ctx, st, feat, N, L); break;
         default: launch_embed<7>(ctx, st, feat, N, L); break;
     }
-    // vertex numbering: slot -> id by an exclusive scan of the occupancy flags; counts[0] = V
-    RSS_LAUNCH(ctx, table_flags_kernel, rss_div_up(hcap, 256), 256, 0, st, L.table.as<Key128>(), hcap,
-               L.slot_id.as<uint32_t>());
-    exclusive_scan_u32(L.slot_id.as<uint32_t>(), L.slot_id.as<uint32_t>(), hcap, L.scan_tmp.as<uint32_t>(), counts, st,
+    // vertex numbering by first appearance: flags over the (point, corner) pairs -> exclusive scan; counts[0] = V
+    RSS_LAUNCH(ctx, first_flags_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
+               L.first_ref.as<uint32_t>(), counts, L.rank.as<uint32_t>());
+    exclusive_scan_u32(L.rank.as<uint32_t>(), L.rank.as<uint32_t>(), nnz, L.scan_tmp.as<uint32_t>(), counts, st,
                        &ctx->launches);
-    RSS_LAUNCH(ctx, table_compact_kernel, rss_div_up(hcap, 256), 256, 0, st, L.table.as<Key128>(), hcap,
-               L.slot_id.as<uint32_t>(), L.vcap, L.vkeys.as<Key128>(), counts);
+    RSS_LAUNCH(ctx, assign_ids_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
+               L.first_ref.as<uint32_t>(), L.rank.as<uint32_t>(), L.table.as<Key128>(), L.vcap, L.slot_id.as<uint32_t>(),
+               L.vkeys.as<Key128>(), counts);
     RSS_LAUNCH(ctx, remap_offsets_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
                L.slot_id.as<uint32_t>(), L.deg.as<uint32_t>(), counts, L.vcap);
     switch (d) {
@@ -458,23 +554,51 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     return RSS_OK;
 }
 
-// splat -> (d+1) blurs; returns the table holding the blurred values.  in: [N][in_stride], M live channels.
+// splat -> (d+1) blurs; returns the table holding the blurred values.  in: [N][in_stride] (in_stride % 4 == 0).
+// Invariant: L.splat_target is all zero on entry; on exit the other table is (or becomes) the next target.
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
-                          int M, int Mp) {
-    const int G = Mp / 4;
-    float* a = L.val_a.as<float>();
-    float* b = L.val_b.as<float>();
-    cudaMemsetAsync(a, 0, (size_t)(L.vcap + 1) * Mp * 4, st);
-    const long long items = (long long)L.maxseg * G;
-    RSS_LAUNCH(ctx, splat_kernel, rss_div_up(items, 256), 256, 0, st, L.seg_v.as<int>(), L.seg_begin.as<uint32_t>(),
-               L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_pt.as<int>(), L.csr_w.as<float>(), in, in_stride,
-               norm, M, Mp, a);
-    for (int j = 0; j <= L.d; j++) {
-        RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st, reinterpret_cast<const float4*>(a),
-                   reinterpret_cast<float4*>(b), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), G);
-        float* t = a; a = b; b = t;
+                          int Mp) {
+    const int G = Mp / 4, d1 = L.d + 1;
+    float* a = L.splat_target ? L.val_b.as<float>() : L.val_a.as<float>();
+    float* b = L.splat_target ? L.val_a.as<float>() : L.val_b.as<float>();
+    RSS_LAUNCH(ctx, splat_kernel, ctx->sm_count * 4, 512, 0, st, L.seg_v.as<int>(),
+               L.seg_begin.as<uint32_t>(), L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_pt.as<int>(),
+               L.csr_w.as<float>(), in, in_stride, norm, G, Mp, a);
+    const bool small = (size_t)L.vcap * G <= (size_t)BLUR_COOP_MAX_ITEMS;
+    if (small) {
+        float4* pa = reinterpret_cast<float4*>(a);
+        float4* pb = reinterpret_cast<float4*>(b);
+        const int2* pn = L.nbr.as<int2>();
+        const uint32_t* pc = L.counts.as<uint32_t>();
+        int Garg = G, d1arg = d1;
+        uint32_t vc = L.vcap;
+        unsigned int* bar = L.counts.as<unsigned int>() + 8;  // counts[8]: the barrier word, zeroed at build time
+        const int grid = ctx->sm_count;
+        unsigned int base = L.barrier_base;
+        L.barrier_base += (unsigned int)d1 * (unsigned int)grid;
+        void* args[] = {&pa, &pb, &pn, &pc, &Garg, &d1arg, &vc, &bar, &base};
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        if (ctx->profile) { ea = ctx->prof_event(); eb = ctx->prof_event(); cudaEventRecord(ea, st); }
+        cudaLaunchCooperativeKernel((const void*)blur_coop_kernel, dim3(grid), dim3(512), args, 0, st);
+        ctx->launches++;
+        if (ctx->profile) { cudaEventRecord(eb, st); ctx->prof_pending.push_back(rss_ctx::Pending{"blur_coop_kernel", ea, eb}); }
+    } else {
+        float* s = a;
+        float* d = b;
+        for (int j = 0; j < d1; j++) {
+            RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st,
+                       reinterpret_cast<const float4*>(s), reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap,
+                       L.counts.as<uint32_t>(), G);
+            float* t = s; s = d; d = t;
+        }
+        RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st, reinterpret_cast<float4*>(d),
+                   L.counts.as<uint32_t>(), G);
     }
-    return a;
+    // after d1 swaps the result is in `a` when d1 is even, else in `b`; the other one was zeroed
+    float* result = (d1 % 2 == 0) ? a : b;
+    float* next_target = (d1 % 2 == 0) ? b : a;
+    L.splat_target = next_target == L.val_b.as<float>() ? 1 : 0;
+    return result;
 }
 
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
@@ -484,15 +608,15 @@ void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* value
 }
 
 // norm_ = 1/sqrt(K 1 + 1e-20) through the scalar path (pairwise.cpp:44,54-57; permutohedral.cpp:600-601)
-rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch /* [N] */) {
+rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch /* [N][4] */) {
     const int N = L.N;
     float* norm = L.norm.as<float>();
     if (L.norm_type == RSS_NO_NORMALIZATION) {
         return ctx->fail(RSS_ERR_INVALID, "NO_NORMALIZATION is not supported on the device path");
     }
-    RSS_LAUNCH(ctx, fill_f32_kernel, rss_div_up(N, 256), 256, 0, st, ones_scratch, (size_t)N, 1.0f);
-    // value tables were allocated for the CRF's Mp >= 4; run the one-channel filter with Mp = 4
-    float* vals = lattice_splat_blur(ctx, st, L, ones_scratch, 1, nullptr, 1, 4);
+    RSS_LAUNCH(ctx, fill_f32_kernel, rss_div_up((long long)N * 4, 256), 256, 0, st, ones_scratch, (size_t)N * 4, 1.0f);
+    // value tables were allocated for the CRF's Mp >= 4; run the filter on four identical all-ones channels
+    float* vals = lattice_splat_blur(ctx, st, L, ones_scratch, 4, nullptr, 4);
     lattice_slice(ctx, st, L, vals, 1, 4, 1, norm, 1);
     RSS_LAUNCH(ctx, norm_kernel, rss_div_up(N, 256), 256, 0, st, norm, N, L.norm_type);
     // the ping-pong partner must have a zero "missing neighbour" row again for the CRF's own Mp

@@ -5,7 +5,8 @@
 namespace rss {
 
 constexpr int LAT_MAX_D = 7;   // feature dimensions; keys are d int16 packed into 128 bits (one spare lane)
-constexpr int SPLAT_SEG = 32;  // nonzeros per splat work item
+constexpr int SPLAT_SEG = 32;  // nonzeros per splat work item (one warp)
+constexpr int BLUR_COOP_MAX_ITEMS = 1 << 20;  // float4 items (vcap * Mp/4) up to which the one-launch blur is used
 
 struct __align__(16) Key128 {
     unsigned long long lo, hi;
@@ -21,13 +22,15 @@ struct Lattice {
     uint32_t vcap = 0;   // vertex capacity = hcap / 2
     int V_host = -1;     // vertex count once read back (diagnostics)
     DevBuf table;        // Key128[hcap]
-    DevBuf slot_id;      // uint32[hcap]   slot -> vertex id (exclusive scan of occupancy)
+    DevBuf slot_id;      // uint32[hcap]   slot -> vertex id
+    DevBuf first_ref;    // uint32[hcap]   smallest (point, corner) pair index touching the slot
+    DevBuf rank;         // uint32[N*(d+1)] first-appearance flags, then their exclusive scan
     DevBuf vkeys;        // Key128[vcap]   vertex id -> key
     DevBuf offsets;      // int  [N][d+1]  vertex id of each enclosing-simplex corner
     DevBuf bary;         // float[N][d+1]
     DevBuf nbr;          // int2 [d+1][vcap]  blur neighbours (n1, n2); missing -> zero row (index = vcap)
     DevBuf norm;         // float[N]
-    DevBuf counts;       // uint32[8]: [0] V, [1] overflow flag, [2] segments, [3] inserted
+    DevBuf counts;       // uint32[16]: [0] V, [1] overflow flag, [2] segments, [3] inserted, [4] seg total, [8] barrier
     DevBuf deg;          // uint32[vcap+1]  row degree, then row_start (in-place scan)
     DevBuf cursor;       // uint32[vcap]
     DevBuf nseg;         // uint32[vcap+1]  segments per row, then segment offsets
@@ -39,8 +42,10 @@ struct Lattice {
     DevBuf val_a, val_b; // float[(vcap+1)][Mp] ping-pong value tables (row vcap stays zero)
     DevBuf scan_tmp;
     uint32_t maxseg = 0;
+    int splat_target = 0;  // which value table is all-zero and receives the next splat (0 = val_a)
+    unsigned int barrier_base = 0;  // grid-barrier arrivals issued so far (counts[8] is the barrier word)
     void release() {
-        DevBuf* b[] = {&table, &slot_id, &vkeys, &offsets, &bary, &nbr, &norm, &counts, &deg, &cursor, &nseg,
+        DevBuf* b[] = {&table, &slot_id, &first_ref, &rank, &vkeys, &offsets, &bary, &nbr, &norm, &counts, &deg, &cursor, &nseg,
                        &csr_pt, &csr_w, &seg_v, &seg_begin, &seg_end, &val_a, &val_b, &scan_tmp};
         for (DevBuf* p : b) p->release();
     }

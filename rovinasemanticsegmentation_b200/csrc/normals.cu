@@ -18,7 +18,9 @@
 
 namespace rss {
 
-size_t integral_elems(int W, int H) { return (size_t)(W + 1) * (H + 1); }
+// Skewed ("anti-diagonal major") storage: element (r, c) of an H x W plane lives at [(r + c) * HP + r], HP = H
+// rounded up to 32.  At wavefront step s = r + c the H threads of a CTA touch one contiguous run of memory.
+size_t integral_elems(int W, int H) { return skew_elems(W, H); }
 
 // ------------------------------------------------------------------------------------------------
 // (1) gradients (initAverage3DGradientMethod) + depth-change mask -> initial distance map
@@ -33,7 +35,8 @@ __global__ void __launch_bounds__(256) gradient_mask_kernel(const float4* __rest
                                                             float* __restrict__ dist_init) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c >= W) return;
-    const size_t i = (size_t)r * W + c, NP = (size_t)W * H;
+    const size_t i = (size_t)r * W + c;
+    const size_t SP = skew_elems(W, H), si = skew_index(r, c, skew_pitch(H));
     float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f};
     if (r >= 1 && r < H - 1 && c >= 1 && c < W - 1) {
         const float4 L = xyz[i - 1], Rr = xyz[i + 1], U = xyz[i - W], Dn = xyz[i + W];
@@ -44,11 +47,11 @@ __global__ void __launch_bounds__(256) gradient_mask_kernel(const float4* __rest
     const bool fy = isfinite(__fadd_rn(__fadd_rn(gy[0], gy[1]), gy[2]));
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        grad[(size_t)k * NP + i] = fx ? gx[k] : 0.f;
-        grad[(size_t)(3 + k) * NP + i] = fy ? gy[k] : 0.f;
+        grad[(size_t)k * SP + si] = fx ? gx[k] : 0.f;
+        grad[(size_t)(3 + k) * SP + si] = fy ? gy[k] : 0.f;
     }
-    fin[i] = fx ? 1 : 0;
-    fin[NP + i] = fy ? 1 : 0;
+    fin[si] = fx ? 1 : 0;
+    fin[SP + si] = fy ? 1 : 0;
     // depth-change map, gathered: a pixel is cleared by its own tests and by its left / upper neighbour's
     const float z = xyz[i].z;
     bool cleared = false;
@@ -164,13 +167,13 @@ __global__ void __launch_bounds__(1024) dist_backward_kernel(const float* __rest
 
 // ------------------------------------------------------------------------------------------------
 // (2) integral images along anti-diagonals.  grid = 6 CTAs (image x channel), block = H threads (<= 1024).
-// Thread r owns integral row r+1.  At step s it computes column c = s - r:
+// Thread r owns image row r.  At step s it computes column c = s - r:
 //     v = ((I[r][c+1] + I[r+1][c]) - I[r][c]) + g      (g = 0 where PCL skips the element)
 // "up" comes from thread r-1 (shared memory, written one step earlier), "left"/"upleft" stay in registers.
-// Gradient values are prefetched 8 columns ahead (two float4 per thread) so that the global-load latency is
-// off the critical path; the recurrence itself is three dependent DADDs per step.
+// Inputs and outputs use the skewed layout, so each step is one coalesced load and one coalesced store per warp;
+// the gradient values are prefetched WF_PF steps ahead.  The recurrence itself is three dependent DADDs per step.
 // ------------------------------------------------------------------------------------------------
-constexpr int PF = 8;
+constexpr int WF_PF = 8;
 __global__ void __launch_bounds__(1024) integral_wavefront_kernel(const float* __restrict__ grad,
                                                                   const uint8_t* __restrict__ fin, int W, int H,
                                                                   double* __restrict__ integ, int* __restrict__ cnt) {
@@ -181,21 +184,12 @@ __global__ void __launch_bounds__(1024) integral_wavefront_kernel(const float* _
     const int img = plane_id / 3, ch = plane_id - img * 3;
     const bool do_cnt = ch == 0;
     const int r = threadIdx.x;
-    const int W1 = W + 1;
-    const size_t NP = (size_t)W * H, IP = (size_t)W1 * (H + 1);
-    double* I = integ + (size_t)plane_id * IP;
-    int* Cn = cnt + (size_t)img * IP;
-    const float* g = grad + (size_t)plane_id * NP + (size_t)r * W;
-    const uint8_t* f = fin + (size_t)img * NP + (size_t)r * W;
-    // zero row / column of the integral image
-    for (int c = threadIdx.x; c < W1; c += blockDim.x) {
-        I[c] = 0.0;
-        if (do_cnt) Cn[c] = 0;
-    }
-    if (r < H) {
-        I[(size_t)(r + 1) * W1] = 0.0;
-        if (do_cnt) Cn[(size_t)(r + 1) * W1] = 0;
-    }
+    const int HP = skew_pitch(H);
+    const size_t SP = skew_elems(W, H);
+    double* I = integ + (size_t)plane_id * SP;
+    int* Cn = cnt + (size_t)img * SP;
+    const float* g = grad + (size_t)plane_id * SP;
+    const uint8_t* f = fin + (size_t)img * SP;
     for (int k = threadIdx.x; k < 2 * (H + 1); k += blockDim.x) {
         sval[k] = 0.0;
         scnt[k] = 0;
@@ -203,54 +197,49 @@ __global__ void __launch_bounds__(1024) integral_wavefront_kernel(const float* _
     __syncthreads();
     double left = 0.0, upleft = 0.0;
     int cleft = 0, cupleft = 0;
-    float buf[2][PF];
-    uint8_t fbuf[2][PF];
-    auto load_chunk = [&](int which, int c0) {
-#pragma unroll
-        for (int k = 0; k < PF; k++) {
-            const bool in = r < H && c0 + k < W;
-            buf[which][k] = in ? __ldg(g + c0 + k) : 0.f;
-            fbuf[which][k] = (in && do_cnt) ? __ldg(f + c0 + k) : 0;
-        }
-    };
-    load_chunk(0, 0);
-    load_chunk(1, PF);
     const int steps = W + H - 1;
-    for (int s = 0; s < steps; s++) {
-        const int c = s - r;
-        const int rb = (s + 1) & 1, wb = s & 1;  // read the buffer written at step s-1
-        if (r < H && c >= 0 && c < W) {
-            const int q = c / PF, k = c - q * PF, which = q & 1;
-            const double up = sval[rb * (H + 1) + r];
-            float gv = 0.f;
-            uint8_t fv = 0;
+    const bool live = r < H;
+    float cur[WF_PF], nxt[WF_PF];
+    uint8_t fcur[WF_PF], fnxt[WF_PF];
 #pragma unroll
-            for (int kk = 0; kk < PF; kk++)
-                if (kk == k) { gv = buf[0][kk]; fv = fbuf[0][kk]; }
-            if (which) {
+    for (int k = 0; k < WF_PF; k++) {
+        cur[k] = live ? __ldg(g + (size_t)k * HP + r) : 0.f;
+        fcur[k] = (live && do_cnt) ? __ldg(f + (size_t)k * HP + r) : 0;
+    }
+    for (int s0 = 0; s0 < steps; s0 += WF_PF) {
 #pragma unroll
-                for (int kk = 0; kk < PF; kk++)
-                    if (kk == k) { gv = buf[1][kk]; fv = fbuf[1][kk]; }
-            }
-            const double v = __dadd_rn(__dsub_rn(__dadd_rn(up, left), upleft), (double)gv);
-            I[(size_t)(r + 1) * W1 + c + 1] = v;
-            sval[wb * (H + 1) + r + 1] = v;
-            upleft = up;
-            left = v;
-            if (do_cnt) {
-                const int cu = scnt[rb * (H + 1) + r];
-                const int cv = cu + cleft - cupleft + (int)fv;
-                Cn[(size_t)(r + 1) * W1 + c + 1] = cv;
-                scnt[wb * (H + 1) + r + 1] = cv;
-                cupleft = cu;
-                cleft = cv;
-            }
-            if (k == PF - 1) {  // chunk consumed: refill it with the chunk after next
-                if (which == 0) load_chunk(0, (q + 2) * PF);
-                else load_chunk(1, (q + 2) * PF);
-            }
+        for (int k = 0; k < WF_PF; k++) {  // the buffers are padded by 16 steps, so s0 + WF_PF + k stays in range
+            nxt[k] = live ? __ldg(g + (size_t)(s0 + WF_PF + k) * HP + r) : 0.f;
+            fnxt[k] = (live && do_cnt) ? __ldg(f + (size_t)(s0 + WF_PF + k) * HP + r) : 0;
         }
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < WF_PF; k++) {
+            const int s = s0 + k;
+            const int c = s - r;
+            const int rb = (s + 1) & 1, wb = s & 1;  // read the buffer written at step s-1
+            if (live && c >= 0 && c < W && s < steps) {
+                const double up = sval[rb * (H + 1) + r];
+                const double v = __dadd_rn(__dsub_rn(__dadd_rn(up, left), upleft), (double)cur[k]);
+                I[(size_t)s * HP + r] = v;
+                sval[wb * (H + 1) + r + 1] = v;
+                upleft = up;
+                left = v;
+                if (do_cnt) {
+                    const int cu = scnt[rb * (H + 1) + r];
+                    const int cv = cu + cleft - cupleft + (int)fcur[k];
+                    Cn[(size_t)s * HP + r] = cv;
+                    scnt[wb * (H + 1) + r + 1] = cv;
+                    cupleft = cu;
+                    cleft = cv;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < WF_PF; k++) {
+            cur[k] = nxt[k];
+            fcur[k] = fnxt[k];
+        }
     }
 }
 
