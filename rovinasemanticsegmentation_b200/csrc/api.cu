@@ -13,6 +13,7 @@ using namespace rss;
 
 namespace rss {
 void crf_release_cached(rss_ctx* ctx);  // crf.cu
+rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
 }
 
 static thread_local std::string g_create_error;
@@ -298,6 +299,7 @@ static void free_ctx(rss_ctx* ctx) {
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_cloud) cudaEventDestroy(ctx->ev_cloud);
     if (ctx->s0) cudaStreamDestroy(ctx->s0);
     if (ctx->s1) cudaStreamDestroy(ctx->s1);
     delete ctx;
@@ -337,7 +339,8 @@ extern "C" rss_status rss_create(const char* config_json_path, const char* fores
     for (cudaEvent_t& e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "cudaEventCreate failed"; return bail(RSS_ERR_CUDA); }
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_cloud, cudaEventDisableTiming) != cudaSuccess) {
         ctx->err = "cudaEventCreate failed";
         return bail(RSS_ERR_CUDA);
     }
@@ -459,6 +462,7 @@ rss_status frame_prepare(rss_ctx* ctx, const float* Kinv, const float* R, const 
                 M[3 * i + j] = s + p2;
             }
         launch_cloud(ctx, ctx->s1, f.depth.as<uint16_t>(), W, H, M, t, dmin, dmax, f.xyz.as<float4>());
+        RSS_CU(ctx, cudaEventRecord(ctx->ev_cloud, ctx->s1));
         f.have_cloud = true;
         if (cfg.use_normal) {
             RSS_CU(ctx, f.dist_a.reserve(NP * 4));
@@ -566,7 +570,18 @@ rss_status frame_segment(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth
     rss_status st = frame_upload(ctx, rgb, depth, W, H);
     if (st != RSS_OK) return st;
     cudaEventRecord(ctx->ev[1], ctx->s0);
-    st = frame_prepare(ctx, Kinv, R, t, cfg.depth_min, cfg.depth_max);
+    return frame_segment_resident(ctx, Kinv, R, t, fill);
+}
+
+// the same on the frame that frame_upload() made resident (events 0/1 recorded by the caller)
+rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill) {
+    FrameState& f = ctx->fr;
+    const HostConfig& cfg = ctx->cfg;
+    const ForestDev& F = ctx->forest;
+    if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
+    const int stride = cfg.rf_stride, W = f.W, H = f.H;
+    if (W % stride || H % stride) return ctx->fail(RSS_ERR_INVALID, "image size must be a multiple of rf_prediction_stride");
+    rss_status st = frame_prepare(ctx, Kinv, R, t, cfg.depth_min, cfg.depth_max);
     if (st != RSS_OK) return st;
     st = frame_extract(ctx, stride, cfg.depth_min, cfg.depth_max, RSS_NO_LABEL, nullptr, 0);
     if (st != RSS_OK) return st;

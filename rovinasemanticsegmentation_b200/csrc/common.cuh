@@ -129,7 +129,7 @@ struct rss_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t s0 = nullptr, s1 = nullptr;
     cudaEvent_t ev[16] = {nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_cloud = nullptr;
     rss::HostConfig cfg;
     rss::ForestDev forest;
     rss::FrameState fr;

@@ -21,7 +21,7 @@ float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float
                           int Mp);
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
                    int out_stride);
-rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch);
+rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L);
 
 constexpr int CRF_MAX_KERNELS = 4;
 constexpr int CRF_MAX_CH = 32;
@@ -406,8 +406,11 @@ static uint32_t next_pow2(uint64_t v) {
     return p;
 }
 
-// builds lattice k from device-resident features; synchronises to detect overflow and grows the table
-rss_status crf_add_kernel_dev(rss_crf* crf, const float* feat_dev, int d, float potts_w, int norm_type, bool sync) {
+// Builds one more lattice from device-resident features on stream `st`.
+// sync = true : waits, checks the overflow flag and regrows the hash table until it fits (reference-shaped API).
+// sync = false: only enqueues; the caller checks crf_lattice_overflow() later (keyframe path, no host sync).
+rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_dev, int d, float potts_w, int norm_type,
+                              bool sync) {
     rss_ctx* ctx = crf->ctx;
     if ((int)crf->kernels.size() >= CRF_MAX_KERNELS) return ctx->fail(RSS_ERR_INVALID, "too many pairwise terms (max 4)");
     if (norm_type < RSS_NORMALIZE_BEFORE || norm_type > RSS_NORMALIZE_SYMMETRIC)
@@ -425,16 +428,16 @@ rss_status crf_add_kernel_dev(rss_crf* crf, const float* feat_dev, int d, float 
     const uint64_t maxv = (uint64_t)crf->N * (d + 1);
     uint32_t hcap = next_pow2(std::min<uint64_t>(2 * maxv, 1u << 17));
     if (L->hcap > hcap && L->d == d) hcap = L->hcap;
-    RSS_CU(ctx, crf->scratch.reserve((size_t)crf->N * (crf->Mp + 4) * 4));
+    if (L->want_hcap > hcap) hcap = L->want_hcap;
     for (;;) {
-        rss_status st = lattice_build(ctx, ctx->s0, *L, feat_dev, crf->N, d, hcap, crf->Mp);
-        if (st != RSS_OK) return st;
-        st = lattice_normalization(ctx, ctx->s0, *L, crf->scratch.as<float>());
-        if (st != RSS_OK) return st;
+        rss_status rc = lattice_build(ctx, st, *L, feat_dev, crf->N, d, hcap, crf->Mp);
+        if (rc != RSS_OK) return rc;
+        rc = lattice_normalization(ctx, st, *L);
+        if (rc != RSS_OK) return rc;
         if (!sync) return RSS_OK;
         uint32_t h[8];
-        RSS_CU(ctx, cudaMemcpyAsync(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx->s0));
-        RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+        RSS_CU(ctx, cudaMemcpyAsync(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost, st));
+        RSS_CU(ctx, cudaStreamSynchronize(st));
         if (!h[1]) {
             L->V_host = (int)h[0];
             return RSS_OK;
@@ -443,6 +446,24 @@ rss_status crf_add_kernel_dev(rss_crf* crf, const float* feat_dev, int d, float 
             return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
         hcap *= 4;
     }
+}
+// after a synchronisation: true when some lattice overflowed; its next build will use a 4x larger table
+rss_status crf_lattice_overflow(rss_crf* crf, bool* any) {
+    rss_ctx* ctx = crf->ctx;
+    *any = false;
+    for (Lattice* L : crf->kernels) {
+        uint32_t h[2];
+        RSS_CU(ctx, cudaMemcpy(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+        L->V_host = (int)h[0];
+        if (h[1]) {
+            const uint64_t maxv = (uint64_t)crf->N * (L->d + 1);
+            if ((uint64_t)L->hcap >= 2 * next_pow2(2 * maxv) || L->hcap >= (1u << 30))
+                return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
+            L->want_hcap = L->hcap * 4;
+            *any = true;
+        }
+    }
+    return RSS_OK;
 }
 
 void crf_free(rss_crf* crf) {
@@ -538,7 +559,7 @@ extern "C" rss_status rss_crf_add_pairwise(rss_crf* crf, const float* feats, int
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * d * 4));
     RSS_CU(ctx, cudaMemcpyAsync(crf->feat_stage.ptr, feats, (size_t)crf->N * d * 4, cudaMemcpyHostToDevice, ctx->s0));
-    return crf_add_kernel_dev(crf, crf->feat_stage.as<float>(), d, potts_w, norm_type, true);
+    return crf_add_kernel_dev(crf, ctx->s0, crf->feat_stage.as<float>(), d, potts_w, norm_type, true);
 }
 
 extern "C" rss_status rss_crf_add_pairwise_gaussian(rss_crf* crf, int W, int H, float sx, float sy, float potts_w) {
@@ -548,7 +569,7 @@ extern "C" rss_status rss_crf_add_pairwise_gaussian(rss_crf* crf, int W, int H, 
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * 2 * 4));
     RSS_LAUNCH(ctx, feat_gaussian_kernel, rss_div_up(crf->N, 256), 256, 0, ctx->s0, W, H, sx, sy, crf->feat_stage.as<float>());
-    return crf_add_kernel_dev(crf, crf->feat_stage.as<float>(), 2, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
+    return crf_add_kernel_dev(crf, ctx->s0, crf->feat_stage.as<float>(), 2, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
 }
 
 extern "C" rss_status rss_crf_add_pairwise_bilateral(rss_crf* crf, int W, int H, float sx, float sy, float sr, float sg,
@@ -562,7 +583,7 @@ extern "C" rss_status rss_crf_add_pairwise_bilateral(rss_crf* crf, int W, int H,
     RSS_CU(ctx, cudaMemcpyAsync(im_dev, im, (size_t)crf->N * 3, cudaMemcpyHostToDevice, ctx->s0));
     RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(crf->N, 256), 256, 0, ctx->s0, W, H, sx, sy, sr, sg, sb, im_dev,
                crf->feat_stage.as<float>());
-    return crf_add_kernel_dev(crf, crf->feat_stage.as<float>(), 5, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
+    return crf_add_kernel_dev(crf, ctx->s0, crf->feat_stage.as<float>(), 5, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
 }
 
 extern "C" rss_status rss_crf_add_pairwise_xyzrgb(rss_crf* crf, const float* xyz, const float* rgb, float wxyz, float wrgb,
@@ -578,7 +599,7 @@ extern "C" rss_status rss_crf_add_pairwise_xyzrgb(rss_crf* crf, const float* xyz
     RSS_CU(ctx, cudaMemcpyAsync(stage + 9 * N, rgb, N * 12, cudaMemcpyHostToDevice, ctx->s0));
     RSS_LAUNCH(ctx, feat_xyzrgb_kernel, rss_div_up((long long)N, 256), 256, 0, ctx->s0, (int)N, stage + 6 * N, stage + 9 * N,
                wxyz, wrgb, stage);
-    return crf_add_kernel_dev(crf, stage, 6, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
+    return crf_add_kernel_dev(crf, ctx->s0, stage, 6, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
 }
 
 extern "C" rss_status rss_crf_lattice_size(rss_crf* crf, int k, int* vertices) {
@@ -701,8 +722,8 @@ extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx,
 // fused keyframe (configs[1]/[2] of BASELINE.json)
 // --------------------------------------------------------------------------------------------------------------------
 namespace rss {
-rss_status frame_segment(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth, int W, int H, const float* Kinv,
-                         const float* R, const float* t, float fill);
+rss_status frame_upload(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth, int W, int H);
+rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
 void frame_collect_timings(rss_ctx* ctx, bool with_d2h);
 }
 
@@ -714,56 +735,84 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     if (!(ctx->cfg.use_height || ctx->cfg.use_normal))
         return ctx->fail(RSS_ERR_STATE, "the keyframe CRF needs the point cloud (feature_height or feature_normal)");
     RSS_CU(ctx, cudaSetDevice(ctx->device));
-    rss_status st = frame_segment(ctx, rgb, depth_mm, W, H, Kinv, R, t, prm->fill);
-    if (st != RSS_OK) return st;
     const ForestDev& F = ctx->forest;
+    if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
     const int N = W * H;
     rss_crf* crf = ctx->keyframe_crf;
+    rss_status st;
     if (!crf || crf->N != N || crf->n_layers != F.L || crf->Mtot != F.sumC) {
         crf_release_cached(ctx);
         st = crf_new(ctx, N, F.L, F.C, &crf);
         if (st != RSS_OK) return st;
         ctx->keyframe_crf = crf;
     }
-    // previous lattices are rebuilt in place (their buffers are reused): the 5-D one first so that pops match
-    while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
-    LayerSpec ls = make_layers(crf, nullptr);
-    RSS_LAUNCH(ctx, unary_from_posteriors_kernel, rss_div_up((long long)N * crf->Mp, 256), 256, 0, ctx->s0,
-               ctx->fr.posteriors.as<float>(), N, crf->Mtot, crf->Mp, ls, crf->unary.as<float>());
-    cudaEventRecord(ctx->ev[8], ctx->s0);
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * 8 * 4));
     float* f3 = crf->feat_stage.as<float>();
     float* f5 = f3 + (size_t)N * 3;
-    RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, ctx->s0, N, ctx->fr.xyz.as<float4>(),
-               1.0f / prm->sigma_xyz, t[0], t[1], t[2], f3);
-    RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(N, 256), 256, 0, ctx->s0, W, H, prm->sigma_px, prm->sigma_px,
-               prm->sigma_rgb, prm->sigma_rgb, prm->sigma_rgb, ctx->fr.rgb.as<uint8_t>(), f5);
-    st = crf_add_kernel_dev(crf, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, true);
+    cudaStream_t sA = crf->side[0], sB = crf->side[1];
+    // ---- upload; the bilateral lattice only needs the colour image, so its construction starts right away on sB
+    cudaEventRecord(ctx->ev[0], ctx->s0);
+    st = frame_upload(ctx, rgb, depth_mm, W, H);
     if (st != RSS_OK) return st;
-    st = crf_add_kernel_dev(crf, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, true);
-    if (st != RSS_OK) return st;
-    cudaEventRecord(ctx->ev[9], ctx->s0);
-    int unk[RSS_MAX_LAYERS];
-    for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = l < ctx->cfg.layer_count ? ctx->cfg.unknown_label[l] : 0;
-    st = crf_run(crf, prm->iters, unk, crf->labels.as<uint8_t>());
-    if (st != RSS_OK) return st;
-    cudaEventRecord(ctx->ev[10], ctx->s0);
-    if (labels) RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.ptr, (size_t)N * F.L, cudaMemcpyDeviceToHost, ctx->s0));
-    if (Qout) {
-        float* dstQ = Qout;
-        for (int l = 0; l < crf->n_layers; l++) {
-            RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, crf->Q.as<float>(),
-                       N, crf->M[l], crf->Mp, crf->moff[l], crf->scratch.as<float>());
-            RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
-            RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
-            dstQ += (size_t)N * crf->M[l];
+    cudaEventRecord(ctx->ev[1], ctx->s0);
+    for (int attempt = 0;; attempt++) {
+        // lattices of the previous keyframe are rebuilt in place (pooled buffers keep their capacity)
+        while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
+        RSS_CU(ctx, cudaEventRecord(crf->ev_fork, ctx->s0));
+        RSS_CU(ctx, cudaStreamWaitEvent(sB, crf->ev_fork, 0));
+        RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(N, 256), 256, 0, sB, W, H, prm->sigma_px, prm->sigma_px,
+                   prm->sigma_rgb, prm->sigma_rgb, prm->sigma_rgb, ctx->fr.rgb.as<uint8_t>(), f5);
+        // pool order: the Gaussian lattice is added first below, so hand it the 3-D lattice's buffers
+        if (crf->pool.size() == 2 && crf->pool.back()->d != 3) std::swap(crf->pool[0], crf->pool[1]);
+        if (attempt == 0) {
+            // ---- frame path on s0 (+ s1 for cloud / normals); ev_cloud marks the point cloud
+            st = frame_segment_resident(ctx, Kinv, R, t, prm->fill);
+            if (st != RSS_OK) return st;
         }
+        // ---- Gaussian lattice on sA as soon as the cloud exists
+        RSS_CU(ctx, cudaStreamWaitEvent(sA, ctx->ev_cloud, 0));
+        RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, sA, N, ctx->fr.xyz.as<float4>(),
+                   1.0f / prm->sigma_xyz, t[0], t[1], t[2], f3);
+        st = crf_add_kernel_dev(crf, sA, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, false);
+        if (st != RSS_OK) return st;
+        st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false);
+        if (st != RSS_OK) return st;
+        RSS_CU(ctx, cudaEventRecord(crf->ev_join[0], sA));
+        RSS_CU(ctx, cudaEventRecord(crf->ev_join[1], sB));
+        // ---- unary = -posteriors, then the mean-field loop once both lattices are ready
+        LayerSpec ls = make_layers(crf, nullptr);
+        RSS_LAUNCH(ctx, unary_from_posteriors_kernel, rss_div_up((long long)N * crf->Mp, 256), 256, 0, ctx->s0,
+                   ctx->fr.posteriors.as<float>(), N, crf->Mtot, crf->Mp, ls, crf->unary.as<float>());
+        cudaEventRecord(ctx->ev[8], ctx->s0);
+        RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[0], 0));
+        RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[1], 0));
+        cudaEventRecord(ctx->ev[9], ctx->s0);
+        int unk[RSS_MAX_LAYERS];
+        for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = l < ctx->cfg.layer_count ? ctx->cfg.unknown_label[l] : 0;
+        st = crf_run(crf, prm->iters, unk, crf->labels.as<uint8_t>());
+        if (st != RSS_OK) return st;
+        cudaEventRecord(ctx->ev[10], ctx->s0);
+        if (labels) RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.ptr, (size_t)N * F.L, cudaMemcpyDeviceToHost, ctx->s0));
+        if (Qout) {
+            float* dstQ = Qout;
+            for (int l = 0; l < crf->n_layers; l++) {
+                RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0,
+                           crf->Q.as<float>(), N, crf->M[l], crf->Mp, crf->moff[l], crf->scratch.as<float>());
+                RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
+                RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+                dstQ += (size_t)N * crf->M[l];
+            }
+        }
+        cudaEventRecord(ctx->ev[5], ctx->s0);
+        RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+        bool overflow = false;
+        st = crf_lattice_overflow(crf, &overflow);
+        if (st != RSS_OK) return st;
+        if (!overflow) break;  // otherwise: rebuild with larger hash tables and run the CRF again (rare)
     }
-    cudaEventRecord(ctx->ev[5], ctx->s0);
-    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     frame_collect_timings(ctx, false);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]); ctx->tim.lattice_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]); ctx->tim.lattice_ms = ms;  // lattice time NOT hidden behind the frame path
     cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]); ctx->tim.meanfield_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[5]); ctx->tim.d2h_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]); ctx->tim.total_ms = ms;

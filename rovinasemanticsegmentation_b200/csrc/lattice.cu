@@ -607,19 +607,45 @@ void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* value
                L.N, L.d + 1, lattice_alpha(L.d), values, M, Mp, seq, L.counts.as<uint32_t>(), out, out_stride);
 }
 
-// norm_ = 1/sqrt(K 1 + 1e-20) through the scalar path (pairwise.cpp:44,54-57; permutohedral.cpp:600-601)
-rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L, float* ones_scratch /* [N][4] */) {
-    const int N = L.N;
+// splat of the all-ones vector: values[v][0] = sum of the barycentric weights that reference v (no Q gather needed)
+__global__ void __launch_bounds__(256) splat_ones_kernel(const int* __restrict__ seg_v, const uint32_t* __restrict__ seg_begin,
+                                                         const uint32_t* __restrict__ seg_end, const uint32_t* __restrict__ counts,
+                                                         const float* __restrict__ csr_w, float* __restrict__ values) {
+    const uint32_t warp = (uint32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (counts[1] || warp >= counts[2]) return;
+    const uint32_t b = seg_begin[warp], e = seg_end[warp];
+    float w = b + lane < e ? __ldg(csr_w + b + lane) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) atomicAdd(values + (size_t)seg_v[warp] * 4, w);
+}
+
+// norm_ = 1/sqrt(K 1 + 1e-20) through the scalar path (pairwise.cpp:44,54-57; permutohedral.cpp:600-601).
+// The value tables (allocated for the CRF's Mp >= 4) are used with a row stride of 4 floats, channel 0 live.
+rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
+    const int N = L.N, d1 = L.d + 1;
     float* norm = L.norm.as<float>();
-    if (L.norm_type == RSS_NO_NORMALIZATION) {
+    if (L.norm_type == RSS_NO_NORMALIZATION)
         return ctx->fail(RSS_ERR_INVALID, "NO_NORMALIZATION is not supported on the device path");
+    float* a = L.splat_target ? L.val_b.as<float>() : L.val_a.as<float>();
+    float* b = L.splat_target ? L.val_a.as<float>() : L.val_b.as<float>();
+    RSS_LAUNCH(ctx, splat_ones_kernel, rss_div_up((long long)L.maxseg * 32, 256), 256, 0, st, L.seg_v.as<int>(),
+               L.seg_begin.as<uint32_t>(), L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_w.as<float>(), a);
+    float* s = a;
+    float* d = b;
+    for (int j = 0; j < d1; j++) {
+        RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<const float4*>(s),
+                   reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), 1);
+        float* t = s; s = d; d = t;
     }
-    RSS_LAUNCH(ctx, fill_f32_kernel, rss_div_up((long long)N * 4, 256), 256, 0, st, ones_scratch, (size_t)N * 4, 1.0f);
-    // value tables were allocated for the CRF's Mp >= 4; run the filter on four identical all-ones channels
-    float* vals = lattice_splat_blur(ctx, st, L, ones_scratch, 4, nullptr, 4);
-    lattice_slice(ctx, st, L, vals, 1, 4, 1, norm, 1);
+    lattice_slice(ctx, st, L, s, 1, 4, 1, norm, 1);
     RSS_LAUNCH(ctx, norm_kernel, rss_div_up(N, 256), 256, 0, st, norm, N, L.norm_type);
-    // the ping-pong partner must have a zero "missing neighbour" row again for the CRF's own Mp
+    // both tables are dirty in their first V*4 floats: clear them again for the filter proper
+    RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(a),
+               L.counts.as<uint32_t>(), 1);
+    RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(b),
+               L.counts.as<uint32_t>(), 1);
     RSS_CU(ctx, cudaGetLastError());
     return RSS_OK;
 }

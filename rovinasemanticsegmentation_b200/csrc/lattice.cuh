@@ -20,6 +20,7 @@ struct Lattice {
     int norm_type = RSS_NORMALIZE_SYMMETRIC;
     uint32_t hcap = 0;   // hash capacity (power of two)
     uint32_t vcap = 0;   // vertex capacity = hcap / 2
+    uint32_t want_hcap = 0;  // capacity requested for the next build after an overflow
     int V_host = -1;     // vertex count once read back (diagnostics)
     DevBuf table;        // Key128[hcap]
     DevBuf slot_id;      // uint32[hcap]   slot -> vertex id

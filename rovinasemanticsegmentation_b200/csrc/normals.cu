@@ -174,73 +174,65 @@ __global__ void __launch_bounds__(1024) dist_backward_kernel(const float* __rest
 // the gradient values are prefetched WF_PF steps ahead.  The recurrence itself is three dependent DADDs per step.
 // ------------------------------------------------------------------------------------------------
 constexpr int WF_PF = 8;
-__global__ void __launch_bounds__(1024) integral_wavefront_kernel(const float* __restrict__ grad,
-                                                                  const uint8_t* __restrict__ fin, int W, int H,
-                                                                  double* __restrict__ integ, int* __restrict__ cnt) {
-    extern __shared__ double smd[];  // [2][H+1] doubles, then [2][H+1] ints
-    double* sval = smd;
-    int* scnt = reinterpret_cast<int*>(smd + 2 * (H + 1));
-    const int plane_id = blockIdx.x;  // img*3 + ch
-    const int img = plane_id / 3, ch = plane_id - img * 3;
-    const bool do_cnt = ch == 0;
+// grid = 8 CTAs: planes 0..5 = the six double integral images, 6..7 = the two finite-count images (int, exact).
+template <int MAXT, typename T, typename TIn>
+__device__ __forceinline__ void wavefront_plane(const TIn* __restrict__ g, T* __restrict__ I, T* sval, int W, int H) {
     const int r = threadIdx.x;
     const int HP = skew_pitch(H);
-    const size_t SP = skew_elems(W, H);
-    double* I = integ + (size_t)plane_id * SP;
-    int* Cn = cnt + (size_t)img * SP;
-    const float* g = grad + (size_t)plane_id * SP;
-    const uint8_t* f = fin + (size_t)img * SP;
-    for (int k = threadIdx.x; k < 2 * (H + 1); k += blockDim.x) {
-        sval[k] = 0.0;
-        scnt[k] = 0;
-    }
+    for (int k = threadIdx.x; k < 2 * (H + 1); k += blockDim.x) sval[k] = T(0);
     __syncthreads();
-    double left = 0.0, upleft = 0.0;
-    int cleft = 0, cupleft = 0;
+    T left = T(0), upleft = T(0);
     const int steps = W + H - 1;
     const bool live = r < H;
-    float cur[WF_PF], nxt[WF_PF];
-    uint8_t fcur[WF_PF], fnxt[WF_PF];
+    TIn cur[WF_PF], nxt[WF_PF];
+    const TIn* gp = g + r;          // advances by HP per step
+    T* ip = I + r;
 #pragma unroll
-    for (int k = 0; k < WF_PF; k++) {
-        cur[k] = live ? __ldg(g + (size_t)k * HP + r) : 0.f;
-        fcur[k] = (live && do_cnt) ? __ldg(f + (size_t)k * HP + r) : 0;
-    }
+    for (int k = 0; k < WF_PF; k++) cur[k] = live ? __ldg(gp + (size_t)k * HP) : TIn(0);
+    gp += (size_t)WF_PF * HP;
+    T* rd0 = sval + r;              // buffer 0, slot of thread r-1 (index r)
+    T* rd1 = sval + (H + 1) + r;    // buffer 1
     for (int s0 = 0; s0 < steps; s0 += WF_PF) {
 #pragma unroll
-        for (int k = 0; k < WF_PF; k++) {  // the buffers are padded by 16 steps, so s0 + WF_PF + k stays in range
-            nxt[k] = live ? __ldg(g + (size_t)(s0 + WF_PF + k) * HP + r) : 0.f;
-            fnxt[k] = (live && do_cnt) ? __ldg(f + (size_t)(s0 + WF_PF + k) * HP + r) : 0;
-        }
+        for (int k = 0; k < WF_PF; k++) nxt[k] = live ? __ldg(gp + (size_t)k * HP) : TIn(0);  // padded by 16 steps
+        gp += (size_t)WF_PF * HP;
 #pragma unroll
         for (int k = 0; k < WF_PF; k++) {
             const int s = s0 + k;
             const int c = s - r;
-            const int rb = (s + 1) & 1, wb = s & 1;  // read the buffer written at step s-1
-            if (live && c >= 0 && c < W && s < steps) {
-                const double up = sval[rb * (H + 1) + r];
-                const double v = __dadd_rn(__dsub_rn(__dadd_rn(up, left), upleft), (double)cur[k]);
-                I[(size_t)s * HP + r] = v;
-                sval[wb * (H + 1) + r + 1] = v;
+            // step s reads the buffer written at step s-1 (parity (s+1)&1) and writes parity s&1; WF_PF is even, so the
+            // parity of s equals the parity of k and the buffer choice is a compile-time constant.
+            T* rd = (k & 1) ? rd0 : rd1;
+            T* wr = (k & 1) ? rd1 : rd0;
+            if (live && c >= 0 && c < W) {
+                const T up = *rd;
+                T v;
+                if constexpr (sizeof(T) == 8) v = __dadd_rn(__dsub_rn(__dadd_rn(up, left), upleft), (double)cur[k]);
+                else v = up + left - upleft + (T)cur[k];
+                *ip = v;
+                wr[1] = v;
                 upleft = up;
                 left = v;
-                if (do_cnt) {
-                    const int cu = scnt[rb * (H + 1) + r];
-                    const int cv = cu + cleft - cupleft + (int)fcur[k];
-                    Cn[(size_t)s * HP + r] = cv;
-                    scnt[wb * (H + 1) + r + 1] = cv;
-                    cupleft = cu;
-                    cleft = cv;
-                }
             }
+            ip += HP;
             __syncthreads();
         }
 #pragma unroll
-        for (int k = 0; k < WF_PF; k++) {
-            cur[k] = nxt[k];
-            fcur[k] = fnxt[k];
-        }
+        for (int k = 0; k < WF_PF; k++) cur[k] = nxt[k];
     }
+}
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) integral_wavefront_kernel(const float* __restrict__ grad,
+                                                                  const uint8_t* __restrict__ fin, int W, int H,
+                                                                  double* __restrict__ integ, int* __restrict__ cnt) {
+    extern __shared__ double smd[];  // [2][H+1] doubles (or ints)
+    const size_t SP = skew_elems(W, H);
+    const int plane_id = blockIdx.x;
+    if (plane_id < 6)
+        wavefront_plane<MAXT, double, float>(grad + (size_t)plane_id * SP, integ + (size_t)plane_id * SP, smd, W, H);
+    else
+        wavefront_plane<MAXT, int, uint8_t>(fin + (size_t)(plane_id - 6) * SP, cnt + (size_t)(plane_id - 6) * SP,
+                                            reinterpret_cast<int*>(smd), W, H);
 }
 
 void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int W, int H, float* dist_a,
@@ -254,8 +246,9 @@ void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int 
     RSS_LAUNCH(c, dist_forward_kernel, rss_div_up(H, band), threads, smem, st, dist_b, W, H, band, dist_a);
     RSS_LAUNCH(c, dist_backward_kernel, rss_div_up(H, band), threads, smem, st, dist_a, W, H, band, dist_b);
     const int wt = min(1024, rss_div_up(H, 32) * 32);
-    const size_t wsmem = (size_t)2 * (H + 1) * (sizeof(double) + sizeof(int));
-    RSS_LAUNCH(c, integral_wavefront_kernel, 6, wt, wsmem, st, grad, fin, W, H, integ, integ_cnt);
+    const size_t wsmem = (size_t)2 * (H + 1) * sizeof(double);
+    if (wt <= 512) RSS_LAUNCH(c, integral_wavefront_kernel<512>, 8, wt, wsmem, st, grad, fin, W, H, integ, integ_cnt);
+    else RSS_LAUNCH(c, integral_wavefront_kernel<1024>, 8, wt, wsmem, st, grad, fin, W, H, integ, integ_cnt);
 }
 
 __global__ void __launch_bounds__(256) normals_full_kernel(const float4* __restrict__ xyz,
