@@ -70,6 +70,10 @@ typedef struct {
  * ------------------------------------------------------------------------------------------------- */
 rss_status rss_create(const char* config_json_path, const char* forest_dat_path, int cuda_device, rss_ctx** out);
 rss_status rss_destroy(rss_ctx* ctx);
+/* RandomForest::read(std::istream&) (classifier.cpp:222-235) for a context created without a model, or to swap
+ * models: from a file, or from a buffer holding the bytes of the libforest stream. */
+rss_status rss_load_forest(rss_ctx* ctx, const char* forest_dat_path);
+rss_status rss_load_forest_memory(rss_ctx* ctx, const void* bytes, size_t size);
 rss_status rss_get_info(const rss_ctx* ctx, rss_info* out);
 /* message of the last failing call on this context ("" if none); ctx may be NULL for create failures */
 const char* rss_last_error(const rss_ctx* ctx);

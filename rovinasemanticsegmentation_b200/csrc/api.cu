@@ -128,11 +128,15 @@ struct Reader {
 };
 }  // namespace
 
+static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, size_t size);
 static rss_status load_forest(rss_ctx* ctx, const char* path) {
     std::ifstream f(path, std::ios::binary);
     if (!f) return ctx->fail(RSS_ERR_IO, std::string("cannot open forest ") + path);
     std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    Reader rd{bytes.data(), bytes.data() + bytes.size()};
+    return load_forest_bytes(ctx, bytes.data(), bytes.size());
+}
+static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, size_t size) {
+    Reader rd{data, data + size};
     ForestDev& F = ctx->forest;
     const int T = rd.i32();
     if (!rd.ok || T <= 0 || T > 4096) return ctx->fail(RSS_ERR_MODEL, "forest: bad tree count");
@@ -352,6 +356,21 @@ extern "C" rss_status rss_create(const char* config_json_path, const char* fores
     }
     *out = ctx;
     return RSS_OK;
+}
+
+extern "C" rss_status rss_load_forest(rss_ctx* ctx, const char* forest_dat_path) {
+    if (!ctx || !forest_dat_path) return RSS_ERR_INVALID;
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    ctx->forest.loaded = false;
+    return load_forest(ctx, forest_dat_path);
+}
+extern "C" rss_status rss_load_forest_memory(rss_ctx* ctx, const void* bytes, size_t size) {
+    if (!ctx || !bytes) return RSS_ERR_INVALID;
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    ctx->forest.loaded = false;
+    return load_forest_bytes(ctx, static_cast<const unsigned char*>(bytes), size);
 }
 
 extern "C" rss_status rss_destroy(rss_ctx* ctx) {
