@@ -142,11 +142,43 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-ALGO_BYTES = {
-    # algorithmic (compulsory) bytes per launch, SURVEY.md 8(d) / DESIGN.md "Kernels"; N = W*H points, M = 17 labels
-    # slice of both lattices + soft-max: offsets+bary 8(d+1)N per lattice, unary 4MN, Q write 4MN, norm 4N per lattice
-    "slice_softmax_kernel<20>": lambda N, M: 8 * (4 + 6) * N + 4 * M * N * 2 + 4 * 2 * N,
-}
+def algo_bytes(name, env):
+    """Algorithmic (compulsory) bytes of ONE launch of kernel `name`: every unique input byte read once, every output
+    byte written once (DESIGN.md "Kernels").  Kernels launched once per lattice get the mean over the
+    lattices.  env: N = W*H CRF points, M = labels over both layers, Ns = forest samples, D = features per sample,
+    T trees, nodes/leaves of the forest, lat = [(d, V)] of the keyframe's lattices, P = patch_size (border)."""
+    N, M, Ns, D, T, P = env["N"], env["M"], env["Ns"], env["D"], env["T"], env["P"]
+    Wb, Hb = W + 2 * P, H + 2 * P
+    lat = env["lat"]
+    mean = lambda f: sum(f(d, V) for d, V in lat) / max(len(lat), 1)
+    table = {
+        # F1..F4 (feature_extractor.h)
+        "lab_border_kernel": 3 * N + 3 * Wb * Hb,
+        "patch_features_kernel": 3 * Wb * Hb + 2 * Ns + 8 * Ns + 4 * (D - 3) * Ns,
+        "cloud_kernel": 2 * N + 12 * N,
+        "select_kernel": 2 * Ns + 4 * Ns, "compact_kernel": 8 * Ns + 8 * Ns,
+        "gradient_mask_kernel": 12 * N + 24 * N + 2 * N + 4 * N,
+        "dist_forward_kernel": 8 * N, "dist_backward_kernel": 8 * N,
+        "integral_wavefront_kernel<512>": 24 * N + 2 * N + 48 * N + 8 * N,
+        "scalar_features_kernel": 8 * Ns + 2 * Ns + 12 * Ns + 12 * Ns,
+        # R1, R2 (classifier.cpp, segmenter.cpp:355-431)
+        "forest_traverse_kernel": 4 * D * Ns + 16 * env["nodes"] + 4 * T * Ns,
+        "forest_posterior_kernel": 4 * T * Ns + 4 * M * env["leaves"] + 4 * M * Ns,
+        "fill_kernel": 4 * M * (N // 4), "lowres_scatter_kernel": 8 * M * Ns + 8 * Ns,
+        "upsample_kernel": 4 * M * (N // 4) + 4 * M * N,
+        "unary_from_posteriors_kernel": 8 * M * N,
+        # C0 lattice construction (permutohedral.cpp:140-321)
+        "lattice_embed_kernel<D>": mean(lambda d, V: 4 * d * N + 8 * (d + 1) * N + 2 * d * V),
+        "remap_offsets_kernel": mean(lambda d, V: 8 * (d + 1) * N), "csr_fill_kernel": mean(lambda d, V: 16 * (d + 1) * N),
+        "first_flags_kernel": mean(lambda d, V: 8 * (d + 1) * N), "assign_ids_kernel": mean(lambda d, V: 8 * (d + 1) * N),
+        # C1 mean-field iteration (permutohedral.cpp:529-589, densecrf.cpp:98-131)
+        "softmax_init_kernel": 8 * M * N,
+        "splat_kernel": mean(lambda d, V: 4 * M * N + 8 * (d + 1) * N + 4 * N + 4 * M * V),
+        "blur_coop_kernel": mean(lambda d, V: (d + 1) * (8 * M * V + 8 * V) + 4 * M * V),
+        "blur_kernel": mean(lambda d, V: 8 * M * V + 8 * V),
+        "slice_softmax_kernel<MP>": sum(8 * (d + 1) * N + 4 * N + 4 * M * V for d, V in lat) + 8 * M * N,
+    }
+    return table.get(name)
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -225,6 +257,8 @@ def run_gpu(args, rank, world, local_rank):
         return ms, stg, ctx.kernel_launches - l0, rep
 
     dev_ms, stage, launches, _ = resident_pass(False)
+    lat_info = [ctx.keyframe_lattice_info(k) for k in range(2)]
+    n_samples = int(((frames[0][1][::2, ::2] >= 500) & (frames[0][1][::2, ::2] <= 15000)).sum())
     dev_ms_prof, _, _, prof = resident_pass(True)
 
     # ---- several keyframes in flight: C contexts on this GPU, one host thread each (keyframes are independent, the
@@ -266,7 +300,7 @@ def run_gpu(args, rank, world, local_rank):
             c.close()
         return dt_
 
-    sweep = [args.inflight] if args.inflight > 0 else [1, 2, 3, 4]
+    sweep = [] if args.quick else ([args.inflight] if args.inflight > 0 else [1, 2, 3, 4])
     inflight = {}
     for C_ in sweep:
         barrier()
@@ -307,19 +341,34 @@ def run_gpu(args, rank, world, local_rank):
         # dominant kernel = largest accumulated device time in the timed region
         top = sorted(prof.items(), key=lambda kv: -kv[1][0])
         kernel_table = [{"kernel": n, "ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
-                         "us_per_launch": 1000.0 * ms / max(cnt, 1)} for n, (ms, cnt) in top[:12]]
+                         "us_per_launch": 1000.0 * ms / max(cnt, 1)} for n, (ms, cnt) in top[:16]]
+        info = ctx.info
+        env = {"N": W * H, "M": int(info.total_classes), "Ns": int(n_samples), "D": int(info.feature_length),
+               "T": int(info.num_trees), "nodes": int(info.total_nodes), "leaves": int(info.total_leaves),
+               "P": int(info.patch_size), "lat": lat_info}
+        for row, (n, (ms, cnt)) in zip(kernel_table, top[:16]):
+            ab = algo_bytes(n, env)
+            if ab is not None:
+                row["algorithmic_bytes_per_launch"] = int(ab)
+                row["achieved_gbs"] = ab / (ms / max(cnt, 1) / 1000.0) / 1e9
+                row["frac_of_hbm_peak"] = row["achieved_gbs"] / peak
         dom_name, (dom_ms, dom_cnt) = top[0]
-        N, M = W * H, 17
-        algo = ALGO_BYTES.get(dom_name)
-        roof = None
-        if algo is not None:
-            ach = algo(N, M) / (dom_ms / dom_cnt / 1000.0) / 1e9
-            roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo(N, M),
-                    "us_per_launch": 1000.0 * dom_ms / dom_cnt}
-        else:
-            roof = {"bound": "hbm", "kernel": dom_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                    "traffic": None, "peak_source": peak_src, "us_per_launch": 1000.0 * dom_ms / dom_cnt}
+        ab = algo_bytes(dom_name, env)
+        ach = ab / (dom_ms / dom_cnt / 1000.0) / 1e9 if ab is not None else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full` captures
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom_name, {}).get("dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(ab) if ab is not None else None,
+                "us_per_launch": 1000.0 * dom_ms / dom_cnt,
+                "lattices": [{"d": d, "vertices": V} for d, V in lat_info]}
+        # whole-step roofline: algorithmic bytes of every launch of the step / the step's device time
+        step_bytes = sum((algo_bytes(n, env) or 0) * cnt / args.steps for n, (ms, cnt) in top)
+        roof["step_algorithmic_bytes"] = int(step_bytes)
+        roof["step_achieved"] = step_bytes / (dev_ms_max / args.steps / 1000.0) / 1e9
+        roof["step_frac"] = roof["step_achieved"] / peak
         sweep_out = {str(C_): {"resident_kf_s": total_kf / (a / 1000.0), "e2e_kf_s": total_kf / (b / 1000.0)}
                      for C_, (a, b) in inflight_max.items()}
         line = {
@@ -340,7 +389,7 @@ def run_gpu(args, rank, world, local_rank):
                             "(%.3f ms/step vs %.3f ms/step in the timed pass)" % (dev_ms_prof / args.steps, dev_ms / args.steps),
             "ms_per_meanfield_iter": stage.get("meanfield_ms", 0.0) / args.steps / KF["iters"],
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and not args.quick:
             import oracle
             oracle.build(ref=False)
             procs = max(1, min(os.cpu_count() or 1, 32))
@@ -362,6 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="skip the keyframes-in-flight sweep and the cpu_baseline leg (profiling runs)")
     ap.add_argument("--inflight", type=int, default=0,
                     help="keyframes in flight per GPU (one context + host thread each); 0 = sweep 1,2,3,4 and report the best")
     args = ap.parse_args()

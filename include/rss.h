@@ -137,6 +137,11 @@ rss_status rss_crf_add_pairwise_bilateral(rss_crf* crf, int W, int H, float sx, 
  * labels: host N bytes per layer, gated argmax of src/segmenter.cpp:645-657 (label = argmax if Q > 2/M
  * else unknown_label[layer]); pass unknown_label < 0 for the plain DenseCRF::map argmax (densecrf.cpp:200-208). */
 rss_status rss_crf_inference(rss_crf* crf, int layer, int iters, float* Q, uint8_t* labels, const int* unknown_label);
+/* DenseCRF::startInference / stepInference / currentMap (densecrf.cpp:178-211): Q stays on the device between
+ * calls; rss_crf_current copies the current marginals and/or their (gated) argmax back, arguments as above. */
+rss_status rss_crf_start_inference(rss_crf* crf);
+rss_status rss_crf_step_inference(rss_crf* crf, int steps);
+rss_status rss_crf_current(rss_crf* crf, int layer, float* Q, uint8_t* labels, const int* unknown_label);
 /* number of lattice vertices of pairwise term k (diagnostics) */
 rss_status rss_crf_lattice_size(rss_crf* crf, int k, int* vertices);
 /* Permutohedral::compute on pairwise term k without normalisation (permutohedral.cpp:596-604):
@@ -179,6 +184,13 @@ rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, const uint16_t
 /* Makes a frame resident on the device (H2D copy only).  Every call that takes rgb/depth_mm accepts NULL for
  * both to work on the resident frame instead: that is how the device-resident throughput is measured. */
 rss_status rss_upload_frame(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth_mm, int W, int H);
+/* Page-locked host memory for frame / label staging buffers (so that a C++ host needs no CUDA headers): copies
+ * from and to such buffers run at full PCIe rate and asynchronously.  Not tied to a context. */
+void* rss_host_alloc(size_t bytes);
+void rss_host_free(void* p);
+/* Diagnostics of the last rss_segment_keyframe: feature dimension and vertex count of its lattice k
+ * (0 = Gaussian 3-D, 1 = bilateral 5-D); RSS_ERR_STATE before the first keyframe. */
+rss_status rss_keyframe_lattice_info(rss_ctx* ctx, int k, int* d, int* vertices);
 
 /* ---------------------------------------------------------------------------------------------------
  * Instrumentation: device time (CUDA events on the context's stream) of the stages of the last call,

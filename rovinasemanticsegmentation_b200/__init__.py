@@ -216,6 +216,12 @@ class Context:
                                                    C.byref(params), _ptr(labels, C.c_uint8), _ptr(Q, C.c_float)))
         return (labels, Q) if want_Q else labels
 
+    def keyframe_lattice_info(self, k):
+        """(feature dimension, vertex count) of lattice k of the last segment_keyframe call."""
+        d, v = C.c_int(0), C.c_int(0)
+        self._check(self._lib.rss_keyframe_lattice_info(self.h, int(k), C.byref(d), C.byref(v)))
+        return d.value, v.value
+
     def crf(self, N, M):
         return DenseCRF(self, N, M)
 

@@ -46,5 +46,19 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST_BIN = os.path.join(HERE, "host", "keyframe_worker")
+
+
+def build_host(force=False):
+    """C++ host programs over the C ABI (g++, no CUDA headers needed): the multi-GPU keyframe worker."""
+    src = os.path.join(HERE, "host", "keyframe_worker.cpp")
+    hdr = os.path.join(HERE, "host", "rss_adapters.hpp")
+    if force or _newer(src, HOST_BIN) or _newer(hdr, HOST_BIN) or _newer(OUT, HOST_BIN):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", HOST_BIN, src, "-L" + HERE, "-lrss",
+                               "-Wl,-rpath,$ORIGIN/..", "-lpthread"])
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

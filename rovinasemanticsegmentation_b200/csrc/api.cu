@@ -373,6 +373,15 @@ extern "C" rss_status rss_load_forest_memory(rss_ctx* ctx, const void* bytes, si
     return load_forest_bytes(ctx, static_cast<const unsigned char*>(bytes), size);
 }
 
+extern "C" void* rss_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void rss_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" rss_status rss_destroy(rss_ctx* ctx) {
     if (!ctx) return RSS_ERR_INVALID;
     free_ctx(ctx);

@@ -344,7 +344,9 @@ static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
 }
 
 // the mean-field loop, fully enqueued (no host synchronisation).  labels_dev may be NULL.
-rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_dev) {
+// init: start from Q0 = expAndNormalize(-unary) (DenseCRF::inference / startInference); otherwise continue from the
+// resident Q (DenseCRF::stepInference).
+rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_dev, bool init = true) {
     rss_ctx* ctx = crf->ctx;
     cudaStream_t s0 = ctx->s0;
     const int N = crf->N, Mp = crf->Mp, K = (int)crf->kernels.size();
@@ -352,10 +354,11 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
     float* Q = crf->Q.as<float>();
     const float* U = crf->unary.as<float>();
     const int G = Mp / 4;
-    RSS_LAUNCH(ctx, softmax_init_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, U, N, G, Mp, ls, Q);
+    if (init) RSS_LAUNCH(ctx, softmax_init_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, U, N, G, Mp, ls, Q);
     if (iters <= 0 || K == 0) {
-        if (iters > 0) {  // no pairwise terms: every iteration reproduces expAndNormalize(-unary)
-        }
+        // no pairwise terms: every iteration reproduces expAndNormalize(-unary), i.e. Q0
+        if (!init && K == 0 && iters > 0)
+            RSS_LAUNCH(ctx, softmax_init_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, U, N, G, Mp, ls, Q);
         if (labels_dev)
             RSS_LAUNCH(ctx, argmax_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, (const float*)Q, N, G, Mp, ls, labels_dev);
         RSS_CU(ctx, cudaGetLastError());
@@ -630,22 +633,9 @@ extern "C" rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float
     return RSS_OK;
 }
 
-extern "C" rss_status rss_crf_inference(rss_crf* crf, int layer, int iters, float* Q, uint8_t* labels,
-                                        const int* unknown_label) {
-    if (!crf) return RSS_ERR_INVALID;
+// device -> host copies of the current Q (per-layer matrices, layers concatenated for layer = -1) and label maps
+static rss_status crf_fetch(rss_crf* crf, int layer, float* Q, uint8_t* labels) {
     rss_ctx* ctx = crf->ctx;
-    if (layer < -1 || layer >= crf->n_layers || iters < 0) return ctx->fail(RSS_ERR_INVALID, "bad layer or iteration count");
-    RSS_CU(ctx, cudaSetDevice(ctx->device));
-    int unk[RSS_MAX_LAYERS];
-    for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = -1;
-    if (unknown_label) {
-        if (layer < 0) for (int l = 0; l < crf->n_layers; l++) unk[l] = unknown_label[l];
-        else unk[layer] = unknown_label[0];
-    }
-    cudaEventRecord(ctx->ev[6], ctx->s0);
-    rss_status st = crf_run(crf, iters, unk, labels ? crf->labels.as<uint8_t>() : nullptr);
-    if (st != RSS_OK) return st;
-    cudaEventRecord(ctx->ev[7], ctx->s0);
     const int N = crf->N;
     if (Q) {
         if (layer < 0 && crf->n_layers == 1) layer = 0;
@@ -669,15 +659,67 @@ extern "C" rss_status rss_crf_inference(rss_crf* crf, int layer, int iters, floa
         else RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.as<uint8_t>() + (size_t)layer * N, (size_t)N, cudaMemcpyDeviceToHost, ctx->s0));
     }
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
-    ctx->tim.meanfield_ms = ms;
     for (Lattice* L : crf->kernels) {
         uint32_t h[2];
         RSS_CU(ctx, cudaMemcpy(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost));
         if (h[1]) return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
     }
     return RSS_OK;
+}
+static void fill_unknown(const rss_crf* crf, int layer, const int* unknown_label, int* unk) {
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = -1;
+    if (unknown_label) {
+        if (layer < 0) for (int l = 0; l < crf->n_layers; l++) unk[l] = unknown_label[l];
+        else unk[layer] = unknown_label[0];
+    }
+}
+
+extern "C" rss_status rss_crf_inference(rss_crf* crf, int layer, int iters, float* Q, uint8_t* labels,
+                                        const int* unknown_label) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (layer < -1 || layer >= crf->n_layers || iters < 0) return ctx->fail(RSS_ERR_INVALID, "bad layer or iteration count");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    int unk[RSS_MAX_LAYERS];
+    fill_unknown(crf, layer, unknown_label, unk);
+    cudaEventRecord(ctx->ev[6], ctx->s0);
+    rss_status st = crf_run(crf, iters, unk, labels ? crf->labels.as<uint8_t>() : nullptr);
+    if (st != RSS_OK) return st;
+    cudaEventRecord(ctx->ev[7], ctx->s0);
+    st = crf_fetch(crf, layer, Q, labels);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+    ctx->tim.meanfield_ms = ms;
+    return st;
+}
+
+// DenseCRF::startInference / stepInference / currentMap (densecrf.cpp:178-211): Q stays on the device between steps
+extern "C" rss_status rss_crf_start_inference(rss_crf* crf) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    return crf_run(crf, 0, nullptr, nullptr, true);
+}
+extern "C" rss_status rss_crf_step_inference(rss_crf* crf, int steps) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (steps < 1) return ctx->fail(RSS_ERR_INVALID, "steps must be >= 1");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    return crf_run(crf, steps, nullptr, nullptr, false);
+}
+extern "C" rss_status rss_crf_current(rss_crf* crf, int layer, float* Q, uint8_t* labels, const int* unknown_label) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (layer < -1 || layer >= crf->n_layers) return ctx->fail(RSS_ERR_INVALID, "bad layer");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    if (labels) {
+        int unk[RSS_MAX_LAYERS];
+        fill_unknown(crf, layer, unknown_label, unk);
+        const LayerSpec ls = make_layers(crf, unk);
+        RSS_LAUNCH(ctx, argmax_kernel, rss_div_up((long long)crf->N * 8, 256), 256, 0, ctx->s0, (const float*)crf->Q.as<float>(),
+                   crf->N, crf->Mp / 4, crf->Mp, ls, crf->labels.as<uint8_t>());
+    }
+    return crf_fetch(crf, layer, Q, labels);
 }
 
 extern "C" rss_status rss_crf_unary_reset(rss_crf* crf) {
@@ -816,5 +858,14 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]); ctx->tim.meanfield_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[5]); ctx->tim.d2h_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]); ctx->tim.total_ms = ms;
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_keyframe_lattice_info(rss_ctx* ctx, int k, int* d, int* vertices) {
+    if (!ctx) return RSS_ERR_INVALID;
+    rss_crf* crf = ctx->keyframe_crf;
+    if (!crf || k < 0 || k >= (int)crf->kernels.size()) return ctx->fail(RSS_ERR_STATE, "no keyframe lattice with this index");
+    if (d) *d = crf->kernels[k]->d;
+    if (vertices) *vertices = crf->kernels[k]->V_host;
     return RSS_OK;
 }
