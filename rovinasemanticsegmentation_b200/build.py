@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librss.so")
-SOURCES = ["api.cu", "features.cu", "normals.cu", "forest.cu", "lattice.cu", "crf.cu"]
+SOURCES = ["api.cu", "features.cu", "normals.cu", "forest.cu", "lattice.cu", "meanfield.cu", "crf.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
@@ -24,6 +24,7 @@ def _newer(a, b):
 
 
 def build(force=False, verbose=False):
+    extra = os.environ.get("RSS_NVCC_DEFS", "").split()  # e.g. "-DRSS_TILE_MINB=2" for tuning sweeps
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "rss.h")]
     objs = []
     jobs = []
@@ -32,7 +33,7 @@ def build(force=False, verbose=False):
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or any(_newer(d, o) for d in deps):
-            jobs.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0 or verbose:

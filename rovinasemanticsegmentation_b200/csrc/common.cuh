@@ -138,6 +138,8 @@ struct rss_ctx {
     rss::PinBuf pin_in, pin_out, pin_small;
     rss_timings tim = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
+    unsigned fused_attr_mask = 0;  // meanfield_tile_kernel instances whose dynamic shared memory limit was raised
+    unsigned tile_attr_mask = 0;  // tile_csr_build_kernel<D> instances whose dynamic shared memory limit was raised
     std::string err;
     rss_crf* keyframe_crf = nullptr;  // cached CRF of rss_segment_keyframe
     // optional per-kernel timing (rss_profile_enable)
@@ -192,6 +194,23 @@ struct rss_ctx {
         if ((ctx)->profile) {                                                    \
             cudaEventRecord(pb__, (stream));                                     \
             (ctx)->prof_pending.push_back(rss_ctx::Pending{#kernel, pa__, pb__}); \
+        }                                                                        \
+    } while (0)
+
+// the same for kernels whose name cannot be stringified (template instantiations with several arguments)
+#define RSS_LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, stream, ...)     \
+    do {                                                                         \
+        cudaEvent_t pa__ = nullptr, pb__ = nullptr;                              \
+        if ((ctx)->profile) {                                                    \
+            pa__ = (ctx)->prof_event();                                          \
+            pb__ = (ctx)->prof_event();                                          \
+            cudaEventRecord(pa__, (stream));                                     \
+        }                                                                        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        (ctx)->launches++;                                                       \
+        if ((ctx)->profile) {                                                    \
+            cudaEventRecord(pb__, (stream));                                     \
+            (ctx)->prof_pending.push_back(rss_ctx::Pending{name, pa__, pb__});   \
         }                                                                        \
     } while (0)
 

@@ -11,17 +11,23 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "kernels.hpp"
 #include "lattice.cuh"
+#include "meanfield.cuh"
 
 namespace rss {
 float lattice_alpha(int d);
-rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp);
+rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp,
+                         bool want_csr);
+rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G);
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
                           int Mp);
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
                    int out_stride);
 rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L);
+void launch_run_count(rss_ctx* c, cudaStream_t st, Lattice& L);
 
 constexpr int CRF_MAX_KERNELS = 4;
 constexpr int CRF_MAX_CH = 32;
@@ -343,6 +349,105 @@ static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
     return ls;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused path (meanfield.cu): K <= 2 lattices over spatially coherent points.  n iterations = n + 1 point kernels
+// (Q0 + splat | slice + soft-max + splat | ... | slice + soft-max + labels) and n cooperative blur launches.
+// ---------------------------------------------------------------------------------------------------------------
+static bool crf_fused_order(const rss_crf* crf, int* first, int* second) {
+    const int K = (int)crf->kernels.size();
+    if (K < 1 || K > FUSED_MAX_LAT) return false;
+    const int G = crf->Mp / 4;
+    for (const Lattice* L : crf->kernels)
+        if (!L->ordered || L->tile_TP != fused_tile_points(G)) return false;
+    if (K == 1) {
+        *first = 0; *second = -1;
+        return fused_signature_supported(G, crf->kernels[0]->d + 1, 0);
+    }
+    const int a = crf->kernels[0]->d + 1, b = crf->kernels[1]->d + 1;
+    if (fused_signature_supported(G, a, b)) { *first = 0; *second = 1; return true; }
+    if (fused_signature_supported(G, b, a)) { *first = 1; *second = 0; return true; }
+    return false;
+}
+static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_dev, int i0, int i1) {
+    rss_ctx* ctx = crf->ctx;
+    cudaStream_t s0 = ctx->s0;
+    const int N = crf->N, Mp = crf->Mp, G = Mp / 4;
+    Lattice* Ls[FUSED_MAX_LAT] = {crf->kernels[i0], i1 >= 0 ? crf->kernels[i1] : nullptr};
+    const int K = i1 >= 0 ? 2 : 1;
+    const LayerSpec ls0 = make_layers(crf, unknown);
+    FusedLayers ls;
+    ls.n_layers = ls0.n_layers;
+    for (int l = 0; l <= RSS_MAX_LAYERS; l++) ls.off[l] = ls0.off[l];
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) {
+        ls.unknown[l] = ls0.unknown[l];
+        const int Ml = ls0.off[l + 1] - ls0.off[l];
+        ls.gate[l] = (ls0.unknown[l] >= 0 && Ml > 0) ? (float)(2.0 / (double)Ml) : -INFINITY;  // segmenter.cpp:647
+    }
+    ls.aligned = 1;
+    for (int l = 0; l < ls.n_layers; l++)
+        if (ls.off[l] % 4) ls.aligned = 0;
+    DevBuf* tgt[FUSED_MAX_LAT];
+    DevBuf* spare[FUSED_MAX_LAT];
+    DevBuf* res[FUSED_MAX_LAT];
+    FusedArgs fa;
+    BlurMultiArgs ba;
+    ba.K = K;
+    for (int k = 0; k < FUSED_MAX_LAT; k++) {
+        if (k >= K) {
+            fa.lat[k] = FusedLat{}; fa.counts[k] = nullptr; fa.pairs[k] = nullptr; fa.ent_meta[k] = nullptr;
+            fa.tile_nent[k] = nullptr;
+            continue;
+        }
+        Lattice& L = *Ls[k];
+        tgt[k] = L.splat_target ? &L.val_b : &L.val_a;
+        spare[k] = L.splat_target ? &L.val_a : &L.val_b;
+        res[k] = &L.val_c;
+        FusedLat& f = fa.lat[k];
+        f.offsets = L.offsets.as<int>(); f.bary = L.bary.as<float>(); f.norm = L.norm.as<float>();
+        f.potts = L.potts_w; f.alpha = lattice_alpha(L.d);
+        f.pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
+        f.post = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_AFTER;
+        fa.counts[k] = L.counts.as<uint32_t>();
+        fa.pairs[k] = L.tile_pairs.as<uint2>(); fa.ent_meta[k] = L.tile_ent_meta.as<int2>();
+        fa.tile_nent[k] = L.tile_nent.as<int>();
+        ba.nbr[k] = L.nbr.as<int2>(); ba.counts[k] = L.counts.as<uint32_t>(); ba.d1[k] = L.d + 1; ba.vcap[k] = L.vcap;
+    }
+    const int d1a = Ls[0]->d + 1, d1b = K > 1 ? Ls[1]->d + 1 : 0;
+    const int maxd1 = std::max(d1a, d1b);
+    const float* U = crf->unary.as<float>();
+    float* Q = crf->Q.as<float>();
+    Lattice& L0 = *Ls[0];
+    // pass 0: Q0 = expAndNormalize(-unary) and its splat
+    for (int k = 0; k < K; k++) { fa.lat[k].vin = nullptr; fa.lat[k].vout = tgt[k]->as<float>(); }
+    launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, nullptr, N, G, ls, 2);
+    for (int it = 0; it < iters; it++) {
+        for (int k = 0; k < K; k++) {
+            ba.ping[k] = tgt[k]->as<float4>(); ba.pong[k] = spare[k]->as<float4>(); ba.zero[k] = res[k]->as<float4>();
+        }
+        launch_blur_multi(ctx, s0, ba, G, L0.counts.as<unsigned int>() + 8, L0.barrier_base);
+        L0.barrier_base += (unsigned int)(maxd1 - 1) * (unsigned int)blur_multi_grid(ctx);
+        for (int k = 0; k < K; k++) {
+            DevBuf* X = (ba.d1[k] % 2 == 0) ? tgt[k] : spare[k];  // blurred result
+            DevBuf* Y = (ba.d1[k] % 2 == 0) ? spare[k] : tgt[k];
+            DevBuf* Z = res[k];                                    // cleared by the blur kernel: next splat target
+            res[k] = X; spare[k] = Y; tgt[k] = Z;
+            fa.lat[k].vin = res[k]->as<float>();
+            fa.lat[k].vout = tgt[k]->as<float>();
+        }
+        const bool last = it == iters - 1;
+        launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, last ? labels_dev : nullptr, N, G, ls, last ? (1 | 4) : (1 | 2));
+    }
+    // restore the two-table convention of the generic path: val_a = the all-zero table, splat_target = 0
+    for (int k = 0; k < K; k++) {
+        Lattice& L = *Ls[k];
+        const DevBuf t = *tgt[k], r = *res[k], sp = *spare[k];
+        L.val_a = t; L.val_b = r; L.val_c = sp;
+        L.splat_target = 0;
+    }
+    RSS_CU(ctx, cudaGetLastError());
+    return RSS_OK;
+}
+
 // the mean-field loop, fully enqueued (no host synchronisation).  labels_dev may be NULL.
 // init: start from Q0 = expAndNormalize(-unary) (DenseCRF::inference / startInference); otherwise continue from the
 // resident Q (DenseCRF::stepInference).
@@ -364,6 +469,8 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
         RSS_CU(ctx, cudaGetLastError());
         return RSS_OK;
     }
+    int fi0 = 0, fi1 = -1;
+    if (init && crf_fused_order(crf, &fi0, &fi1)) return crf_run_fused(crf, iters, unknown, labels_dev, fi0, fi1);
     for (int it = 0; it < iters; it++) {
         SliceArgs sa;
         sa.K = K;
@@ -412,8 +519,10 @@ static uint32_t next_pow2(uint64_t v) {
 // Builds one more lattice from device-resident features on stream `st`.
 // sync = true : waits, checks the overflow flag and regrows the hash table until it fits (reference-shaped API).
 // sync = false: only enqueues; the caller checks crf_lattice_overflow() later (keyframe path, no host sync).
+// raster: the caller guarantees image raster order (keyframe path) -> the fused mean-field path is used without
+// measuring the run statistic.
 rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_dev, int d, float potts_w, int norm_type,
-                              bool sync) {
+                              bool sync, bool raster = false) {
     rss_ctx* ctx = crf->ctx;
     if ((int)crf->kernels.size() >= CRF_MAX_KERNELS) return ctx->fail(RSS_ERR_INVALID, "too many pairwise terms (max 4)");
     if (norm_type < RSS_NORMALIZE_BEFORE || norm_type > RSS_NORMALIZE_SYMMETRIC)
@@ -433,16 +542,27 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
     if (L->hcap > hcap && L->d == d) hcap = L->hcap;
     if (L->want_hcap > hcap) hcap = L->want_hcap;
     for (;;) {
-        rss_status rc = lattice_build(ctx, st, *L, feat_dev, crf->N, d, hcap, crf->Mp);
+        // raster order: the tile kernel does the splat, the vertex-major CSR of the generic path is not needed
+        const bool tile_ok = fused_group_supported(crf->Mp / 4);
+        rss_status rc = lattice_build(ctx, st, *L, feat_dev, crf->N, d, hcap, crf->Mp, !(raster && tile_ok));
         if (rc != RSS_OK) return rc;
         rc = lattice_normalization(ctx, st, *L);
         if (rc != RSS_OK) return rc;
+        if (tile_ok) {
+            rc = lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4);
+            if (rc != RSS_OK) return rc;
+        }
+        L->ordered = raster;
         if (!sync) return RSS_OK;
+        launch_run_count(ctx, st, *L);
         uint32_t h[8];
         RSS_CU(ctx, cudaMemcpyAsync(h, L->counts.ptr, sizeof(h), cudaMemcpyDeviceToHost, st));
         RSS_CU(ctx, cudaStreamSynchronize(st));
         if (!h[1]) {
             L->V_host = (int)h[0];
+            L->runs = (long long)h[5];
+            // coherent point order: on average every vertex run spans more than two points
+            L->ordered = raster || 2 * L->runs <= (long long)maxv;
             return RSS_OK;
         }
         if ((uint64_t)hcap >= 2 * next_pow2(2 * maxv) || hcap >= (1u << 30))
@@ -815,9 +935,9 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
         RSS_CU(ctx, cudaStreamWaitEvent(sA, ctx->ev_cloud, 0));
         RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, sA, N, ctx->fr.xyz.as<float4>(),
                    1.0f / prm->sigma_xyz, t[0], t[1], t[2], f3);
-        st = crf_add_kernel_dev(crf, sA, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, false);
+        st = crf_add_kernel_dev(crf, sA, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, false, true);
         if (st != RSS_OK) return st;
-        st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false);
+        st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false, true);
         if (st != RSS_OK) return st;
         RSS_CU(ctx, cudaEventRecord(crf->ev_join[0], sA));
         RSS_CU(ctx, cudaEventRecord(crf->ev_join[1], sB));

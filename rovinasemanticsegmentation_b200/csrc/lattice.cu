@@ -16,6 +16,7 @@
 //    vertices for 2*10^6 adds per channel) while staying load-balanced in the many-vertices regime.
 //  * No kernel needs the vertex count on the host: V lives in device memory, launches are sized by capacity.
 #include "lattice.cuh"
+#include "meanfield.cuh"
 #include "scan.cuh"
 
 namespace rss {
@@ -212,7 +213,22 @@ __global__ void __launch_bounds__(256) remap_offsets_kernel(int* __restrict__ of
     const int slot = offsets[k];
     const uint32_t id = slot_id[slot];
     offsets[k] = (int)id;
-    if (id < vcap) atomicAdd(deg + id, 1u);
+    if (deg && id < vcap) atomicAdd(deg + id, 1u);
+}
+
+// counts[5] += number of (point, corner) pairs whose vertex differs from the same corner of the previous point: the
+// number of atomics the fused mean-field splat (meanfield.cu) would issue per channel group with unbounded chunks
+__global__ void __launch_bounds__(256) run_count_kernel(const int* __restrict__ offsets, size_t n, int d1,
+                                                        uint32_t* __restrict__ counts) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool differs = !counts[1] && k < n && (k < (size_t)d1 || offsets[k] != offsets[k - d1]);
+    const unsigned m = __ballot_sync(0xffffffffu, differs);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counts + 5, (uint32_t)__popc(m));
+}
+void launch_run_count(rss_ctx* c, cudaStream_t st, Lattice& L) {
+    const size_t nnz = (size_t)L.N * (L.d + 1);
+    RSS_LAUNCH(c, run_count_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz, L.d + 1,
+               L.counts.as<uint32_t>());
 }
 
 // blur neighbours (:303-318): along axis j, n1 = key - 1 with coordinate j set to key[j] + d, n2 the opposite
@@ -473,7 +489,8 @@ float lattice_alpha(int d) { return 1.0f / (1 + powf(2, -(float)d)); }  // :571
 
 // Allocates for capacity hcap and enqueues the whole construction on `st`.  feat: device [N][d].  Mp = padded
 // channel count of the value tables.  No host synchronisation; overflow is reported in counts[1].
-rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp) {
+rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp,
+                         bool want_csr) {
     if (d < 1 || d > LAT_MAX_D) return ctx->fail(RSS_ERR_INVALID, "pairwise feature dimension must be in [1, 7]");
     L.d = d; L.N = N; L.hcap = hcap; L.vcap = hcap / 2;
     const int d1 = d + 1;
@@ -492,22 +509,30 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     RSS_CU(ctx, L.deg.reserve((size_t)(L.vcap + 2) * 4));
     RSS_CU(ctx, L.cursor.reserve((size_t)(L.vcap + 1) * 4));
     RSS_CU(ctx, L.nseg.reserve((size_t)(L.vcap + 2) * 4));
-    RSS_CU(ctx, L.csr_pt.reserve(nnz * 4));
-    RSS_CU(ctx, L.csr_w.reserve(nnz * 4));
-    RSS_CU(ctx, L.seg_v.reserve((size_t)L.maxseg * 4));
-    RSS_CU(ctx, L.seg_begin.reserve((size_t)L.maxseg * 4));
-    RSS_CU(ctx, L.seg_end.reserve((size_t)L.maxseg * 4));
+    if (want_csr) {
+        RSS_CU(ctx, L.csr_pt.reserve(nnz * 4));
+        RSS_CU(ctx, L.csr_w.reserve(nnz * 4));
+        RSS_CU(ctx, L.seg_v.reserve((size_t)L.maxseg * 4));
+        RSS_CU(ctx, L.seg_begin.reserve((size_t)L.maxseg * 4));
+        RSS_CU(ctx, L.seg_end.reserve((size_t)L.maxseg * 4));
+    }
+    L.have_csr = want_csr;
+    L.tile_TP = 0;
     RSS_CU(ctx, L.val_a.reserve((size_t)(L.vcap + 1) * Mp * 4));
     RSS_CU(ctx, L.val_b.reserve((size_t)(L.vcap + 1) * Mp * 4));
+    RSS_CU(ctx, L.val_c.reserve((size_t)(L.vcap + 1) * Mp * 4));
     RSS_CU(ctx, L.scan_tmp.reserve((scan_tmp_elems(nnz > hcap ? nnz : hcap) + 8) * 4));
     uint32_t* counts = L.counts.as<uint32_t>();
     RSS_CU(ctx, cudaMemsetAsync(L.table.ptr, 0xFF, (size_t)hcap * sizeof(Key128), st));
     RSS_CU(ctx, cudaMemsetAsync(L.first_ref.ptr, 0xFF, (size_t)hcap * 4, st));
     RSS_CU(ctx, cudaMemsetAsync(counts, 0, 64, st));
-    RSS_CU(ctx, cudaMemsetAsync(L.deg.ptr, 0, (size_t)(L.vcap + 2) * 4, st));
-    RSS_CU(ctx, cudaMemsetAsync(L.cursor.ptr, 0, (size_t)(L.vcap + 1) * 4, st));
+    if (want_csr) {
+        RSS_CU(ctx, cudaMemsetAsync(L.deg.ptr, 0, (size_t)(L.vcap + 2) * 4, st));
+        RSS_CU(ctx, cudaMemsetAsync(L.cursor.ptr, 0, (size_t)(L.vcap + 1) * 4, st));
+    }
     RSS_CU(ctx, cudaMemsetAsync(L.val_a.ptr, 0, (size_t)(L.vcap + 1) * Mp * 4, st));
     RSS_CU(ctx, cudaMemsetAsync(L.val_b.ptr, 0, (size_t)(L.vcap + 1) * Mp * 4, st));
+    RSS_CU(ctx, cudaMemsetAsync(L.val_c.ptr, 0, (size_t)(L.vcap + 1) * Mp * 4, st));
     L.splat_target = 0;
     L.barrier_base = 0;
     switch (d) {
@@ -528,7 +553,7 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
                L.first_ref.as<uint32_t>(), L.rank.as<uint32_t>(), L.table.as<Key128>(), L.vcap, L.slot_id.as<uint32_t>(),
                L.vkeys.as<Key128>(), counts);
     RSS_LAUNCH(ctx, remap_offsets_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
-               L.slot_id.as<uint32_t>(), L.deg.as<uint32_t>(), counts, L.vcap);
+               L.slot_id.as<uint32_t>(), want_csr ? L.deg.as<uint32_t>() : (uint32_t*)nullptr, counts, L.vcap);
     switch (d) {
         case 1: launch_neighbors<1>(ctx, st, L); break;
         case 2: launch_neighbors<2>(ctx, st, L); break;
@@ -537,6 +562,10 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
         case 5: launch_neighbors<5>(ctx, st, L); break;
         case 6: launch_neighbors<6>(ctx, st, L); break;
         default: launch_neighbors<7>(ctx, st, L); break;
+    }
+    if (!want_csr) {
+        RSS_CU(ctx, cudaGetLastError());
+        return RSS_OK;
     }
     // CSR: segments per row, row_start = scan(deg), seg_off = scan(nseg)
     RSS_LAUNCH(ctx, seg_count_kernel, rss_div_up((long long)L.vcap + 1, 256), 256, 0, st, L.deg.as<uint32_t>(), counts,
@@ -630,8 +659,11 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
         return ctx->fail(RSS_ERR_INVALID, "NO_NORMALIZATION is not supported on the device path");
     float* a = L.splat_target ? L.val_b.as<float>() : L.val_a.as<float>();
     float* b = L.splat_target ? L.val_a.as<float>() : L.val_b.as<float>();
-    RSS_LAUNCH(ctx, splat_ones_kernel, rss_div_up((long long)L.maxseg * 32, 256), 256, 0, st, L.seg_v.as<int>(),
-               L.seg_begin.as<uint32_t>(), L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_w.as<float>(), a);
+    if (L.have_csr)
+        RSS_LAUNCH(ctx, splat_ones_kernel, rss_div_up((long long)L.maxseg * 32, 256), 256, 0, st, L.seg_v.as<int>(),
+                   L.seg_begin.as<uint32_t>(), L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_w.as<float>(), a);
+    else  // no CSR (keyframe path): run-accumulating scatter over the points
+        launch_splat_ones_runs(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), N, d1, L.counts.as<uint32_t>(), a);
     float* s = a;
     float* d = b;
     for (int j = 0; j < d1; j++) {
@@ -646,6 +678,22 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
                L.counts.as<uint32_t>(), 1);
     RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(b),
                L.counts.as<uint32_t>(), 1);
+    RSS_CU(ctx, cudaGetLastError());
+    return RSS_OK;
+}
+
+// tile-local CSR for the fused mean-field kernel (after the normalisation: the pre-scale is folded into the weights)
+rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G) {
+    const int TP = fused_tile_points(G), d1 = L.d + 1;
+    const size_t ntiles = (size_t)rss_div_up(L.N, TP), cap = ntiles * TP * d1;
+    RSS_CU(ctx, L.tile_pairs.reserve(cap * sizeof(uint2)));
+    RSS_CU(ctx, L.tile_ent_meta.reserve(cap * sizeof(int2)));
+    RSS_CU(ctx, L.tile_nent.reserve(ntiles * 4));
+    const bool pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
+    launch_tile_csr_build(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), pre ? L.norm.as<float>() : nullptr, L.N, d1, TP, G * 16,
+                          L.counts.as<uint32_t>(), L.tile_pairs.as<uint2>(), L.tile_ent_meta.as<int2>(),
+                          L.tile_nent.as<int>());
+    L.tile_TP = TP;
     RSS_CU(ctx, cudaGetLastError());
     return RSS_OK;
 }

@@ -41,13 +41,19 @@ struct Lattice {
     DevBuf seg_begin;    // uint32[maxseg]
     DevBuf seg_end;      // uint32[maxseg]
     DevBuf val_a, val_b; // float[(vcap+1)][Mp] ping-pong value tables (row vcap stays zero)
+    DevBuf val_c;        // third table of the fused mean-field path (meanfield.cu)
+    DevBuf tile_pairs, tile_ent_meta, tile_nent;  // tile-local CSR of the splat matrix (meanfield.cu)
+    int tile_TP = 0;     // points per tile the tile CSR was built for (0 = not built)
+    bool have_csr = false;  // vertex-major CSR + segments (generic splat path) built
+    bool ordered = false;  // consecutive points share lattice vertices (raster order): the fused path applies
+    long long runs = -1;   // number of (point, corner) pairs whose vertex differs from the previous point's (diagnostics)
     DevBuf scan_tmp;
     uint32_t maxseg = 0;
     int splat_target = 0;  // which value table is all-zero and receives the next splat (0 = val_a)
     unsigned int barrier_base = 0;  // grid-barrier arrivals issued so far (counts[8] is the barrier word)
     void release() {
         DevBuf* b[] = {&table, &slot_id, &first_ref, &rank, &vkeys, &offsets, &bary, &nbr, &norm, &counts, &deg, &cursor, &nseg,
-                       &csr_pt, &csr_w, &seg_v, &seg_begin, &seg_end, &val_a, &val_b, &scan_tmp};
+                       &csr_pt, &csr_w, &seg_v, &seg_begin, &seg_end, &val_a, &val_b, &val_c, &scan_tmp, &tile_pairs, &tile_ent_meta, &tile_nent};
         for (DevBuf* p : b) p->release();
     }
 };

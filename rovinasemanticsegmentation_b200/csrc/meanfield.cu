@@ -1,0 +1,730 @@
+// Fused mean-field iteration for point sets whose order is spatially coherent (image raster order, the keyframe
+// path): ONE point-parallel kernel per iteration does slice (of the previous iteration's blurred tables) + Potts +
+// unary + per-layer soft-max + the SPLAT of the new marginals for the next iteration, plus one cooperative launch
+// that blurs every lattice of the CRF along all of its axes.  Reference: third-party/densecrf/src/densecrf.cpp:98-131
+// (expAndNormalize, inference), pairwise.cpp:63-80 (DenseKernel::filter), permutohedral.cpp:529-589 (sseCompute).
+//
+// Work decomposition of the point kernel: a thread is (chunk, channel group).  A chunk is a run of Pc CONSECUTIVE
+// points that the thread walks serially; the G = Mp/4 lanes of a chunk hold the point's label vector as one float4
+// each, so a value-table row (Mp floats) is read by G adjacent lanes as one contiguous 16*G-byte access.
+//   slice:    t -= -w * norm_i * sum_j (bary_ij * alpha) * blurred[vertex_ij]        (row gathers hit L1/L2)
+//   soft-max: per label layer across the G lanes (fixed-order all-gather through shuffles)
+//   splat:    per simplex corner j the thread keeps (current vertex, float4 accumulator); while consecutive points
+//             stay on the same vertex it only accumulates in registers, when the vertex changes it flushes ONE
+//             red.global.add.v4.f32.  Neighbouring pixels share lattice vertices (remainder-j corner of adjacent
+//             simplices is the same lattice point), so the atomic traffic is (number of runs), not (number of
+//             nonzeros), and no CSR of the splat matrix, no re-read of Q and no separate splat launch are needed.
+// Value tables rotate through three buffers per lattice: `res` (blurred result being sliced), `tgt` (all zero, receives
+// the splat) and `spare`; the blur ping-pongs between tgt and spare and zeroes the old `res`, which becomes the next tgt.
+#include <algorithm>
+#include <cstdlib>
+
+#include "kernels.hpp"
+#include "lattice.cuh"
+#include "meanfield.cuh"
+
+#ifndef RSS_TILE_MINB
+#define RSS_TILE_MINB 4  // resident CTAs per SM the point kernel is compiled for (register budget)
+#endif
+#ifndef RSS_TILE_PREFETCH
+#define RSS_TILE_PREFETCH 0  // request the streaming inputs of step s + 1 before step s gathers its rows
+#endif
+#ifndef RSS_TILE_IU
+#define RSS_TILE_IU 2  // splat segments a thread walks at once
+#endif
+#ifndef RSS_TILE_POINTS
+#define RSS_TILE_POINTS 512  // target points per tile (<= 512: the tile CSR build kernel's hash capacity)
+#endif
+
+namespace rss {
+
+template <int D1>
+__device__ __forceinline__ void load_row_i(const int* __restrict__ p, int (&o)[D1]) {
+    if constexpr (D1 % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < D1 / 4; k++) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(p) + k);
+            o[4 * k] = v.x; o[4 * k + 1] = v.y; o[4 * k + 2] = v.z; o[4 * k + 3] = v.w;
+        }
+    } else if constexpr (D1 % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < D1 / 2; k++) {
+            const int2 v = __ldg(reinterpret_cast<const int2*>(p) + k);
+            o[2 * k] = v.x; o[2 * k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D1; k++) o[k] = __ldg(p + k);
+    }
+}
+template <int D1>
+__device__ __forceinline__ void load_row_f(const float* __restrict__ p, float (&o)[D1]) {
+    if constexpr (D1 % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < D1 / 4; k++) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p) + k);
+            o[4 * k] = v.x; o[4 * k + 1] = v.y; o[4 * k + 2] = v.z; o[4 * k + 3] = v.w;
+        }
+    } else if constexpr (D1 % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < D1 / 2; k++) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(p) + k);
+            o[2 * k] = v.x; o[2 * k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D1; k++) o[k] = __ldg(p + k);
+    }
+}
+__device__ __forceinline__ void red_add_v4(float* dst, const float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile-local CSR of the splat matrix.  A tile is TP consecutive points (the points one CTA of the mean-field kernel
+// owns).  For every tile: the distinct lattice vertices its points touch ("entries") and, per entry, the list of
+// (local point, weight) pairs.  Built once per lattice by one CTA per tile with a shared-memory hash table (native
+// 32-bit CAS / integer adds only): insert keys -> count -> compact + scan -> fill.  weight = bary * norm_i when the
+// kernel is pre-normalised (DenseKernel::filter, pairwise.cpp:65-66), so the gather needs no norm lookup.
+// Entry meta: x = (start of the segment in the tile's pair array) | (length << 16), y = vertex id.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TILE_HASH = 8192;      // >= 2 * max pairs per tile (512 points * 8 corners)
+constexpr int TILE_MAX_PAIRS = 4096;
+constexpr int TILE_SEG = 8;          // pairs per splat segment (one thread walks one segment serially)
+constexpr int TILE_SMEM_BYTES = 2 * TILE_HASH * 4 + TILE_MAX_PAIRS * 2;
+
+__device__ __forceinline__ int2 block_excl_scan2(int a, int b, int2* total) {  // 256 threads
+    __shared__ int2 wsum[8];
+    __shared__ int2 btot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) wsum[w] = make_int2(ia, ib);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sa = 0, sb = 0;
+        for (int k = 0; k < 8; k++) { const int2 v = wsum[k]; wsum[k] = make_int2(sa, sb); sa += v.x; sb += v.y; }
+        btot = make_int2(sa, sb);
+    }
+    __syncthreads();
+    const int2 r = make_int2(ia - a + wsum[w].x, ib - b + wsum[w].y);
+    *total = btot;
+    __syncthreads();
+    return r;
+}
+
+template <int D1>
+__global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restrict__ offsets, const float* __restrict__ bary,
+                                                             const float* __restrict__ norm, int N, int TP, int row_bytes,
+                                                             const uint32_t* __restrict__ counts, uint2* __restrict__ pairs,
+                                                             int2* __restrict__ ent_meta, int* __restrict__ tile_nent) {
+    __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1];
+    extern __shared__ int tile_smem[];  // TILE_SMEM_BYTES, above the 48 KB static limit
+    int* hkeys = tile_smem;
+    int* hcnt = tile_smem + TILE_HASH;
+    unsigned short* pslot = reinterpret_cast<unsigned short*>(tile_smem + 2 * TILE_HASH);
+    const int tile = blockIdx.x;
+    const int base = tile * TP;
+    const int npts = min(TP, N - base);
+    const int npairs = npts * D1;
+    const size_t tb = (size_t)tile * TP * D1;
+    if (counts[1]) {
+        if (threadIdx.x == 0) tile_nent[tile] = 0;
+        return;
+    }
+    for (int i = threadIdx.x; i < TILE_HASH; i += 256) { hkeys[i] = -1; hcnt[i] = 0; }
+    if (threadIdx.x <= TILE_SEG) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int* off_t = offsets + (size_t)base * D1;
+    for (int i = threadIdx.x; i < npairs; i += 256) {
+        const int key = off_t[i];
+        unsigned h = ((unsigned)key * 2654435761u) >> 19;  // 13 bits
+        for (;;) {
+            const int cur = hkeys[h];
+            if (cur == key) break;
+            if (cur == -1) {
+                const int old = atomicCAS(&hkeys[h], -1, key);
+                if (old == -1 || old == key) break;
+            }
+            h = (h + 1) & (TILE_HASH - 1);
+        }
+        pslot[i] = (unsigned short)h;
+        atomicAdd(&hcnt[h], 1);
+    }
+    __syncthreads();
+    // Lists are cut into segments of at most TILE_SEG pairs and the segments are ordered by length (longest first), so
+    // that the lanes of a warp of the gather walk lists of (nearly) equal length.  Thread t owns slots [32t, 32t+32).
+    int nseg = 0, ncnt = 0;
+    const int s0 = threadIdx.x * (TILE_HASH / 256);
+#pragma unroll 4
+    for (int k = 0; k < TILE_HASH / 256; k++) {
+        const int c = hcnt[s0 + k];
+        if (c > 0) {
+            const int full = c / TILE_SEG, rem = c - full * TILE_SEG;
+            if (full) atomicAdd(&hist[TILE_SEG], full);
+            if (rem) atomicAdd(&hist[rem], 1);
+            nseg += full + (rem ? 1 : 0);
+            ncnt += c;
+        }
+    }
+    int2 tot;
+    int2 pre = block_excl_scan2(nseg, ncnt, &tot);  // ends with a barrier: hist is complete
+    if (threadIdx.x == 0) {
+        int pos = 0;
+        for (int len = TILE_SEG; len >= 1; len--) { binstart[len] = pos; pos += hist[len]; hist[len] = 0; }
+        tile_nent[tile] = tot.x;
+    }
+    __syncthreads();
+    for (int k = 0; k < TILE_HASH / 256; k++) {
+        const int c = hcnt[s0 + k];
+        if (c > 0) {
+            const int key = hkeys[s0 + k];
+            for (int o = 0; o < c; o += TILE_SEG) {
+                const int len = min(TILE_SEG, c - o);
+                const int idx = binstart[len] + atomicAdd(&hist[len], 1);
+                ent_meta[tb + idx] = make_int2((pre.y + o) | (len << 16), key);
+            }
+            hcnt[s0 + k] = pre.y;  // becomes the fill cursor of the slot's pair list
+            pre.y += c;
+        }
+    }
+    __syncthreads();
+    const float* bary_t = bary + (size_t)base * D1;
+    for (int i = threadIdx.x; i < npairs; i += 256) {
+        const int pos = atomicAdd(&hcnt[pslot[i]], 1);
+        const int lp = i / D1;
+        float w = bary_t[i];
+        if (norm) w = __fmul_rn(w, norm[base + lp]);
+        pairs[tb + pos] = make_uint2((unsigned)lp * (unsigned)row_bytes, __float_as_uint(w));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The point kernel.  One CTA = one tile of TP consecutive points.
+//  phase 1 (lane = (point, channel group), G lanes per point, 32/G points per warp-step):
+//     t = -unary + sum over lattices of w * norm_i * sum_j (bary_ij * alpha) * blurred[vertex_ij]; soft-max per label
+//     layer across the G lanes; marginals go to the shared-memory tile (and to global Q / label maps on request).
+//     A value-table row (Mp floats) is read by G adjacent lanes as one contiguous 16*G-byte access.
+//  phase 2 (item = (tile entry, channel group)): sum w * Q[point] over the entry's pair list out of shared memory and
+//     issue ONE red.global.add.v4.f32 per item.  Global atomics per iteration = (distinct vertices per tile) * G
+//     instead of (nonzeros) * G, Q is never re-read from L2, and nothing depends on how noisy the point order is.
+// `mode` bit 0: slice (not the first pass), bit 1: splat (not the last pass), bit 2: store Q.
+// ---------------------------------------------------------------------------------------------------------------
+// streaming inputs of one point for one lattice, loaded one step ahead of their use
+template <int D1>
+struct PointIn {
+    int key[D1 > 0 ? D1 : 1];
+    float w[D1 > 0 ? D1 : 1];
+    float nrm;
+    __device__ __forceinline__ void load(const FusedLat& L, int p) {
+        if constexpr (D1 > 0) {
+            load_row_i<D1>(L.offsets + (size_t)p * D1, key);
+            load_row_f<D1>(L.bary + (size_t)p * D1, w);
+            nrm = __ldg(L.norm + p);
+        }
+    }
+};
+template <int D1>
+__device__ __forceinline__ void slice_lattice(const FusedLat& L, const PointIn<D1>& in, int Mp, int g, float4& t) {
+    float4 row[D1];
+#pragma unroll
+    for (int j = 0; j < D1; j++) row[j] = __ldg(reinterpret_cast<const float4*>(L.vin + (size_t)in.key[j] * Mp) + g);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < D1; j++) {
+        acc.x = fmaf(in.w[j], row[j].x, acc.x); acc.y = fmaf(in.w[j], row[j].y, acc.y);
+        acc.z = fmaf(in.w[j], row[j].z, acc.z); acc.w = fmaf(in.w[j], row[j].w, acc.w);
+    }
+    // tmp = -unary - (-w * (alpha * filtered) * norm)   (densecrf.cpp:126, pairwise.cpp:78-79, permutohedral.cpp:571)
+    const float c = L.potts * L.alpha * (L.post ? in.nrm : 1.f);
+    t.x = fmaf(c, acc.x, t.x); t.y = fmaf(c, acc.y, t.y); t.z = fmaf(c, acc.z, t.z); t.w = fmaf(c, acc.w, t.w);
+}
+
+template <int G>
+__device__ __forceinline__ float group_gather_max(float v, int gbase) {
+    float m = v;
+#pragma unroll
+    for (int i = 0; i < G; i++) m = fmaxf(m, __shfl_sync(0xffffffffu, v, (gbase + i) & 31));
+    return m;
+}
+template <int G>
+__device__ __forceinline__ float group_gather_sum(float v, int gbase) {  // same order on every lane of the group
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; i++) s += __shfl_sync(0xffffffffu, v, (gbase + i) & 31);
+    return s;
+}
+
+// pairs[].x holds the BYTE offset of the local point's row inside the shared tile (lp * G * 16).
+// Entry meta of the tile was staged into shared memory at kernel start (`cap` entries; the rest comes from global).
+// Every thread walks IU segments at once (independent load streams); segments are sorted by length, so the lanes of
+// a warp finish together.
+template <int G, int IU>
+__device__ __forceinline__ void gather_entries(const uint2* __restrict__ pr, const int2* meta, int cap,
+                                               const int2* __restrict__ meta_g, int ne, float* __restrict__ vout,
+                                               const float4* qtile) {
+    constexpr int Mp = 4 * G;
+    const char* qbytes = reinterpret_cast<const char*>(qtile);
+    const int items = ne * G;
+    for (int it0 = threadIdx.x; it0 < items; it0 += 256 * IU) {
+        const uint2* pp[IU];
+        int len[IU], vertex[IU];
+        const char* qb[IU];
+        float4 acc[IU];
+        int longest = 0;
+#pragma unroll
+        for (int u = 0; u < IU; u++) {
+            const int it = it0 + u * 256;
+            len[u] = 0; vertex[u] = -1; pp[u] = pr; qb[u] = qbytes;
+            acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < items) {
+                const int e = it / G;
+                const int2 m = e < cap ? meta[e] : __ldg(meta_g + e);
+                pp[u] = pr + (m.x & 0xffff);
+                len[u] = m.x >> 16;
+                vertex[u] = m.y;
+                qb[u] = qbytes + 16 * (it - e * G);
+                longest = max(longest, len[u]);
+            }
+        }
+        for (int i = 0; i < longest; i++) {
+#pragma unroll
+            for (int u = 0; u < IU; u++) {
+                if (i < len[u]) {
+                    const uint2 pw = __ldg(pp[u] + i);
+                    const float w = __uint_as_float(pw.y);
+                    const float4 q = *reinterpret_cast<const float4*>(qb[u] + pw.x);
+                    acc[u].x = fmaf(w, q.x, acc[u].x); acc[u].y = fmaf(w, q.y, acc[u].y);
+                    acc[u].z = fmaf(w, q.z, acc[u].z); acc[u].w = fmaf(w, q.w, acc[u].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < IU; u++)
+            if (vertex[u] >= 0) red_add_v4(vout + (size_t)vertex[u] * Mp + (qb[u] - qbytes) / 4, acc[u]);
+    }
+}
+
+template <int G, int D1A, int D1B>
+__global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(const __grid_constant__ FusedArgs a,
+                                                             const float* __restrict__ unary, float* __restrict__ Q,
+                                                             uint8_t* __restrict__ labels, int N, int TP, int steps,
+                                                             const __grid_constant__ FusedLayers ls, int mode) {
+    extern __shared__ float4 qtile[];  // [TP][G]
+    if (a.counts[0][1]) return;  // lattice overflow: the host rebuilds with a larger table and runs again
+    if constexpr (D1B > 0) { if (a.counts[1][1]) return; }
+    constexpr int Mp = 4 * G, cpw = 32 / G;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane / G, g = lane - sub * G, gbase = sub * G;
+    const bool lane_on = sub < cpw;
+    const int tile = blockIdx.x, base = tile * TP;
+    const bool do_slice = mode & 1, do_splat = mode & 2, store_q = mode & 4;
+    const int c0 = 4 * g;
+    // entry metadata of this tile's splat (list end, vertex) -> shared memory; consumed after phase 1
+    // (2 * TP slots shared by the lattices; entries beyond the staged ones are read from global memory)
+    int2* metaA = reinterpret_cast<int2*>(qtile + (size_t)TP * G);
+    int2* metaB = metaA;
+    int neA = 0, neB = 0, capA = 0, capB = 0;
+    if (do_splat) {
+        neA = __ldg(a.tile_nent[0] + tile);
+        capA = min(neA, 2 * TP);
+        const size_t tbA = (size_t)tile * TP * D1A;
+        for (int e = threadIdx.x; e < capA; e += 256) metaA[e] = __ldg(a.ent_meta[0] + tbA + e);
+        if constexpr (D1B > 0) {
+            neB = __ldg(a.tile_nent[1] + tile);
+            metaB = metaA + capA;
+            capB = min(neB, 2 * TP - capA);
+            const size_t tbB = (size_t)tile * TP * D1B;
+            for (int e = threadIdx.x; e < capB; e += 256) metaB[e] = __ldg(a.ent_meta[1] + tbB + e);
+        }
+    }
+    // which of my four channels belong to which layer: one nibble per layer
+    unsigned lmask = 0;
+    for (int l = 0; l < ls.n_layers; l++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (c0 + k >= ls.off[l] && c0 + k < ls.off[l + 1]) lmask |= 1u << (4 * l + k);
+    // aligned layers (every boundary a multiple of 4): my layer, my valid channels, and which lanes of the group share it
+    unsigned vm = 0;
+    float peer_bias[G], peer_w[G];
+    {
+        int my_l = -1;
+        for (int l = 0; l < ls.n_layers; l++)
+            if (c0 >= ls.off[l] && c0 < ls.off[l + 1]) my_l = l;
+        if (my_l >= 0) vm = (lmask >> (4 * my_l)) & 15u;
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            int l_i = -1;
+            for (int l = 0; l < ls.n_layers; l++)
+                if (4 * i >= ls.off[l] && 4 * i < ls.off[l + 1]) l_i = l;
+            // a pad-only lane (my_l < 0) keeps itself as its only peer so that its (discarded) result stays finite
+            const bool peer = my_l >= 0 ? l_i == my_l : i == g;
+            peer_bias[i] = peer ? 0.f : -INFINITY;
+            peer_w[i] = peer ? 1.f : 0.f;
+        }
+    }
+
+    // software pipeline: the streaming inputs (unary, vertex ids, barycentric weights, norms) of step s + 1 are requested
+    // before step s gathers its value rows, so one DRAM/L2 round trip is hidden behind the other.  Two input buffers
+    // alternate (the loop is unrolled by two), so no register copies are needed.
+    struct StepIn {
+        float4 u;
+        PointIn<D1A> A;
+        PointIn<D1B> B;
+        bool valid;
+    };
+    auto load_step = [&](int s, StepIn& in) {
+        const int lp = (s * 8 + wib) * cpw + sub, p = base + lp;
+        in.valid = lane_on && lp < TP && p < N;
+        in.u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in.valid) {
+            in.u = __ldg(reinterpret_cast<const float4*>(unary + (size_t)p * Mp) + g);
+            if (do_slice) { in.A.load(a.lat[0], p); in.B.load(a.lat[1], p); }
+        }
+    };
+    auto run_step = [&](int s, const StepIn& in) {
+        const int lp = (s * 8 + wib) * cpw + sub;
+        const int p = base + lp;
+        const bool valid = in.valid;
+        float4 t = make_float4(-in.u.x, -in.u.y, -in.u.z, -in.u.w);
+        if (valid && do_slice) {
+            slice_lattice<D1A>(a.lat[0], in.A, Mp, g, t);
+            if constexpr (D1B > 0) slice_lattice<D1B>(a.lat[1], in.B, Mp, g, t);
+        }
+        // expAndNormalize per label layer across the G lanes of the point (densecrf.cpp:98-106)
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+        float qv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ls.aligned) {
+            // every lane's four channels lie in ONE layer: a single pass, the lanes of the other layers are masked out
+            // of the all-gathers by a -inf bias (max) and a 0/1 weight (sum); same summation order on every lane
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 4; k++) mx = fmaxf(mx, (vm >> k) & 1u ? tv[k] : -INFINITY);
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < G; i++) m = fmaxf(m, __shfl_sync(0xffffffffu, mx, (gbase + i) & 31) + peer_bias[i]);
+            float e[4], sl = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                e[k] = (vm >> k) & 1u ? __expf(tv[k] - m) : 0.f;  // ex2.approx: |rel err| < 2e-6, the tolerance is 1e-4 abs
+                sl += e[k];
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < G; i++) sum = fmaf(__shfl_sync(0xffffffffu, sl, (gbase + i) & 31), peer_w[i], sum);
+            const float rs = __fdividef(1.0f, sum);
+#pragma unroll
+            for (int k = 0; k < 4; k++) qv[k] = e[k] * rs;
+        } else {
+            for (int l = 0; l < ls.n_layers; l++) {
+                const unsigned m4 = (lmask >> (4 * l)) & 15u;
+                float mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < 4; k++) mx = fmaxf(mx, (m4 >> k) & 1u ? tv[k] : -INFINITY);
+                const float m = group_gather_max<G>(mx, gbase);
+                float e[4], sl = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    e[k] = (m4 >> k) & 1u ? __expf(tv[k] - m) : 0.f;
+                    sl += e[k];
+                }
+                const float rs = __fdividef(1.0f, group_gather_sum<G>(sl, gbase));
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((m4 >> k) & 1u) qv[k] = e[k] * rs;
+            }
+        }
+        const float4 q = make_float4(qv[0], qv[1], qv[2], qv[3]);
+        if (valid) {
+            qtile[lp * G + g] = q;
+            if (store_q) reinterpret_cast<float4*>(Q + (size_t)p * Mp)[g] = q;
+        }
+        if (labels) {
+            // gated argmax (segmenter.cpp:645-657) / plain argmax (densecrf.cpp:200-208); ties -> lower label
+            for (int l = 0; l < ls.n_layers; l++) {
+                const unsigned m4 = (lmask >> (4 * l)) & 15u;
+                const float gate = ls.gate[l];
+                float bv = gate;
+                int best = 1 << 20;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (((m4 >> k) & 1u) && qv[k] > bv) { bv = qv[k]; best = c0 + k - ls.off[l]; }
+                float fv = gate;
+                int fb = 1 << 20;
+#pragma unroll
+                for (int i = 0; i < G; i++) {  // lanes in channel order: strict '>' keeps the first maximum
+                    const float ov = __shfl_sync(0xffffffffu, bv, (gbase + i) & 31);
+                    const int ob = __shfl_sync(0xffffffffu, best, (gbase + i) & 31);
+                    if (ob < (1 << 20) && ov > fv) { fv = ov; fb = ob; }
+                }
+                if (valid && g == 0)
+                    labels[(size_t)l * N + p] = (uint8_t)(fb < (1 << 20) ? fb : (ls.unknown[l] >= 0 ? ls.unknown[l] : 0));
+            }
+        }
+    };
+#if RSS_TILE_PREFETCH
+    StepIn in0, in1;
+    load_step(0, in0);
+    for (int s = 0; s < steps; s += 2) {
+        if (s + 1 < steps) load_step(s + 1, in1);
+        run_step(s, in0);
+        if (s + 1 < steps) {
+            if (s + 2 < steps) load_step(s + 2, in0);
+            run_step(s + 1, in1);
+        }
+    }
+#else
+    for (int s = 0; s < steps; s++) {  // no register prefetch: fewer registers, more resident warps hide the latency
+        StepIn in0;
+        load_step(s, in0);
+        run_step(s, in0);
+    }
+#endif
+    if (!do_splat) return;
+    __syncthreads();
+    // phase 2: tile-local gather splat out of shared memory
+    {
+        const size_t tbA = (size_t)tile * TP * D1A;
+        gather_entries<G, RSS_TILE_IU>(a.pairs[0] + tbA, metaA, capA, a.ent_meta[0] + tbA, neA, a.lat[0].vout, qtile);
+    }
+    if constexpr (D1B > 0) {
+        const size_t tbB = (size_t)tile * TP * D1B;
+        gather_entries<G, RSS_TILE_IU>(a.pairs[1] + tbB, metaB, capB, a.ent_meta[1] + tbB, neB, a.lat[1].vout, qtile);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Blur of every lattice of the CRF in ONE cooperative launch (permutohedral.cpp:555-569).  Phase j blurs axis j of
+// each lattice that has one; phases are separated by a grid barrier on an L2 counter.  The neighbour pair of the next
+// axis is fetched before the barrier (it does not depend on it).  Phase 0 additionally clears `zero` (the table the
+// point kernel sliced from one iteration ago), which becomes the next splat target - so no phase follows the last axis.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier2(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float4 blur3(const float4 o, const float4 x, const float4 y) {
+    float4 r;
+    r.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(x.x, y.x)));
+    r.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(x.y, y.y)));
+    r.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(x.z, y.z)));
+    r.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(x.w, y.w)));
+    return r;
+}
+// one axis of one lattice: items are (vertex, channel group); U independent items per thread are in flight at once
+template <int U>
+__device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4* __restrict__ dst, const int2* __restrict__ nb_j,
+                                          uint32_t items, int G, uint32_t tid, uint32_t nthr) {
+    for (uint32_t base = tid; base < items; base += U * nthr) {
+        int2 nb[U];
+        uint32_t gq[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t it = base + u * nthr;
+            if (it < items) {
+                const uint32_t v = it / (uint32_t)G;
+                gq[u] = it - v * (uint32_t)G;
+                nb[u] = __ldg(nb_j + v);
+            }
+        }
+        float4 o[U], x[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t it = base + u * nthr;
+            if (it < items) {
+                o[u] = __ldcg(src + it);
+                x[u] = __ldcg(src + (size_t)nb[u].x * G + gq[u]);
+                y[u] = __ldcg(src + (size_t)nb[u].y * G + gq[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t it = base + u * nthr;
+            if (it < items) __stcg(dst + it, blur3(o[u], x[u], y[u]));
+        }
+    }
+}
+__global__ void __launch_bounds__(512) blur_multi_coop_kernel(const __grid_constant__ BlurMultiArgs a, int G,
+                                                              unsigned int* barrier, unsigned int barrier_base) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    uint32_t V[FUSED_MAX_LAT];
+    int maxd1 = 0;
+    for (int k = 0; k < a.K; k++) {
+        V[k] = a.counts[k][1] ? 0u : a.counts[k][0];
+        maxd1 = max(maxd1, a.d1[k]);
+    }
+    for (int j = 0; j < maxd1; j++) {
+        for (int k = 0; k < a.K; k++) {
+            if (j >= a.d1[k]) continue;
+            const float4* src = (j & 1) ? a.pong[k] : a.ping[k];
+            float4* dst = (j & 1) ? a.ping[k] : a.pong[k];
+            const uint32_t items = V[k] * (uint32_t)G;
+            blur_axis<4>(src, dst, a.nbr[k] + (size_t)j * a.vcap[k], items, G, tid, nthr);
+            if (j == 0 && a.zero[k])
+                for (uint32_t it = tid; it < items; it += nthr) __stcg(a.zero[k] + it, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (j + 1 < maxd1) grid_barrier2(barrier, barrier_base + (unsigned int)(j + 1) * gridDim.x);
+    }
+}
+
+// splat of the all-ones vector for the normalisation (pairwise.cpp:44): values[v][0] += sum of barycentric weights.
+// Same run-accumulation as the point kernel, one thread per chunk, rows of 4 floats with channel 0 live.
+template <int D1>
+__global__ void __launch_bounds__(256) splat_ones_runs_kernel(const int* __restrict__ offsets, const float* __restrict__ bary,
+                                                              int N, int Pc, const uint32_t* __restrict__ counts,
+                                                              float* __restrict__ values) {
+    if (counts[1]) return;
+    const long long chunk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk * Pc >= N) return;
+    const int p0 = (int)(chunk * Pc), p1 = min(N, p0 + Pc);
+    int cur[D1];
+    float acc[D1];
+#pragma unroll
+    for (int j = 0; j < D1; j++) { cur[j] = -1; acc[j] = 0.f; }
+    for (int p = p0; p < p1; p++) {
+        int key[D1];
+        float w[D1];
+        load_row_i<D1>(offsets + (size_t)p * D1, key);
+        load_row_f<D1>(bary + (size_t)p * D1, w);
+#pragma unroll
+        for (int j = 0; j < D1; j++) {
+            if (key[j] != cur[j]) {
+                if (cur[j] >= 0) atomicAdd(values + (size_t)cur[j] * 4, acc[j]);
+                cur[j] = key[j];
+                acc[j] = 0.f;
+            }
+            acc[j] += w[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < D1; j++)
+        if (cur[j] >= 0) atomicAdd(values + (size_t)cur[j] * 4, acc[j]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+int fused_tile_steps(int G) {  // warp-steps per tile so that a tile holds about RSS_TILE_POINTS points
+    const int per_step = 8 * (32 / G);
+    return std::max(1, (RSS_TILE_POINTS + per_step / 2) / per_step);
+}
+int fused_tile_points(int G) { return 8 * (32 / G) * fused_tile_steps(G); }
+
+bool fused_group_supported(int G) { return G == 1 || G == 2 || G == 3 || G == 5 || G == 6; }
+bool fused_signature_supported(int G, int d1a, int d1b) {
+    if (!fused_group_supported(G)) return false;
+    switch (d1a * 16 + d1b) {
+        case 0x46: case 0x36: case 0x70: case 0x60: case 0x40: case 0x30: return true;
+        default: return false;
+    }
+}
+
+template <int G>
+static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
+                          uint8_t* labels, int N, const FusedLayers& ls, int mode) {
+    const int TP = fused_tile_points(G), steps = fused_tile_steps(G);
+    const int grid = rss_div_up(N, TP);
+#define RSS_TILE(A, B)                                                                                                  \
+    do {                                                                                                                \
+        auto kfn = meanfield_tile_kernel<G, A, B>;                                                                      \
+        const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2);                                \
+        const unsigned bit__ = 1u << (G * 4 + (B ? 1 : 0) + (A > 4 ? 2 : 0));                                          \
+        if (!(c->fused_attr_mask & bit__)) { /* once per context (= per device): shared memory limit and carveout */    \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
+            c->fused_attr_mask |= bit__;                                                                                \
+        }                                                                                                               \
+        RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, N, TP, steps, ls, mode); \
+    } while (0)
+    switch (d1a * 16 + d1b) {
+        case 0x46: RSS_TILE(4, 6); break;
+        case 0x36: RSS_TILE(3, 6); break;
+        case 0x70: RSS_TILE(7, 0); break;
+        case 0x60: RSS_TILE(6, 0); break;
+        case 0x40: RSS_TILE(4, 0); break;
+        case 0x30: RSS_TILE(3, 0); break;
+        default: break;
+    }
+#undef RSS_TILE
+}
+void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
+                            uint8_t* labels, int N, int G, const FusedLayers& ls, int mode) {
+    switch (G) {
+        case 1: launch_tile_g<1>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
+        case 2: launch_tile_g<2>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
+        case 3: launch_tile_g<3>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
+        case 5: launch_tile_g<5>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
+        case 6: launch_tile_g<6>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
+        default: break;
+    }
+}
+
+void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, int N,
+                           int d1, int TP, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta, int* tile_nent) {
+    const int grid = rss_div_up(N, TP);
+#define RSS_TCB(D)                                                                                                      \
+    do {                                                                                                                \
+        if (!(c->tile_attr_mask & (1u << D))) {  /* once per context (= per device) */                                  \
+            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES); \
+            c->tile_attr_mask |= 1u << D;                                                                               \
+        }                                                                                                               \
+        RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, TILE_SMEM_BYTES, st, offsets, bary, norm, N, TP, row_bytes, counts, pairs, \
+                   ent_meta, tile_nent);                                                                                \
+    } while (0)
+    switch (d1) {
+        case 2: RSS_TCB(2); break;
+        case 3: RSS_TCB(3); break;
+        case 4: RSS_TCB(4); break;
+        case 5: RSS_TCB(5); break;
+        case 6: RSS_TCB(6); break;
+        case 7: RSS_TCB(7); break;
+        default: RSS_TCB(8); break;
+    }
+#undef RSS_TCB
+}
+
+int blur_multi_grid(const rss_ctx* c) {
+    static const char* e = getenv("RSS_BLUR_GRID");
+    return e && atoi(e) > 0 ? atoi(e) : c->sm_count;
+}
+void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
+    static const char* eb_ = getenv("RSS_BLUR_BLOCK");
+    const int grid = blur_multi_grid(c), block = eb_ && atoi(eb_) > 0 ? atoi(eb_) : 512;
+    void* args[] = {&a, &G, &barrier, &barrier_base};
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }
+    cudaLaunchCooperativeKernel((const void*)blur_multi_coop_kernel, dim3(grid), dim3(block), args, 0, st);
+    c->launches++;
+    if (c->profile) { cudaEventRecord(eb, st); c->prof_pending.push_back(rss_ctx::Pending{"blur_multi_coop_kernel", ea, eb}); }
+}
+
+void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
+                            const uint32_t* counts, float* values) {
+    const int Pc = 16;
+    const int grid = rss_div_up(rss_div_up(N, Pc), 256);
+#define RSS_ONES(D) RSS_LAUNCH(c, splat_ones_runs_kernel<D>, grid, 256, 0, st, offsets, bary, N, Pc, counts, values)
+    switch (d1) {
+        case 2: RSS_ONES(2); break;
+        case 3: RSS_ONES(3); break;
+        case 4: RSS_ONES(4); break;
+        case 5: RSS_ONES(5); break;
+        case 6: RSS_ONES(6); break;
+        case 7: RSS_ONES(7); break;
+        default: RSS_ONES(8); break;
+    }
+#undef RSS_ONES
+}
+
+}  // namespace rss

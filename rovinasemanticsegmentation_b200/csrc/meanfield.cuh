@@ -1,0 +1,56 @@
+// Argument blocks of the fused mean-field kernels (meanfield.cu).
+#pragma once
+#include "common.cuh"
+
+namespace rss {
+
+constexpr int FUSED_MAX_LAT = 2;
+
+struct FusedLat {
+    const int* offsets;   // [N][d+1] vertex ids
+    const float* bary;    // [N][d+1]
+    const float* norm;    // [N]
+    const float* vin;     // blurred value table of the previous iteration (slice source)
+    float* vout;          // all-zero table receiving this iteration's splat
+    float potts, alpha;   // Potts weight w, slice scale 1/(1+2^-d)
+    int pre, post;        // normalisation applied before the splat / after the slice (NormalizationType)
+};
+struct FusedArgs {
+    FusedLat lat[FUSED_MAX_LAT];
+    const uint32_t* counts[FUSED_MAX_LAT];  // [0] V, [1] overflow flag
+    // tile-local CSR of the splat matrix (tile t owns the slice [t * TP * d1, (t + 1) * TP * d1) of each array)
+    const uint2* pairs[FUSED_MAX_LAT];      // (byte offset of the local point's row in the shared tile, weight bits), by entry
+    const int2* ent_meta[FUSED_MAX_LAT];    // per segment: x = start in the tile's pair array | length << 16, y = vertex id
+    const int* tile_nent[FUSED_MAX_LAT];    // segments per tile
+};
+struct FusedLayers {
+    int n_layers;
+    int off[RSS_MAX_LAYERS + 1];
+    int unknown[RSS_MAX_LAYERS];  // < 0: plain argmax
+    float gate[RSS_MAX_LAYERS];   // 2 / M_l when gated (segmenter.cpp:647), else -inf
+    int aligned;                  // every layer boundary is a multiple of 4 channels
+};
+struct BlurMultiArgs {
+    int K;
+    float4* ping[FUSED_MAX_LAT];  // holds the splat on entry
+    float4* pong[FUSED_MAX_LAT];
+    float4* zero[FUSED_MAX_LAT];  // table to clear (next splat target) or NULL
+    const int2* nbr[FUSED_MAX_LAT];
+    const uint32_t* counts[FUSED_MAX_LAT];
+    int d1[FUSED_MAX_LAT];
+    uint32_t vcap[FUSED_MAX_LAT];
+};
+
+bool fused_group_supported(int G);  // channel-group counts the tile kernel is instantiated for
+bool fused_signature_supported(int G, int d1a, int d1b);
+int fused_tile_points(int G);
+void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
+                            uint8_t* labels, int N, int G, const FusedLayers& ls, int mode);
+void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, int N,
+                           int d1, int TP, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta, int* tile_nent);
+int blur_multi_grid(const rss_ctx* c);  // CTAs of the cooperative blur (one barrier arrival each)
+void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base);
+void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
+                            const uint32_t* counts, float* values);
+
+}  // namespace rss
