@@ -8,8 +8,10 @@ normal features -> multi-label forest (4 trees, 17 classes in 2 layers) -> 2x up
 pixels with a 3-D Gaussian kernel on the back-projected points and a 5-D bilateral kernel, 10 mean-field iterations,
 both label layers, gated argmax (BASELINE.json configs[1], with configs[2]'s second layer included).
 
-  value : keyframes/s with the frame already resident in HBM (device time, CUDA events on the library's stream)
-  e2e   : keyframes/s through the C ABI with HOST buffers: pinned rgb/depth in, label maps out, copies timed
+  value : keyframes/s with the frames already resident in HBM, --inflight keyframes in flight per GPU (CUDA events around
+          the K steps, device-wide synchronisation on both sides)
+  e2e   : the same through the C ABI with HOST buffers: pinned rgb/depth in, label maps out, copies inside the timed region
+  latency: one keyframe at a time (library CUDA events), with the per-stage and per-kernel break-down
 N > 1 (torchrun): every rank owns one GPU and its own keyframes (weak scaling, no collective on the data path);
 the timed region is bracketed by a barrier + synchronize and the slowest rank's time is used.
 """
@@ -40,6 +42,27 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def frame_seeds(rank, n=None):
+    """Seeds of the synthetic frames rank `rank` owns: every rank works on its own keyframes (weak scaling; keyframes are
+    independent units, so the shards share nothing)."""
+    n = N_FRAMES if n is None else n
+    return [10_000 + rank * n + k for k in range(n)]
+
+
+def max_over_ranks(values, dist=None, device=None):
+    """Slowest rank decides: element-wise MAX of per-rank timings over the process group (identity without one)."""
+    import torch
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def job_throughput(steps_per_rank, world, ms):
+    """Whole-job keyframes/s: every rank ran `steps_per_rank` keyframes inside the same (max over ranks) `ms`."""
+    return steps_per_rank * world / (ms / 1000.0)
 
 
 class ClockSampler(threading.Thread):
@@ -177,11 +200,21 @@ def algo_bytes(name, env):
         "blur_coop_kernel": mean(lambda d, V: (d + 1) * (8 * M * V + 8 * V) + 4 * M * V),
         "blur_kernel": mean(lambda d, V: 8 * M * V + 8 * V),
         "slice_softmax_kernel<MP>": sum(8 * (d + 1) * N + 4 * N + 4 * M * V for d, V in lat) + 8 * M * N,
+        # fused path (meanfield.cu): one point kernel per iteration = slice (vertex ids + weights, norms, unique rows) +
+        # unary + tile-local splat (pair list, unique rows out); one cooperative blur for all lattices
+        "meanfield_tile_kernel": 4 * M * N + sum(16 * (d + 1) * N + 4 * N + 8 * M * V for d, V in lat),
+        "blur_multi_coop_kernel": sum((d + 1) * (8 * M * V + 8 * V) + 4 * M * V for d, V in lat),
+        "tile_csr_build_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * N + 16 * (d + 1) * N),
+        "splat_ones_runs_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * V),
+        "slice_kernel": mean(lambda d, V: 8 * (d + 1) * N + 4 * V + 4 * N),
     }
     return table.get(name)
 
 
 def run_gpu(args, rank, world, local_rank):
+    import ctypes as C
+    import threading as th
+
     import torch
     import rovinasemanticsegmentation_b200 as rss
     from rovinasemanticsegmentation_b200 import synth
@@ -198,147 +231,124 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx = rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank)
+    NC = max(1, args.inflight)  # keyframes in flight on this GPU: one context + one host thread each
+    ctxs = [rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank) for _ in range(NC)]
+    ctx = ctxs[0]
+    lib = ctx._lib
     Kinv, R, t = synth.calibration()
+    Kp, Rp, tp = (np.ascontiguousarray(a, np.float32).reshape(-1) for a in (Kinv, R, t))
     frames = []
-    for k in range(N_FRAMES):
-        rgb, depth = synth.frame(10_000 + rank * N_FRAMES + k)
+    for seed in frame_seeds(rank):
+        rgb, depth = synth.frame(seed)
         prgb = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
         pdep = torch.empty((H, W), dtype=torch.int16, pin_memory=True)
         prgb.numpy()[...] = rgb
         pdep.numpy().view(np.uint16)[...] = depth
         frames.append((prgb.numpy(), pdep.numpy().view(np.uint16)))
-    plabels = torch.empty((2, H * W), dtype=torch.uint8, pin_memory=True)
-    labels_np = plabels.numpy()
+    outs = [torch.empty((2, H * W), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(NC)]
     prm = rss.KeyframeParams(KF["sigma_xyz"], KF["w_gauss"], KF["sigma_px"], KF["sigma_rgb"], KF["w_bilateral"],
                              KF["iters"], KF["fill"])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=dev) for _ in range(NC)]  # each > 126 MB L2
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NC)]
 
-    import ctypes as C
-    lib = ctx._lib
-    Kp, Rp, tp = (np.ascontiguousarray(a, np.float32).reshape(-1) for a in (Kinv, R, t))
-
-    def call(rgb, depth, labels):
-        st = lib.rss_segment_keyframe(ctx.h, rss._ptr(rgb, C.c_uint8), rss._ptr(depth, C.c_uint16), W, H,
+    def call(c, rgb, depth, labels):
+        st = lib.rss_segment_keyframe(c.h, rss._ptr(rgb, C.c_uint8), rss._ptr(depth, C.c_uint16), W, H,
                                       rss._ptr(Kp, C.c_float), rss._ptr(Rp, C.c_float), rss._ptr(tp, C.c_float),
                                       C.byref(prm), rss._ptr(labels, C.c_uint8), None)
-        ctx._check(st)
+        c._check(st)
 
-    # ---- warm-up (untimed)
+    def flush_l2(i):
+        with torch.cuda.stream(streams[i]):
+            flushes[i].zero_()
+        streams[i].synchronize()
+
+    # ---- warm-up (untimed): every context, host buffers (allocations, lattice capacities)
     for k in range(args.warmup):
-        call(frames[k % N_FRAMES][0], frames[k % N_FRAMES][1], labels_np)
+        for i, c in enumerate(ctxs):
+            call(c, frames[(i + k) % N_FRAMES][0], frames[(i + k) % N_FRAMES][1], outs[i])
     barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
 
-    # ---- device-resident throughput: frame k resident before the step, L2 flushed, device time from CUDA events
-    # (the library brackets every call with events on its own stream).  Pass 1 is the timed region; pass 2 repeats the
-    # same K steps with per-kernel event bracketing switched on (costs a few microseconds per launch, so it is kept out
-    # of the headline number) and yields the per-kernel table and the roofline of the dominant kernel.
-    def resident_pass(profile):
+    # ---- (1) latency: ONE keyframe at a time on one context, frame resident, L2 flushed, device time from the library's
+    # CUDA events on its own stream; (2) the same steps again with per-kernel event bracketing on (costs a few
+    # microseconds per launch, so it is kept out of every headline number) -> per-kernel table and roofline.
+    def latency_pass(profile):
         ctx.profile_enable(profile)
-        l0 = ctx.kernel_launches
         ms, stg = 0.0, {}
-        barrier()
         for k in range(args.steps):
             ctx.upload_frame(*frames[k % N_FRAMES])
-            flush.zero_()
+            flush_l2(0)
             torch.cuda.synchronize()
-            call(None, None, None)
+            call(ctx, None, None, None)
             tm = ctx.timings()
             ms += tm["total_ms"]
             for n, v in tm.items():
                 stg[n] = stg.get(n, 0.0) + v
-        barrier()
         rep = ctx.profile_report() if profile else {}
         ctx.profile_enable(False)
-        return ms, stg, ctx.kernel_launches - l0, rep
+        return ms, stg, rep
 
-    dev_ms, stage, launches, _ = resident_pass(False)
+    lat_ms, stage, _ = latency_pass(False)
     lat_info = [ctx.keyframe_lattice_info(k) for k in range(2)]
     n_samples = int(((frames[0][1][::2, ::2] >= 500) & (frames[0][1][::2, ::2] <= 15000)).sum())
-    dev_ms_prof, _, _, prof = resident_pass(True)
+    lat_ms_prof, _, prof = latency_pass(True)
 
-    # ---- several keyframes in flight: C contexts on this GPU, one host thread each (keyframes are independent, the
-    # reference runs one worker per stage; here one worker per context).  Wall clock over the whole batch between
-    # device-wide synchronisations; every context works on its own frames.
-    def run_inflight(C_, steps_total, host_io):
-        import threading as th
-        ctxs = [ctx] + [rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank) for _ in range(C_ - 1)]
-        outs = [np.empty((2, H * W), np.uint8) if not host_io else
-                torch.empty((2, H * W), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(C_)]
-        per = [steps_total // C_ + (1 if i < steps_total % C_ else 0) for i in range(C_)]
+    # ---- (3) throughput: K steps shared by the NC contexts (keyframes are independent units; the reference runs one
+    # worker per stage, here one worker per context).  Every step is preceded by a 256 MiB write on the worker's side
+    # stream (L2 flush).  resident: the context's frame is already in HBM; e2e: pinned host rgb/depth in, labels out.
+    def throughput_pass(host_io):
+        per = [args.steps // NC + (1 if i < args.steps % NC else 0) for i in range(NC)]
+        if not host_io:
+            for i, c in enumerate(ctxs):
+                c.upload_frame(*frames[i % N_FRAMES])
+        errs = []
 
-        def worker(ci, n, warm):
-            c = ctxs[ci]
-            for k in range(n):
-                fr = frames[(ci * 3 + k) % N_FRAMES]
-                if host_io:
-                    stc = lib.rss_segment_keyframe(c.h, rss._ptr(fr[0], C.c_uint8), rss._ptr(fr[1], C.c_uint16), W, H,
-                                                   rss._ptr(Kp, C.c_float), rss._ptr(Rp, C.c_float), rss._ptr(tp, C.c_float),
-                                                   C.byref(prm), rss._ptr(outs[ci], C.c_uint8), None)
-                else:
-                    if warm or k == 0:
-                        c.upload_frame(*fr)
-                    stc = lib.rss_segment_keyframe(c.h, None, None, W, H, rss._ptr(Kp, C.c_float), rss._ptr(Rp, C.c_float),
-                                                   rss._ptr(tp, C.c_float), C.byref(prm), None, None)
-                c._check(stc)
+        def worker(i):
+            try:
+                c = ctxs[i]
+                for k in range(per[i]):
+                    flush_l2(i)
+                    if host_io:
+                        fr = frames[(i * 3 + k) % N_FRAMES]
+                        call(c, fr[0], fr[1], outs[i])
+                    else:
+                        call(c, None, None, None)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
 
-        for phase in ("warm", "timed"):
-            ths = [th.Thread(target=worker, args=(i, 2 if phase == "warm" else per[i], phase == "warm")) for i in range(C_)]
-            torch.cuda.synchronize()
-            t0_ = time.perf_counter()
-            for t_ in ths:
-                t_.start()
-            for t_ in ths:
-                t_.join()
-            torch.cuda.synchronize()
-            dt_ = time.perf_counter() - t0_
-        for c in ctxs[1:]:
-            c.close()
-        return dt_
-
-    sweep = [] if args.quick else ([args.inflight] if args.inflight > 0 else [1, 2, 3, 4])
-    inflight = {}
-    for C_ in sweep:
+        l0 = sum(c.kernel_launches for c in ctxs)
+        ths = [th.Thread(target=worker, args=(i,)) for i in range(NC)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        dt_res = run_inflight(C_, args.steps, False)
-        dt_e2e = run_inflight(C_, args.steps, True)
-        inflight[C_] = (dt_res, dt_e2e)
-    barrier()
+        e0.record()
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        torch.cuda.synchronize()  # device-wide: every stream of every context
+        e1.record()
+        e1.synchronize()
+        if errs:
+            raise errs[0]
+        return e0.elapsed_time(e1), sum(c.kernel_launches for c in ctxs) - l0
 
-    # ---- end to end through the C ABI with host buffers (pinned), wall clock over K synchronous calls
+    res_ms, launches = throughput_pass(False)
+    e2e_ms, _ = throughput_pass(True)
     barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        call(frames[k % N_FRAMES][0], frames[k % N_FRAMES][1], labels_np)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
-
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
     # slowest rank decides
-    flat = [dev_ms, e2e_s * 1000.0]
-    for C_ in sweep:
-        flat += [inflight[C_][0] * 1000.0, inflight[C_][1] * 1000.0]
-    times = torch.tensor(flat, dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    flat = times.tolist()
-    dev_ms_max, e2e_ms_max = flat[0], flat[1]
-    inflight_max = {C_: (flat[2 + 2 * i], flat[3 + 2 * i]) for i, C_ in enumerate(sweep)}
+    res_ms_max, e2e_ms_max, lat_ms_max = max_over_ranks([res_ms, e2e_ms, lat_ms], dist, dev)
 
     if rank == 0:
-        total_kf = args.steps * world
-        value = total_kf / (dev_ms_max / 1000.0)
-        e2e = total_kf / (e2e_ms_max / 1000.0)
+        value = job_throughput(args.steps, world, res_ms_max)
+        e2e = job_throughput(args.steps, world, e2e_ms_max)
         peak, peak_src = peaks()
-        # dominant kernel = largest accumulated device time in the timed region
         top = sorted(prof.items(), key=lambda kv: -kv[1][0])
         kernel_table = [{"kernel": n, "ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
                          "us_per_launch": 1000.0 * ms / max(cnt, 1)} for n, (ms, cnt) in top[:16]]
@@ -356,38 +366,38 @@ def run_gpu(args, rank, world, local_rank):
         ab = algo_bytes(dom_name, env)
         ach = ab / (dom_ms / dom_cnt / 1000.0) / 1e9 if ab is not None else None
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full` captures
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom_name, {}).get("dram_bytes_per_launch")
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full` captures
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = next((v.get("dram_bytes_per_launch") for k, v in tj.items() if k.split("<")[0] == dom_name.split("<")[0]), None)
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(ab) if ab is not None else None,
                 "us_per_launch": 1000.0 * dom_ms / dom_cnt,
                 "lattices": [{"d": d, "vertices": V} for d, V in lat_info]}
-        # whole-step roofline: algorithmic bytes of every launch of the step / the step's device time
         step_bytes = sum((algo_bytes(n, env) or 0) * cnt / args.steps for n, (ms, cnt) in top)
         roof["step_algorithmic_bytes"] = int(step_bytes)
-        roof["step_achieved"] = step_bytes / (dev_ms_max / args.steps / 1000.0) / 1e9
+        roof["step_achieved"] = step_bytes / (res_ms_max / args.steps / 1000.0) / 1e9
         roof["step_frac"] = roof["step_achieved"] / peak
-        sweep_out = {str(C_): {"resident_kf_s": total_kf / (a / 1000.0), "e2e_kf_s": total_kf / (b / 1000.0)}
-                     for C_, (a, b) in inflight_max.items()}
         line = {
-            "inflight_sweep": sweep_out,
             "metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": res_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "flushed with a 256 MiB write before every timed step",
-                       "frames": "%d distinct synthetic frames per rank" % N_FRAMES},
+            "config": {"workload": WORKLOAD, "l2": "every step is preceded by a 256 MiB device write (L2 flush)",
+                       "frames": "%d distinct synthetic frames per rank" % N_FRAMES,
+                       "inflight": "%d keyframes in flight per GPU (one context + host thread each)" % NC},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": W * H * 3 + W * H * 2,
                     "d2h_bytes_per_step": 2 * W * H, "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "stages_ms_per_step": {n: v / args.steps for n, v in stage.items()},
+            "latency": {"ms_per_keyframe": lat_ms_max / args.steps,
+                        "note": "one keyframe at a time on one context, frame resident, L2 flushed, library CUDA events",
+                        "stages_ms": {n: v / args.steps for n, v in stage.items()},
+                        "ms_per_meanfield_iter": stage.get("meanfield_ms", 0.0) / args.steps / KF["iters"]},
             "kernels": kernel_table,
-            "kernels_note": "per-kernel times from a second pass over the same steps with event bracketing on "
-                            "(%.3f ms/step vs %.3f ms/step in the timed pass)" % (dev_ms_prof / args.steps, dev_ms / args.steps),
-            "ms_per_meanfield_iter": stage.get("meanfield_ms", 0.0) / args.steps / KF["iters"],
+            "kernels_note": "per-kernel device times from a second single-context pass with event bracketing on "
+                            "(%.3f ms/keyframe vs %.3f ms/keyframe without)" % (lat_ms_prof / args.steps, lat_ms / args.steps),
         }
         if world == 1 and not args.no_cpu and not args.quick:
             import oracle
@@ -398,7 +408,8 @@ def run_gpu(args, rank, world, local_rank):
                                     "sample": "%d full 640x480 keyframes, one single-thread oracle pipeline per core "
                                               "(%.1f s)" % (procs, cdt)}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -412,8 +423,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="skip the keyframes-in-flight sweep and the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--inflight", type=int, default=0,
-                    help="keyframes in flight per GPU (one context + host thread each); 0 = sweep 1,2,3,4 and report the best")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="keyframes in flight per GPU (one context + host thread each)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -386,6 +386,15 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     ls.aligned = 1;
     for (int l = 0; l < ls.n_layers; l++)
         if (ls.off[l] % 4) ls.aligned = 0;
+    for (int gq = 0; gq < 8; gq++) {
+        ls.group_lmask[gq] = 0; ls.group_valid[gq] = 0; ls.group_layer[gq] = -1;
+        for (int l = 0; l < ls.n_layers; l++) {
+            for (int k = 0; k < 4; k++)
+                if (4 * gq + k >= ls.off[l] && 4 * gq + k < ls.off[l + 1]) ls.group_lmask[gq] |= 1u << (4 * l + k);
+            if (4 * gq >= ls.off[l] && 4 * gq < ls.off[l + 1]) ls.group_layer[gq] = l;
+        }
+        if (ls.group_layer[gq] >= 0) ls.group_valid[gq] = (ls.group_lmask[gq] >> (4 * ls.group_layer[gq])) & 15u;
+    }
     DevBuf* tgt[FUSED_MAX_LAT];
     DevBuf* spare[FUSED_MAX_LAT];
     DevBuf* res[FUSED_MAX_LAT];

@@ -342,30 +342,18 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
             for (int e = threadIdx.x; e < capB; e += 256) metaB[e] = __ldg(a.ent_meta[1] + tbB + e);
         }
     }
-    // which of my four channels belong to which layer: one nibble per layer
-    unsigned lmask = 0;
-    for (int l = 0; l < ls.n_layers; l++)
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (c0 + k >= ls.off[l] && c0 + k < ls.off[l + 1]) lmask |= 1u << (4 * l + k);
-    // aligned layers (every boundary a multiple of 4): my layer, my valid channels, and which lanes of the group share it
-    unsigned vm = 0;
+    // per channel group (host-precomputed, FusedLayers): which of my four channels belong to which layer (one nibble per
+    // layer), and for aligned layers my layer, my valid channels and which lanes of the group share the layer
+    const unsigned lmask = ls.group_lmask[g];
+    const unsigned vm = ls.group_valid[g];
+    const int my_l = ls.group_layer[g];
     float peer_bias[G], peer_w[G];
-    {
-        int my_l = -1;
-        for (int l = 0; l < ls.n_layers; l++)
-            if (c0 >= ls.off[l] && c0 < ls.off[l + 1]) my_l = l;
-        if (my_l >= 0) vm = (lmask >> (4 * my_l)) & 15u;
 #pragma unroll
-        for (int i = 0; i < G; i++) {
-            int l_i = -1;
-            for (int l = 0; l < ls.n_layers; l++)
-                if (4 * i >= ls.off[l] && 4 * i < ls.off[l + 1]) l_i = l;
-            // a pad-only lane (my_l < 0) keeps itself as its only peer so that its (discarded) result stays finite
-            const bool peer = my_l >= 0 ? l_i == my_l : i == g;
-            peer_bias[i] = peer ? 0.f : -INFINITY;
-            peer_w[i] = peer ? 1.f : 0.f;
-        }
+    for (int i = 0; i < G; i++) {
+        // a pad-only lane (my_l < 0) keeps itself as its only peer so that its (discarded) result stays finite
+        const bool peer = my_l >= 0 ? ls.group_layer[i] == my_l : i == g;
+        peer_bias[i] = peer ? 0.f : -INFINITY;
+        peer_w[i] = peer ? 1.f : 0.f;
     }
 
     // software pipeline: the streaming inputs (unary, vertex ids, barycentric weights, norms) of step s + 1 are requested

@@ -29,6 +29,11 @@ struct FusedLayers {
     int unknown[RSS_MAX_LAYERS];  // < 0: plain argmax
     float gate[RSS_MAX_LAYERS];   // 2 / M_l when gated (segmenter.cpp:647), else -inf
     int aligned;                  // every layer boundary is a multiple of 4 channels
+    // per channel group g (channels 4g..4g+3): layer membership nibbles (4 bits per layer), and for aligned layers the
+    // group's layer (-1: padding only) and its valid-channel nibble
+    unsigned group_lmask[8];
+    unsigned group_valid[8];
+    int group_layer[8];
 };
 struct BlurMultiArgs {
     int K;
