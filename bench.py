@@ -258,6 +258,8 @@ def run_gpu(args, rank, world, local_rank):
         c._check(st)
 
     def flush_l2(i):
+        if os.environ.get("RSS_BENCH_NOFLUSH"):  # experiments only: the reported numbers always flush
+            return
         with torch.cuda.stream(streams[i]):
             flushes[i].zero_()
         streams[i].synchronize()

@@ -14,6 +14,8 @@ using namespace rss;
 namespace rss {
 void crf_release_cached(rss_ctx* ctx);  // crf.cu
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
+rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
+rss_status frame_segment_finish(rss_ctx* ctx, float fill);
 }
 
 static thread_local std::string g_create_error;
@@ -335,8 +337,11 @@ extern "C" rss_status rss_create(const char* config_json_path, const char* fores
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(RSS_ERR_CUDA); }
     ctx->sm_count = prop.multiProcessorCount;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // s1 carries the cloud -> normals chain (the longest dependency chain of the feature stage): high priority
     if (cudaStreamCreateWithFlags(&ctx->s0, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s1, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithPriority(&ctx->s1, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         ctx->err = "cudaStreamCreate failed";
         return bail(RSS_ERR_CUDA);
     }
@@ -603,15 +608,26 @@ rss_status frame_segment(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth
 
 // the same on the frame that frame_upload() made resident (events 0/1 recorded by the caller)
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill) {
+    rss_status st = frame_segment_begin(ctx, Kinv, R, t);
+    if (st != RSS_OK) return st;
+    return frame_segment_finish(ctx, fill);
+}
+// first half: Lab + border on s0, cloud and the normals preparation on s1 (ev_cloud marks the point cloud)
+rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t) {
+    FrameState& f = ctx->fr;
+    const HostConfig& cfg = ctx->cfg;
+    if (!ctx->forest.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
+    const int stride = cfg.rf_stride, W = f.W, H = f.H;
+    if (W % stride || H % stride) return ctx->fail(RSS_ERR_INVALID, "image size must be a multiple of rf_prediction_stride");
+    return frame_prepare(ctx, Kinv, R, t, cfg.depth_min, cfg.depth_max);
+}
+// second half: samples, features, forest, low-res scatter, upsample
+rss_status frame_segment_finish(rss_ctx* ctx, float fill) {
     FrameState& f = ctx->fr;
     const HostConfig& cfg = ctx->cfg;
     const ForestDev& F = ctx->forest;
-    if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
     const int stride = cfg.rf_stride, W = f.W, H = f.H;
-    if (W % stride || H % stride) return ctx->fail(RSS_ERR_INVALID, "image size must be a multiple of rf_prediction_stride");
-    rss_status st = frame_prepare(ctx, Kinv, R, t, cfg.depth_min, cfg.depth_max);
-    if (st != RSS_OK) return st;
-    st = frame_extract(ctx, stride, cfg.depth_min, cfg.depth_max, RSS_NO_LABEL, nullptr, 0);
+    rss_status st = frame_extract(ctx, stride, cfg.depth_min, cfg.depth_max, RSS_NO_LABEL, nullptr, 0);
     if (st != RSS_OK) return st;
     cudaEventRecord(ctx->ev[2], ctx->s0);
     const int n = f.n_samples;

@@ -557,11 +557,11 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
         if (rc != RSS_OK) return rc;
         rc = lattice_normalization(ctx, st, *L);
         if (rc != RSS_OK) return rc;
-        if (tile_ok) {
+        L->ordered = raster;
+        if (raster && tile_ok) {
             rc = lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4);
             if (rc != RSS_OK) return rc;
         }
-        L->ordered = raster;
         if (!sync) return RSS_OK;
         launch_run_count(ctx, st, *L);
         uint32_t h[8];
@@ -572,11 +572,12 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
             L->runs = (long long)h[5];
             // coherent point order: on average every vertex run spans more than two points
             L->ordered = raster || 2 * L->runs <= (long long)maxv;
+            if (L->ordered && tile_ok && L->tile_TP == 0) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4);
             return RSS_OK;
         }
         if ((uint64_t)hcap >= 2 * next_pow2(2 * maxv) || hcap >= (1u << 30))
             return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
-        hcap *= 4;
+        hcap = (uint32_t)std::min<uint64_t>((uint64_t)hcap * 8, 1u << 30);
     }
 }
 // after a synchronisation: true when some lattice overflowed; its next build will use a 4x larger table
@@ -639,7 +640,10 @@ rss_status crf_new(rss_ctx* ctx, int N, int n_layers, const int* M, rss_crf** ou
     if (e == cudaSuccess) e = crf->scratch.reserve((size_t)N * (crf->Mp + 4) * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(crf->unary.ptr, 0, (size_t)N * crf->Mp * 4, ctx->s0);
     for (int k = 0; k < 4 && e == cudaSuccess; k++) {
-        e = cudaStreamCreateWithFlags(&crf->side[k], cudaStreamNonBlocking);
+        // lattice construction runs beside the frame path and is on the keyframe's critical path: high priority
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        e = cudaStreamCreateWithPriority(&crf->side[k], cudaStreamNonBlocking, prio_hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&crf->ev_join[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&crf->ev_fork, cudaEventDisableTiming);
@@ -895,6 +899,8 @@ extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx,
 namespace rss {
 rss_status frame_upload(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth, int W, int H);
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
+rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
+rss_status frame_segment_finish(rss_ctx* ctx, float fill);
 void frame_collect_timings(rss_ctx* ctx, bool with_d2h);
 }
 
@@ -933,21 +939,31 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
         RSS_CU(ctx, cudaStreamWaitEvent(sB, crf->ev_fork, 0));
         RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(N, 256), 256, 0, sB, W, H, prm->sigma_px, prm->sigma_px,
                    prm->sigma_rgb, prm->sigma_rgb, prm->sigma_rgb, ctx->fr.rgb.as<uint8_t>(), f5);
-        // pool order: the Gaussian lattice is added first below, so hand it the 3-D lattice's buffers
-        if (crf->pool.size() == 2 && crf->pool.back()->d != 3) std::swap(crf->pool[0], crf->pool[1]);
+        // Enqueue order = start order: the bilateral lattice needs only the colour image, so its whole construction is
+        // queued on sB first; then the first half of the frame path (Lab on s0, cloud + normals on s1); then the Gaussian
+        // lattice on sA behind the cloud; only then the rest of the frame path, which contains the one host
+        // synchronisation (sample count).  kernels[0] = Gaussian, kernels[1] = bilateral (slot order of the mean field).
+        Lattice* pooled[2] = {nullptr, nullptr};  // [0] 3-D, [1] 5-D buffers from the previous keyframe
+        for (Lattice* L : crf->pool) pooled[L->d == 3 ? 0 : 1] = L;
+        crf->pool.clear();
+        if (pooled[1]) crf->pool.push_back(pooled[1]);
+        st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false, true);
+        if (st != RSS_OK) return st;
         if (attempt == 0) {
-            // ---- frame path on s0 (+ s1 for cloud / normals); ev_cloud marks the point cloud
-            st = frame_segment_resident(ctx, Kinv, R, t, prm->fill);
+            st = frame_segment_begin(ctx, Kinv, R, t);
             if (st != RSS_OK) return st;
         }
-        // ---- Gaussian lattice on sA as soon as the cloud exists
         RSS_CU(ctx, cudaStreamWaitEvent(sA, ctx->ev_cloud, 0));
         RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, sA, N, ctx->fr.xyz.as<float4>(),
                    1.0f / prm->sigma_xyz, t[0], t[1], t[2], f3);
+        if (pooled[0]) crf->pool.push_back(pooled[0]);
         st = crf_add_kernel_dev(crf, sA, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, false, true);
         if (st != RSS_OK) return st;
-        st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false, true);
-        if (st != RSS_OK) return st;
+        std::swap(crf->kernels[0], crf->kernels[1]);
+        if (attempt == 0) {
+            st = frame_segment_finish(ctx, prm->fill);
+            if (st != RSS_OK) return st;
+        }
         RSS_CU(ctx, cudaEventRecord(crf->ev_join[0], sA));
         RSS_CU(ctx, cudaEventRecord(crf->ev_join[1], sB));
         // ---- unary = -posteriors, then the mean-field loop once both lattices are ready

@@ -59,9 +59,13 @@ __device__ __forceinline__ Key128 load_key(const Key128* p) {
 // A slot goes EMPTY -> key exactly once.  A plain (cached, possibly stale or torn) 128-bit load may only be trusted
 // when it shows OUR key (then the slot was fully written); every other outcome is confirmed with the CAS itself,
 // whose return value is the authoritative content of the slot.
+// The probe sequence is bounded (HASH_MAX_PROBES): a table that is too small for the lattice must fail FAST (the host
+// retries with a larger one), not degenerate into full-table scans by millions of threads.
+constexpr uint32_t HASH_MAX_PROBES = 256;
 __device__ __forceinline__ int hash_insert(Key128* table, uint32_t mask, const Key128& key, uint32_t* counts) {
     uint32_t h = key_hash(key) & mask;
-    for (uint32_t probes = 0; probes <= mask; probes++) {
+    const uint32_t limit = min(mask, HASH_MAX_PROBES);
+    for (uint32_t probes = 0; probes <= limit; probes++) {
         if (key_eq(load_key(table + h), key)) return (int)h;
         const Key128 old = atomicCAS(table + h, key_empty(), key);
         if (key_eq(old, key_empty())) {
@@ -75,7 +79,8 @@ __device__ __forceinline__ int hash_insert(Key128* table, uint32_t mask, const K
 }
 __device__ __forceinline__ int hash_find(const Key128* table, uint32_t mask, const Key128& key) {
     uint32_t h = key_hash(key) & mask;
-    for (uint32_t probes = 0; probes <= mask; probes++) {
+    const uint32_t limit = min(mask, HASH_MAX_PROBES);  // same bound as hash_insert: a key is never farther from home
+    for (uint32_t probes = 0; probes <= limit; probes++) {
         const Key128 cur = load_key(table + h);
         if (key_eq(cur, key)) return (int)h;
         if (key_eq(cur, key_empty())) return -1;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
                                                             uint32_t* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (*reinterpret_cast<volatile uint32_t*>(counts + 1)) return;  // overflow already detected: the build is void anyway
     const float invdplus1 = __fdiv_rn(1.0f, (float)(D + 1)), dplus1 = (float)(D + 1);
     float elevated[D + 1], rem0[D + 1], rank[D + 1], bary[D + 2];
     // elevate (:203-209)

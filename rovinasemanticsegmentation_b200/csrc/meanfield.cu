@@ -689,7 +689,7 @@ int blur_multi_grid(const rss_ctx* c) {
 }
 void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
     static const char* eb_ = getenv("RSS_BLUR_BLOCK");
-    const int grid = blur_multi_grid(c), block = eb_ && atoi(eb_) > 0 ? atoi(eb_) : 512;
+    const int grid = blur_multi_grid(c), block = eb_ && atoi(eb_) > 0 ? atoi(eb_) : 128;  // small footprint: see DESIGN.md
     void* args[] = {&a, &G, &barrier, &barrier_base};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }

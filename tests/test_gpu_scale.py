@@ -1,0 +1,82 @@
+"""GPU tests at BASELINE.json's full sizes (configs[3]: a local map of 50 keyframes, ~15 M points in one DenseCRF), through
+the C ABI.  The oracle finishes a 1 M-point map in seconds and is the checker there; at 15 M points the checks are
+size-independent properties of the filter (linearity, symmetry of the splat-blur-slice operator, K1 = 1/norm^2) and of the
+marginals (rows sum to one, labels in range).  Both lattice regimes of SURVEY 8(d) are covered: the node's scales
+(a few thousand vertices: atomic contention) and fine scales (millions of vertices: hash capacity)."""
+import numpy as np
+import pytest
+
+from conftest import CONFIG, FOREST
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import rovinasemanticsegmentation_b200 as rss
+    c = rss.Context(CONFIG, FOREST, 0)
+    yield c
+    c.close()
+
+
+@pytest.mark.timeout(300)
+def test_local_map_1m_points_vs_oracle(ctx, orc):
+    from rovinasemanticsegmentation_b200 import synth
+    N, M = 1_000_000, 9
+    xyz, col = synth.local_map(seed=41, n_points=N)
+    lab = (np.floor(xyz[:, 0]).astype(int) + np.floor(xyz[:, 1] * 2).astype(int)) % M
+    U = synth.unary_from_labels(lab, M, seed=2)
+    f6 = orc.features_xyzrgb(xyz, col, 0.5, 4.0)  # the node's kernel widths, src/segmenter.cpp:629-637
+    Q0 = orc.crf_inference(U, [(f6, 10.0)], 5)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise_xyzrgb(xyz, col, 0.5, 4.0, 10.0)
+    Q1, l1 = crf.inference(5, unknown=M - 1, want_labels=True)
+    assert np.abs(Q0 - Q1).max() <= 1e-4
+    assert (orc.gated_argmax(Q0, M - 1) == l1).mean() >= 0.999
+    crf.close()
+
+
+@pytest.mark.timeout(420)
+@pytest.mark.parametrize("wxyz,wrgb,min_vertices", [(0.5, 4.0, 1_000), (20.0, 40.0, 1_000_000)])
+def test_local_map_15m_points_properties(ctx, wxyz, wrgb, min_vertices):
+    from rovinasemanticsegmentation_b200 import synth
+    N = 15_000_000
+    xyz, col = synth.local_map(seed=43, n_points=N)
+    rng = np.random.default_rng(7)
+    # ---- filter properties with one channel
+    crf = ctx.crf(N, 1)
+    crf.add_pairwise_xyzrgb(xyz, col, wxyz, wrgb, 1.0)
+    V = crf.lattice_size(0)
+    assert V >= min_vertices
+    x = rng.random((N, 1), dtype=np.float32)
+    y = rng.random((N, 1), dtype=np.float32)
+    Kx, Ky = crf.filter(x), crf.filter(y)
+    Kxy = crf.filter((2.0 * x - 0.5 * y).astype(np.float32))
+    scale = max(np.abs(Kx).max(), np.abs(Ky).max())
+    assert np.abs(Kxy - (2.0 * Kx - 0.5 * Ky)).max() <= 2e-4 * scale                      # linearity
+    a, b = float(np.dot(x[:, 0].astype(np.float64), Ky[:, 0])), float(np.dot(Kx[:, 0].astype(np.float64), y[:, 0]))
+    assert abs(a - b) <= 1e-5 * abs(a)                                                     # <x, K y> = <K x, y>
+    K1 = crf.filter(np.ones((N, 1), np.float32))
+    assert K1.min() > 0
+    crf.close()
+    # ---- mean field with two label layers sharing the lattice (configs[2] + configs[3])
+    del Kx, Ky, Kxy, K1, x, y
+    Ms = [8, 9]
+    crf = ctx.crf(N, Ms)
+    for l, M in enumerate(Ms):
+        lab = (np.floor(xyz[:, 0] * (1 + l)).astype(int) + np.floor(xyz[:, 2] * 3).astype(int)) % M
+        crf.set_unary(synth.unary_from_labels(lab, M, seed=l), l)
+    crf.add_pairwise_xyzrgb(xyz, col, wxyz, wrgb, 10.0)
+    Q, labels = crf.inference(10, unknown=[7, 8], want_labels=True)
+    for l, M in enumerate(Ms):
+        assert np.isfinite(Q[l]).all()
+        assert np.abs(Q[l].sum(1) - 1.0).max() <= 1e-5
+        assert labels[l].max() < M
+        # the gate of src/segmenter.cpp:645-657 on the returned marginals
+        best = Q[l].argmax(1)
+        gated = np.where(Q[l].max(1) > np.float32(2.0 / M), best, [7, 8][l])
+        assert (gated == labels[l]).mean() >= 0.9999
+    t = ctx.timings()
+    print("15M points, %d vertices: %.1f ms per mean-field iteration" % (V, t["meanfield_ms"] / 10))
+    crf.close()
