@@ -21,7 +21,7 @@ namespace rss {
 float lattice_alpha(int d);
 rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp,
                          bool want_csr);
-rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G);
+rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h);
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
                           int Mp);
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
@@ -357,8 +357,9 @@ static bool crf_fused_order(const rss_crf* crf, int* first, int* second) {
     const int K = (int)crf->kernels.size();
     if (K < 1 || K > FUSED_MAX_LAT) return false;
     const int G = crf->Mp / 4;
+    const TileMap tm = fused_tile_map(G, crf->N, crf->grid_w, crf->grid_h, crf->ctx->sm_count);
     for (const Lattice* L : crf->kernels)
-        if (!L->ordered || L->tile_TP != fused_tile_points(G)) return false;
+        if (!L->ordered || L->tile_TP != tm.TP || L->tile_W != tm.W) return false;
     if (K == 1) {
         *first = 0; *second = -1;
         return fused_signature_supported(G, crf->kernels[0]->d + 1, 0);
@@ -426,9 +427,10 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     const float* U = crf->unary.as<float>();
     float* Q = crf->Q.as<float>();
     Lattice& L0 = *Ls[0];
+    const TileMap tm = fused_tile_map(G, N, crf->grid_w, crf->grid_h, ctx->sm_count);
     // pass 0: Q0 = expAndNormalize(-unary) and its splat
     for (int k = 0; k < K; k++) { fa.lat[k].vin = nullptr; fa.lat[k].vout = tgt[k]->as<float>(); }
-    launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, nullptr, N, G, ls, 2);
+    launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, nullptr, tm, G, ls, 2);
     for (int it = 0; it < iters; it++) {
         for (int k = 0; k < K; k++) {
             ba.ping[k] = tgt[k]->as<float4>(); ba.pong[k] = spare[k]->as<float4>(); ba.zero[k] = res[k]->as<float4>();
@@ -444,7 +446,7 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
             fa.lat[k].vout = tgt[k]->as<float>();
         }
         const bool last = it == iters - 1;
-        launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, last ? labels_dev : nullptr, N, G, ls, last ? (1 | 4) : (1 | 2));
+        launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, last ? labels_dev : nullptr, tm, G, ls, last ? (1 | 4) : (1 | 2));
     }
     // restore the two-table convention of the generic path: val_a = the all-zero table, splat_target = 0
     for (int k = 0; k < K; k++) {
@@ -559,7 +561,7 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
         if (rc != RSS_OK) return rc;
         L->ordered = raster;
         if (raster && tile_ok) {
-            rc = lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4);
+            rc = lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, crf->grid_w, crf->grid_h);
             if (rc != RSS_OK) return rc;
         }
         if (!sync) return RSS_OK;
@@ -572,7 +574,7 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
             L->runs = (long long)h[5];
             // coherent point order: on average every vertex run spans more than two points
             L->ordered = raster || 2 * L->runs <= (long long)maxv;
-            if (L->ordered && tile_ok && L->tile_TP == 0) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4);
+            if (L->ordered && tile_ok && L->tile_TP == 0) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, crf->grid_w, crf->grid_h);
             return RSS_OK;
         }
         if ((uint64_t)hcap >= 2 * next_pow2(2 * maxv) || hcap >= (1u << 30))
@@ -702,6 +704,7 @@ extern "C" rss_status rss_crf_add_pairwise_gaussian(rss_crf* crf, int W, int H, 
     if (!crf) return RSS_ERR_INVALID;
     rss_ctx* ctx = crf->ctx;
     if ((long long)W * H != crf->N) return ctx->fail(RSS_ERR_INVALID, "W*H must equal the CRF's point count");
+    if (crf->kernels.empty()) { crf->grid_w = W; crf->grid_h = H; }
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * 2 * 4));
     RSS_LAUNCH(ctx, feat_gaussian_kernel, rss_div_up(crf->N, 256), 256, 0, ctx->s0, W, H, sx, sy, crf->feat_stage.as<float>());
@@ -713,6 +716,7 @@ extern "C" rss_status rss_crf_add_pairwise_bilateral(rss_crf* crf, int W, int H,
     if (!crf) return RSS_ERR_INVALID;
     rss_ctx* ctx = crf->ctx;
     if ((long long)W * H != crf->N || !im) return ctx->fail(RSS_ERR_INVALID, "W*H must equal the CRF's point count; image required");
+    if (crf->kernels.empty()) { crf->grid_w = W; crf->grid_h = H; }
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)crf->N * 5 * 4));
     uint8_t* im_dev = reinterpret_cast<uint8_t*>(crf->scratch.ptr);  // N*Mp*4 >= N*3 bytes
@@ -923,6 +927,7 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
         if (st != RSS_OK) return st;
         ctx->keyframe_crf = crf;
     }
+    crf->grid_w = W; crf->grid_h = H;
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * 8 * 4));
     float* f3 = crf->feat_stage.as<float>();
     float* f5 = f3 + (size_t)N * 3;

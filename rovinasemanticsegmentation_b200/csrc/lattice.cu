@@ -689,17 +689,19 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
 }
 
 // tile-local CSR for the fused mean-field kernel (after the normalisation: the pre-scale is folded into the weights)
-rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G) {
-    const int TP = fused_tile_points(G), d1 = L.d + 1;
-    const size_t ntiles = (size_t)rss_div_up(L.N, TP), cap = ntiles * TP * d1;
+rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h) {
+    const TileMap tm = fused_tile_map(G, L.N, grid_w, grid_h, ctx->sm_count);
+    const int d1 = L.d + 1;
+    const size_t ntiles = (size_t)tm.ntiles, cap = ntiles * tm.TP * d1;
     RSS_CU(ctx, L.tile_pairs.reserve(cap * sizeof(uint2)));
     RSS_CU(ctx, L.tile_ent_meta.reserve(cap * sizeof(int2)));
     RSS_CU(ctx, L.tile_nent.reserve(ntiles * 4));
     const bool pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
-    launch_tile_csr_build(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), pre ? L.norm.as<float>() : nullptr, L.N, d1, TP, G * 16,
+    launch_tile_csr_build(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), pre ? L.norm.as<float>() : nullptr, tm, d1, G * 16,
                           L.counts.as<uint32_t>(), L.tile_pairs.as<uint2>(), L.tile_ent_meta.as<int2>(),
                           L.tile_nent.as<int>());
-    L.tile_TP = TP;
+    L.tile_TP = tm.TP;
+    L.tile_W = tm.W;
     RSS_CU(ctx, cudaGetLastError());
     return RSS_OK;
 }

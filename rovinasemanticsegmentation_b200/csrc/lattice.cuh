@@ -44,6 +44,7 @@ struct Lattice {
     DevBuf val_c;        // third table of the fused mean-field path (meanfield.cu)
     DevBuf tile_pairs, tile_ent_meta, tile_nent;  // tile-local CSR of the splat matrix (meanfield.cu)
     int tile_TP = 0;     // points per tile the tile CSR was built for (0 = not built)
+    int tile_W = 0;      // image width of the 2-D tiling the tile CSR was built for (0 = 1-D tiles)
     bool have_csr = false;  // vertex-major CSR + segments (generic splat path) built
     bool ordered = false;  // consecutive points share lattice vertices (raster order): the fused path applies
     long long runs = -1;   // number of (point, corner) pairs whose vertex differs from the previous point's (diagnostics)
@@ -71,6 +72,7 @@ struct rss_crf {
     rss::DevBuf scratch;           // float[N][Mp] staging for host-layout conversions / filter tests
     rss::DevBuf labels;            // uint8[n_layers][N]
     rss::DevBuf feat_stage;        // float[N][d] staging for feature upload
+    int grid_w = 0, grid_h = 0;    // the points are the pixels of a grid_w x grid_h image in raster order (0 = unknown)
     std::vector<rss::Lattice*> kernels;
     std::vector<rss::Lattice*> pool;  // released lattices whose device buffers are reused by the next build
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // per-lattice streams

@@ -30,7 +30,7 @@
 #define RSS_TILE_PREFETCH 0  // request the streaming inputs of step s + 1 before step s gathers its rows
 #endif
 #ifndef RSS_TILE_IU
-#define RSS_TILE_IU 2  // splat segments a thread walks at once
+#define RSS_TILE_IU 1  // splat segments a thread walks at once
 #endif
 #ifndef RSS_TILE_POINTS
 #define RSS_TILE_POINTS 512  // target points per tile (<= 512: the tile CSR build kernel's hash capacity)
@@ -88,9 +88,13 @@ __device__ __forceinline__ void red_add_v4(float* dst, const float4 v) {
 // kernel is pre-normalised (DenseKernel::filter, pairwise.cpp:65-66), so the gather needs no norm lookup.
 // Entry meta: x = (start of the segment in the tile's pair array) | (length << 16), y = vertex id.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TILE_HASH = 8192;      // >= 2 * max pairs per tile (512 points * 8 corners)
+constexpr int TILE_HASH = 8192;      // largest shared-memory hash: >= 2 * max pairs per tile (512 points * 8 corners)
 constexpr int TILE_MAX_PAIRS = 4096;
-constexpr int TILE_SEG = 8;          // pairs per splat segment (one thread walks one segment serially)
+#ifndef RSS_TILE_SEG
+#define RSS_TILE_SEG 32
+#endif
+constexpr int TILE_SEG = RSS_TILE_SEG;  // pairs per splat segment (one thread walks one segment serially)
+constexpr int TILE_CHUNK = 8;           // pairs requested at once by the gather
 constexpr int TILE_SMEM_BYTES = 2 * TILE_HASH * 4 + TILE_MAX_PAIRS * 2;
 
 __device__ __forceinline__ int2 block_excl_scan2(int a, int b, int2* total) {  // 256 threads
@@ -119,30 +123,32 @@ __device__ __forceinline__ int2 block_excl_scan2(int a, int b, int2* total) {  /
 
 template <int D1>
 __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restrict__ offsets, const float* __restrict__ bary,
-                                                             const float* __restrict__ norm, int N, int TP, int row_bytes,
-                                                             const uint32_t* __restrict__ counts, uint2* __restrict__ pairs,
-                                                             int2* __restrict__ ent_meta, int* __restrict__ tile_nent) {
+                                                             const float* __restrict__ norm, const TileMap tm, int row_bytes,
+                                                             int HC, const uint32_t* __restrict__ counts,
+                                                             uint2* __restrict__ pairs, int2* __restrict__ ent_meta,
+                                                             int* __restrict__ tile_nent) {
     __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1];
     extern __shared__ int tile_smem[];  // TILE_SMEM_BYTES, above the 48 KB static limit
-    int* hkeys = tile_smem;
-    int* hcnt = tile_smem + TILE_HASH;
-    unsigned short* pslot = reinterpret_cast<unsigned short*>(tile_smem + 2 * TILE_HASH);
+    int* hkeys = tile_smem;  // HC slots (power of two, > pairs per tile)
+    int* hcnt = tile_smem + HC;
+    unsigned short* pslot = reinterpret_cast<unsigned short*>(tile_smem + 2 * HC);
+    const int hshift = 32 - (31 - __clz(HC));
     const int tile = blockIdx.x;
-    const int base = tile * TP;
-    const int npts = min(TP, N - base);
-    const int npairs = npts * D1;
+    const int TP = tm.TP;
+    const int npairs = TP * D1;  // slots; points outside the image / beyond N are skipped
     const size_t tb = (size_t)tile * TP * D1;
     if (counts[1]) {
         if (threadIdx.x == 0) tile_nent[tile] = 0;
         return;
     }
-    for (int i = threadIdx.x; i < TILE_HASH; i += 256) { hkeys[i] = -1; hcnt[i] = 0; }
+    for (int i = threadIdx.x; i < HC; i += 256) { hkeys[i] = -1; hcnt[i] = 0; }
     if (threadIdx.x <= TILE_SEG) hist[threadIdx.x] = 0;
     __syncthreads();
-    const int* off_t = offsets + (size_t)base * D1;
     for (int i = threadIdx.x; i < npairs; i += 256) {
-        const int key = off_t[i];
-        unsigned h = ((unsigned)key * 2654435761u) >> 19;  // 13 bits
+        const int lp = i / D1, p = tile_point(tm, tile, lp);
+        if (p < 0) continue;
+        const int key = offsets[(size_t)p * D1 + (i - lp * D1)];
+        unsigned h = ((unsigned)key * 2654435761u) >> hshift;
         for (;;) {
             const int cur = hkeys[h];
             if (cur == key) break;
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
                 const int old = atomicCAS(&hkeys[h], -1, key);
                 if (old == -1 || old == key) break;
             }
-            h = (h + 1) & (TILE_HASH - 1);
+            h = (h + 1) & (HC - 1);
         }
         pslot[i] = (unsigned short)h;
         atomicAdd(&hcnt[h], 1);
@@ -159,9 +165,9 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     // Lists are cut into segments of at most TILE_SEG pairs and the segments are ordered by length (longest first), so
     // that the lanes of a warp of the gather walk lists of (nearly) equal length.  Thread t owns slots [32t, 32t+32).
     int nseg = 0, ncnt = 0;
-    const int s0 = threadIdx.x * (TILE_HASH / 256);
+    const int spt = HC / 256, s0 = threadIdx.x * spt;  // slots per thread
 #pragma unroll 4
-    for (int k = 0; k < TILE_HASH / 256; k++) {
+    for (int k = 0; k < spt; k++) {
         const int c = hcnt[s0 + k];
         if (c > 0) {
             const int full = c / TILE_SEG, rem = c - full * TILE_SEG;
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         tile_nent[tile] = tot.x;
     }
     __syncthreads();
-    for (int k = 0; k < TILE_HASH / 256; k++) {
+    for (int k = 0; k < spt; k++) {
         const int c = hcnt[s0 + k];
         if (c > 0) {
             const int key = hkeys[s0 + k];
@@ -193,12 +199,12 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         }
     }
     __syncthreads();
-    const float* bary_t = bary + (size_t)base * D1;
     for (int i = threadIdx.x; i < npairs; i += 256) {
+        const int lp = i / D1, p = tile_point(tm, tile, lp);
+        if (p < 0) continue;
         const int pos = atomicAdd(&hcnt[pslot[i]], 1);
-        const int lp = i / D1;
-        float w = bary_t[i];
-        if (norm) w = __fmul_rn(w, norm[base + lp]);
+        float w = bary[(size_t)p * D1 + (i - lp * D1)];
+        if (norm) w = __fmul_rn(w, norm[p]);
         pairs[tb + pos] = make_uint2((unsigned)lp * (unsigned)row_bytes, __float_as_uint(w));
     }
 }
@@ -291,15 +297,25 @@ __device__ __forceinline__ void gather_entries(const uint2* __restrict__ pr, con
                 longest = max(longest, len[u]);
             }
         }
-        for (int i = 0; i < longest; i++) {
+        // pairs are requested TILE_CHUNK at a time (independent loads, one L2 round trip per chunk), then the
+        // multiply-adds run out of shared memory
+        for (int c0 = 0; c0 < longest; c0 += TILE_CHUNK) {
+            uint2 pw[IU][TILE_CHUNK];
 #pragma unroll
-            for (int u = 0; u < IU; u++) {
-                if (i < len[u]) {
-                    const uint2 pw = __ldg(pp[u] + i);
-                    const float w = __uint_as_float(pw.y);
-                    const float4 q = *reinterpret_cast<const float4*>(qb[u] + pw.x);
-                    acc[u].x = fmaf(w, q.x, acc[u].x); acc[u].y = fmaf(w, q.y, acc[u].y);
-                    acc[u].z = fmaf(w, q.z, acc[u].z); acc[u].w = fmaf(w, q.w, acc[u].w);
+            for (int u = 0; u < IU; u++)
+#pragma unroll
+                for (int i = 0; i < TILE_CHUNK; i++)
+                    if (c0 + i < len[u]) pw[u][i] = __ldg(pp[u] + c0 + i);
+#pragma unroll
+            for (int i = 0; i < TILE_CHUNK; i++) {
+#pragma unroll
+                for (int u = 0; u < IU; u++) {
+                    if (c0 + i < len[u]) {
+                        const float w = __uint_as_float(pw[u][i].y);
+                        const float4 q = *reinterpret_cast<const float4*>(qb[u] + pw[u][i].x);
+                        acc[u].x = fmaf(w, q.x, acc[u].x); acc[u].y = fmaf(w, q.y, acc[u].y);
+                        acc[u].z = fmaf(w, q.z, acc[u].z); acc[u].w = fmaf(w, q.w, acc[u].w);
+                    }
                 }
             }
         }
@@ -312,7 +328,8 @@ __device__ __forceinline__ void gather_entries(const uint2* __restrict__ pr, con
 template <int G, int D1A, int D1B>
 __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(const __grid_constant__ FusedArgs a,
                                                              const float* __restrict__ unary, float* __restrict__ Q,
-                                                             uint8_t* __restrict__ labels, int N, int TP, int steps,
+                                                             uint8_t* __restrict__ labels,
+                                                             const __grid_constant__ TileMap tm, int steps,
                                                              const __grid_constant__ FusedLayers ls, int mode) {
     extern __shared__ float4 qtile[];  // [TP][G]
     if (a.counts[0][1]) return;  // lattice overflow: the host rebuilds with a larger table and runs again
@@ -321,7 +338,7 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane / G, g = lane - sub * G, gbase = sub * G;
     const bool lane_on = sub < cpw;
-    const int tile = blockIdx.x, base = tile * TP;
+    const int tile = blockIdx.x, TP = tm.TP, N = tm.N;
     const bool do_slice = mode & 1, do_splat = mode & 2, store_q = mode & 4;
     const int c0 = 4 * g;
     // entry metadata of this tile's splat (list end, vertex) -> shared memory; consumed after phase 1
@@ -363,11 +380,14 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
         float4 u;
         PointIn<D1A> A;
         PointIn<D1B> B;
+        int p;
         bool valid;
     };
     auto load_step = [&](int s, StepIn& in) {
-        const int lp = (s * 8 + wib) * cpw + sub, p = base + lp;
-        in.valid = lane_on && lp < TP && p < N;
+        const int lp = (s * 8 + wib) * cpw + sub;
+        const int p = lane_on ? tile_point(tm, tile, lp) : -1;
+        in.valid = p >= 0;
+        in.p = p;
         in.u = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in.valid) {
             in.u = __ldg(reinterpret_cast<const float4*>(unary + (size_t)p * Mp) + g);
@@ -376,7 +396,7 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
     };
     auto run_step = [&](int s, const StepIn& in) {
         const int lp = (s * 8 + wib) * cpw + sub;
-        const int p = base + lp;
+        const int p = in.p;
         const bool valid = in.valid;
         float4 t = make_float4(-in.u.x, -in.u.y, -in.u.z, -in.u.w);
         if (valid && do_slice) {
@@ -604,11 +624,39 @@ __global__ void __launch_bounds__(256) splat_ones_runs_kernel(const int* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-int fused_tile_steps(int G) {  // warp-steps per tile so that a tile holds about RSS_TILE_POINTS points
+static int fused_tile_steps(int G, int TP) {  // warp-steps a CTA needs for TP points: 8 warps x (32 / G) points per step
     const int per_step = 8 * (32 / G);
-    return std::max(1, (RSS_TILE_POINTS + per_step / 2) / per_step);
+    return (TP + per_step - 1) / per_step;
 }
-int fused_tile_points(int G) { return 8 * (32 / G) * fused_tile_steps(G); }
+// The point kernel is latency-bound per CTA, so ONE full wave of resident CTAs is the sweet spot: when the default
+// tile size would need slightly more tiles than fit at once (sm_count * RSS_TILE_MINB), the tiles grow (up to
+// TILE_MAX_POINTS) until they fit.
+constexpr int TILE_MAX_POINTS = 576;
+TileMap fused_tile_map(int G, int N, int W, int H, int sm_count) {
+    TileMap m;
+    m.N = N;
+    const int slots = std::max(1, sm_count * RSS_TILE_MINB);
+    if (W > 0 && H > 0 && (long long)W * H == N) {
+        m.W = W; m.H = H; m.TW = 32; m.TH = RSS_TILE_POINTS / 32;
+        m.tiles_x = (W + m.TW - 1) / m.TW;
+        if (m.tiles_x <= slots) {
+            const int rows_fit = slots / m.tiles_x;                 // tile rows of one wave
+            const int th = (H + rows_fit - 1) / rows_fit;           // tile height that makes the image fit in one wave
+            if (th > m.TH && th * m.TW <= TILE_MAX_POINTS) m.TH = th;
+        }
+        m.TP = m.TW * m.TH;
+        m.ntiles = m.tiles_x * ((H + m.TH - 1) / m.TH);
+    } else {
+        const int per_step = 8 * (32 / G);
+        m.W = m.H = 0; m.TW = m.TH = 0; m.tiles_x = 0;
+        m.TP = per_step * std::max(1, (RSS_TILE_POINTS + per_step / 2) / per_step);
+        const long long fit = ((long long)N + slots - 1) / slots;  // points per tile for one wave
+        const int tp_fit = (int)((fit + per_step - 1) / per_step) * per_step;
+        if (tp_fit > m.TP && tp_fit <= TILE_MAX_POINTS) m.TP = tp_fit;
+        m.ntiles = (int)(((long long)N + m.TP - 1) / m.TP);
+    }
+    return m;
+}
 
 bool fused_group_supported(int G) { return G == 1 || G == 2 || G == 3 || G == 5 || G == 6; }
 bool fused_signature_supported(int G, int d1a, int d1b) {
@@ -621,9 +669,9 @@ bool fused_signature_supported(int G, int d1a, int d1b) {
 
 template <int G>
 static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
-                          uint8_t* labels, int N, const FusedLayers& ls, int mode) {
-    const int TP = fused_tile_points(G), steps = fused_tile_steps(G);
-    const int grid = rss_div_up(N, TP);
+                          uint8_t* labels, const TileMap& tm, const FusedLayers& ls, int mode) {
+    const int TP = tm.TP, steps = fused_tile_steps(G, TP);
+    const int grid = tm.ntiles;
 #define RSS_TILE(A, B)                                                                                                  \
     do {                                                                                                                \
         auto kfn = meanfield_tile_kernel<G, A, B>;                                                                      \
@@ -634,7 +682,7 @@ static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d
             cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
             c->fused_attr_mask |= bit__;                                                                                \
         }                                                                                                               \
-        RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, N, TP, steps, ls, mode); \
+        RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, tm, steps, ls, mode); \
     } while (0)
     switch (d1a * 16 + d1b) {
         case 0x46: RSS_TILE(4, 6); break;
@@ -648,27 +696,31 @@ static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d
 #undef RSS_TILE
 }
 void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
-                            uint8_t* labels, int N, int G, const FusedLayers& ls, int mode) {
+                            uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode) {
     switch (G) {
-        case 1: launch_tile_g<1>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
-        case 2: launch_tile_g<2>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
-        case 3: launch_tile_g<3>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
-        case 5: launch_tile_g<5>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
-        case 6: launch_tile_g<6>(c, st, a, d1a, d1b, unary, Q, labels, N, ls, mode); break;
+        case 1: launch_tile_g<1>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
+        case 2: launch_tile_g<2>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
+        case 3: launch_tile_g<3>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
+        case 5: launch_tile_g<5>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
+        case 6: launch_tile_g<6>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
         default: break;
     }
 }
 
-void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, int N,
-                           int d1, int TP, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta, int* tile_nent) {
-    const int grid = rss_div_up(N, TP);
+void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm,
+                           const TileMap& tm, int d1, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta,
+                           int* tile_nent) {
+    const int grid = tm.ntiles, TP = tm.TP;
+    int HC = 1024;  // power of two with load factor <= 0.8 even when every pair of the tile hits a different vertex
+    while (HC * 4 < TP * d1 * 5) HC *= 2;
+    const size_t tsm = (size_t)2 * HC * 4 + (size_t)TP * d1 * 2;
 #define RSS_TCB(D)                                                                                                      \
     do {                                                                                                                \
         if (!(c->tile_attr_mask & (1u << D))) {  /* once per context (= per device) */                                  \
-            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES); \
+            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   \
             c->tile_attr_mask |= 1u << D;                                                                               \
         }                                                                                                               \
-        RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, TILE_SMEM_BYTES, st, offsets, bary, norm, N, TP, row_bytes, counts, pairs, \
+        RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, tsm, st, offsets, bary, norm, tm, row_bytes, HC, counts, pairs,    \
                    ent_meta, tile_nent);                                                                                \
     } while (0)
     switch (d1) {

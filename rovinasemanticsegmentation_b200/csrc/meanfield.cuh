@@ -6,6 +6,25 @@ namespace rss {
 
 constexpr int FUSED_MAX_LAT = 2;
 
+// How a tile's local point index maps to the point index.  W == 0: tile t owns the TP consecutive points starting at
+// t * TP (generic point sets).  W > 0: the points are the pixels of a W x H image in raster order and a tile is a
+// TW x TH pixel block - neighbouring pixels in BOTH directions share lattice vertices, so a block touches several
+// times fewer distinct vertices than a strip of the same size (fewer splat atomics, better L1 reuse of value rows).
+struct TileMap {
+    int N, TP, W, H, TW, TH, tiles_x, ntiles;
+};
+__host__ __device__ __forceinline__ int tile_point(const TileMap& m, int tile, int lp) {
+    if (lp >= m.TP) return -1;
+    if (m.W == 0) {
+        const long long p = (long long)tile * m.TP + lp;
+        return p < m.N ? (int)p : -1;
+    }
+    const int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
+    const int ly = lp / m.TW, lx = lp - ly * m.TW;
+    const int x = tx * m.TW + lx, y = ty * m.TH + ly;
+    return (x < m.W && y < m.H) ? y * m.W + x : -1;
+}
+
 struct FusedLat {
     const int* offsets;   // [N][d+1] vertex ids
     const float* bary;    // [N][d+1]
@@ -48,11 +67,12 @@ struct BlurMultiArgs {
 
 bool fused_group_supported(int G);  // channel-group counts the tile kernel is instantiated for
 bool fused_signature_supported(int G, int d1a, int d1b);
-int fused_tile_points(int G);
+TileMap fused_tile_map(int G, int N, int W, int H, int sm_count);  // W = H = 0 for point sets without an image grid
 void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
-                            uint8_t* labels, int N, int G, const FusedLayers& ls, int mode);
-void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, int N,
-                           int d1, int TP, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta, int* tile_nent);
+                            uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode);
+void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm,
+                           const TileMap& tm, int d1, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta,
+                           int* tile_nent);
 int blur_multi_grid(const rss_ctx* c);  // CTAs of the cooperative blur (one barrier arrival each)
 void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base);
 void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
