@@ -15,7 +15,7 @@ namespace rss {
 void crf_release_cached(rss_ctx* ctx);  // crf.cu
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
 rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
-rss_status frame_segment_finish(rss_ctx* ctx, float fill);
+rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out = nullptr, int unary_stride = 0);
 }
 
 static thread_local std::string g_create_error;
@@ -622,7 +622,9 @@ rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, 
     return frame_prepare(ctx, Kinv, R, t, cfg.depth_min, cfg.depth_max);
 }
 // second half: samples, features, forest, low-res scatter, upsample
-rss_status frame_segment_finish(rss_ctx* ctx, float fill) {
+// unary_out != NULL: the up-sampled values go, negated, straight into that [pixel][unary_stride] energy matrix and the
+// [layer][y][x][class] posterior vector is not produced (keyframe path)
+rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out, int unary_stride) {
     FrameState& f = ctx->fr;
     const HostConfig& cfg = ctx->cfg;
     const ForestDev& F = ctx->forest;
@@ -636,14 +638,15 @@ rss_status frame_segment_finish(rss_ctx* ctx, float fill) {
     cudaEventRecord(ctx->ev[3], ctx->s0);
     const size_t low_elems = (size_t)f.gw * f.gh * F.sumC;
     RSS_CU(ctx, f.lowres.reserve(low_elems * 4));
-    RSS_CU(ctx, f.posteriors.reserve((size_t)W * H * F.sumC * 4));
+    if (!unary_out) RSS_CU(ctx, f.posteriors.reserve((size_t)W * H * F.sumC * 4));
     launch_lowres_fill(ctx, ctx->s0, f.lowres.as<float>(), low_elems, fill);
     launch_lowres_scatter(ctx, ctx->s0, f.post.as<float>(), F.sumC, f.xs.as<int>(), f.ys.as<int>(), n, stride, f.gw, f.gh,
                           F.L, F.C, f.lowres.as<float>());
-    launch_upsample(ctx, ctx->s0, f.lowres.as<float>(), f.gw, f.gh, W, H, F.L, F.C, f.posteriors.as<float>());
+    if (unary_out) launch_upsample(ctx, ctx->s0, f.lowres.as<float>(), f.gw, f.gh, W, H, F.L, F.C, unary_out, unary_stride);
+    else launch_upsample(ctx, ctx->s0, f.lowres.as<float>(), f.gw, f.gh, W, H, F.L, F.C, f.posteriors.as<float>());
     cudaEventRecord(ctx->ev[4], ctx->s0);
     RSS_CU(ctx, cudaGetLastError());
-    f.have_post = true;
+    f.have_post = unary_out == nullptr;
     return RSS_OK;
 }
 

@@ -328,19 +328,6 @@ __global__ void __launch_bounds__(256) feat_frame_xyz_kernel(int N, const float4
     f[3 * (size_t)p + 1] = __fmul_rn(v.y, inv_sigma);
     f[3 * (size_t)p + 2] = __fmul_rn(v.z, inv_sigma);
 }
-// posteriors [layer][pixel][C_l] -> energies [pixel][Mp] = -posterior (segmenter.cpp:642); pad channels = 0
-__global__ void __launch_bounds__(256) unary_from_posteriors_kernel(const float* __restrict__ post, int N, int Mtot, int Mp,
-                                                                    LayerSpec ls, float* __restrict__ unary) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)N * Mp) return;
-    const int i = (int)(gid / Mp), c = (int)(gid - (long long)i * Mp);
-    if (c >= Mtot) { unary[gid] = 0.f; return; }
-    int l = 0;
-    while (l + 1 < ls.n_layers && c >= ls.off[l + 1]) l++;
-    const int Ml = ls.off[l + 1] - ls.off[l];
-    unary[gid] = -post[(size_t)N * ls.off[l] + (size_t)i * Ml + (c - ls.off[l])];
-}
-
 static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
     LayerSpec ls;
     ls.n_layers = crf->n_layers;
@@ -904,7 +891,7 @@ namespace rss {
 rss_status frame_upload(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth, int W, int H);
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
 rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
-rss_status frame_segment_finish(rss_ctx* ctx, float fill);
+rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out = nullptr, int unary_stride = 0);
 void frame_collect_timings(rss_ctx* ctx, bool with_d2h);
 }
 
@@ -966,15 +953,13 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
         if (st != RSS_OK) return st;
         std::swap(crf->kernels[0], crf->kernels[1]);
         if (attempt == 0) {
-            st = frame_segment_finish(ctx, prm->fill);
+            // the up-sample writes the energies (-log-posteriors, src/segmenter.cpp:642) straight into the CRF's unary matrix
+            st = frame_segment_finish(ctx, prm->fill, crf->unary.as<float>(), crf->Mp);
             if (st != RSS_OK) return st;
         }
         RSS_CU(ctx, cudaEventRecord(crf->ev_join[0], sA));
         RSS_CU(ctx, cudaEventRecord(crf->ev_join[1], sB));
-        // ---- unary = -posteriors, then the mean-field loop once both lattices are ready
-        LayerSpec ls = make_layers(crf, nullptr);
-        RSS_LAUNCH(ctx, unary_from_posteriors_kernel, rss_div_up((long long)N * crf->Mp, 256), 256, 0, ctx->s0,
-                   ctx->fr.posteriors.as<float>(), N, crf->Mtot, crf->Mp, ls, crf->unary.as<float>());
+        // ---- the mean-field loop once both lattices are ready
         cudaEventRecord(ctx->ev[8], ctx->s0);
         RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[0], 0));
         RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[1], 0));

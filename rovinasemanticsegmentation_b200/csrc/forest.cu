@@ -128,22 +128,33 @@ void launch_lowres_scatter(rss_ctx* c, cudaStream_t st, const float* post, int s
 // the index is clamped, vertically the two row indices are clipped and the fraction kept; horizontal pass
 // first (S0*a0 + S1*a1), then vertical (H0*b0 + H1*b1), each product and sum rounded to float.
 // ------------------------------------------------------------------------------------------------
+// UNARY = false: out is the flattened [layer][y][x][class] vector.  UNARY = true (keyframe path): the value is negated
+// (energy = -log-posterior, src/segmenter.cpp:642) and written straight into the CRF's [pixel][Mp] unary layout, which
+// saves the separate posterior -> unary pass; -x is exact, so the energies are bit-identical to the two-pass route.
+template <bool UNARY>
 __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ lowres, int gw, int gh, int W,
-                                                       int H, LayerDims ld, int sumC, double scale_x, double scale_y,
-                                                       float* __restrict__ out) {
+                                                       int H, LayerDims ld, int sumC, int Mp, double scale_x,
+                                                       double scale_y, float* __restrict__ out) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)W * H * sumC;
     if (gid >= total) return;
-    // gid enumerates the flattened output: layer-major
-    int l = 0;
-    long long rem = gid;
-    while (l + 1 < ld.L && rem >= (long long)W * H * ld.C[l]) {
-        rem -= (long long)W * H * ld.C[l];
-        l++;
+    int l = 0, cl;
+    long long px;
+    if (UNARY) {  // gid enumerates [pixel][class over all layers]
+        px = gid / sumC;
+        const int c = (int)(gid - px * sumC);
+        while (l + 1 < ld.L && c >= ld.coff[l + 1]) l++;
+        cl = c - ld.coff[l];
+    } else {      // gid enumerates the flattened output: layer-major
+        long long rem = gid;
+        while (l + 1 < ld.L && rem >= (long long)W * H * ld.C[l]) {
+            rem -= (long long)W * H * ld.C[l];
+            l++;
+        }
+        cl = (int)(rem % ld.C[l]);
+        px = rem / ld.C[l];
     }
     const int C = ld.C[l];
-    const int cl = (int)(rem % C);
-    const long long px = rem / C;
     const int x = (int)(px % W), y = (int)(px / W);
     const float* src = lowres + (size_t)gw * gh * ld.coff[l];
 
@@ -162,17 +173,23 @@ __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__
     const float* r1 = src + (size_t)y1 * gw * C;
     const float h0 = __fadd_rn(__fmul_rn(__ldg(r0 + (size_t)sx * C + cl), a0), __fmul_rn(__ldg(r0 + (size_t)sx1 * C + cl), a1));
     const float h1 = __fadd_rn(__fmul_rn(__ldg(r1 + (size_t)sx * C + cl), a0), __fmul_rn(__ldg(r1 + (size_t)sx1 * C + cl), a1));
-    out[gid] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    const float v = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    if (UNARY) out[(size_t)px * Mp + ld.coff[l] + cl] = -v;
+    else out[gid] = v;
 }
 void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, int gh, int W, int H, int L,
-                     const int* C, float* posteriors) {
+                     const int* C, float* posteriors, int unary_stride) {
     LayerDims d = make_dims(L, C);
     int sumC = 0;
     for (int l = 0; l < L; l++) sumC += C[l];
     const double scale_x = 1.0 / ((double)W / (double)gw), scale_y = 1.0 / ((double)H / (double)gh);
     const long long total = (long long)W * H * sumC;
-    RSS_LAUNCH(c, upsample_kernel, rss_div_up(total, 256), 256, 0, st, lowres, gw, gh, W, H, d, sumC, scale_x,
-               scale_y, posteriors);
+    if (unary_stride > 0)
+        RSS_LAUNCH(c, upsample_kernel<true>, rss_div_up(total, 256), 256, 0, st, lowres, gw, gh, W, H, d, sumC, unary_stride,
+                   scale_x, scale_y, posteriors);
+    else
+        RSS_LAUNCH(c, upsample_kernel<false>, rss_div_up(total, 256), 256, 0, st, lowres, gw, gh, W, H, d, sumC, 0, scale_x,
+                   scale_y, posteriors);
 }
 
 }  // namespace rss

@@ -44,7 +44,8 @@ void launch_lowres_fill(rss_ctx* c, cudaStream_t st, float* lowres, size_t n, fl
 void launch_lowres_scatter(rss_ctx* c, cudaStream_t st, const float* post, int sumC, const int* xs, const int* ys,
                            int n, int stride, int gw, int gh, int L, const int* C, float* lowres);
 // cv::resize(INTER_LINEAR) 32FC(C) to W x H + flatten to [layer][y][x][class] (segmenter.cpp:380-431)
+// unary_stride > 0: write -value into a [pixel][unary_stride] energy matrix instead (keyframe path)
 void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, int gh, int W, int H, int L,
-                     const int* C, float* posteriors);
+                     const int* C, float* posteriors, int unary_stride = 0);
 
 }  // namespace rss
