@@ -29,6 +29,13 @@
 #ifndef RSS_TILE_PREFETCH
 #define RSS_TILE_PREFETCH 0  // request the streaming inputs of step s + 1 before step s gathers its rows
 #endif
+#ifndef RSS_BLUR_U
+#define RSS_BLUR_U 2      // independent (vertex, channel group) items a blur thread keeps in flight
+#endif
+#ifndef RSS_BLUR_MAXT
+#define RSS_BLUR_MAXT 128  // CTA size of the cooperative blur: small register / thread footprint on purpose, so that
+                           // kernels of OTHER keyframes in flight run on the SMs while its CTAs wait at the grid barriers
+#endif
 #ifndef RSS_TILE_IU
 #define RSS_TILE_IU 1  // splat segments a thread walks at once
 #endif
@@ -564,7 +571,7 @@ __device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4
         }
     }
 }
-__global__ void __launch_bounds__(512) blur_multi_coop_kernel(const __grid_constant__ BlurMultiArgs a, int G,
+__global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __grid_constant__ BlurMultiArgs a, int G,
                                                               unsigned int* barrier, unsigned int barrier_base) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     uint32_t V[FUSED_MAX_LAT];
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(512) blur_multi_coop_kernel(const __grid_const
             const float4* src = (j & 1) ? a.pong[k] : a.ping[k];
             float4* dst = (j & 1) ? a.ping[k] : a.pong[k];
             const uint32_t items = V[k] * (uint32_t)G;
-            blur_axis<4>(src, dst, a.nbr[k] + (size_t)j * a.vcap[k], items, G, tid, nthr);
+            blur_axis<RSS_BLUR_U>(src, dst, a.nbr[k] + (size_t)j * a.vcap[k], items, G, tid, nthr);
             if (j == 0 && a.zero[k])
                 for (uint32_t it = tid; it < items; it += nthr) __stcg(a.zero[k] + it, make_float4(0.f, 0.f, 0.f, 0.f));
         }
@@ -741,7 +748,7 @@ int blur_multi_grid(const rss_ctx* c) {
 }
 void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
     static const char* eb_ = getenv("RSS_BLUR_BLOCK");
-    const int grid = blur_multi_grid(c), block = eb_ && atoi(eb_) > 0 ? atoi(eb_) : 128;  // small footprint: see DESIGN.md
+    const int grid = blur_multi_grid(c), block = std::min(RSS_BLUR_MAXT, eb_ && atoi(eb_) > 0 ? atoi(eb_) : 128);
     void* args[] = {&a, &G, &barrier, &barrier_base};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }
