@@ -96,21 +96,25 @@ struct ScaleFactors {
 
 // Permutohedral::init, SSE build (permutohedral.cpp:192-277), one thread per point.
 template <int D>
-__global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restrict__ feat, int N, ScaleFactors sf,
+__global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restrict__ feat, int N, int Next, ScaleFactors sf,
                                                             Key128* __restrict__ table, uint32_t mask,
                                                             int* __restrict__ offsets, float* __restrict__ bary_out,
                                                             uint32_t* __restrict__ first_ref,
                                                             uint32_t* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+    if (i >= Next) return;
     if (*reinterpret_cast<volatile uint32_t*>(counts + 1)) return;  // overflow already detected: the build is void anyway
+    // i == N (only when N % 4 != 0): the reference's SSE loop pads its last block of four points with ZERO features and
+    // still inserts their vertices (permutohedral.cpp:192-198,268-275).  Those vertices never receive a splat, but they
+    // exist for the blur and pass values on between their neighbours - so they must exist here too.
+    const bool padding = i >= N;
     const float invdplus1 = __fdiv_rn(1.0f, (float)(D + 1)), dplus1 = (float)(D + 1);
     float elevated[D + 1], rem0[D + 1], rank[D + 1], bary[D + 2];
     // elevate (:203-209)
     float sm = 0.f;
 #pragma unroll
     for (int j = D; j > 0; j--) {
-        const float cf = __fmul_rn(feat[(size_t)i * D + (j - 1)], sf.s[j - 1]);
+        const float cf = __fmul_rn(padding ? 0.0f : feat[(size_t)i * D + (j - 1)], sf.s[j - 1]);
         elevated[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
         sm = __fadd_rn(sm, cf);
     }
@@ -480,7 +484,8 @@ static ScaleFactors make_scale_factors(int d) {
 
 template <int D>
 static void launch_embed(rss_ctx* c, cudaStream_t st, const float* feat, int N, Lattice& L) {
-    RSS_LAUNCH(c, lattice_embed_kernel<D>, rss_div_up(N, 256), 256, 0, st, feat, N, make_scale_factors(D),
+    const int Next = N + (N % 4 ? 1 : 0);
+    RSS_LAUNCH(c, lattice_embed_kernel<D>, rss_div_up(Next, 256), 256, 0, st, feat, N, Next, make_scale_factors(D),
                L.table.as<Key128>(), L.hcap - 1, L.offsets.as<int>(), L.bary.as<float>(), L.first_ref.as<uint32_t>(),
                L.counts.as<uint32_t>());
 }
@@ -500,15 +505,16 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     if (d < 1 || d > LAT_MAX_D) return ctx->fail(RSS_ERR_INVALID, "pairwise feature dimension must be in [1, 7]");
     L.d = d; L.N = N; L.hcap = hcap; L.vcap = hcap / 2;
     const int d1 = d + 1;
-    const size_t nnz = (size_t)N * d1;
+    const size_t nnz = (size_t)N * d1;                      // pairs of the real points
+    const size_t nnz_ext = nnz + (N % 4 ? (size_t)d1 : 0);  // + the reference's zero-feature padding point (see the embed kernel)
     L.maxseg = (uint32_t)(nnz / SPLAT_SEG + L.vcap + 1);
     RSS_CU(ctx, L.table.reserve((size_t)hcap * sizeof(Key128)));
     RSS_CU(ctx, L.slot_id.reserve((size_t)hcap * 4));
     RSS_CU(ctx, L.first_ref.reserve((size_t)hcap * 4));
-    RSS_CU(ctx, L.rank.reserve((nnz + 8) * 4));
+    RSS_CU(ctx, L.rank.reserve((nnz_ext + 8) * 4));
     RSS_CU(ctx, L.vkeys.reserve((size_t)L.vcap * sizeof(Key128)));
-    RSS_CU(ctx, L.offsets.reserve(nnz * 4));
-    RSS_CU(ctx, L.bary.reserve(nnz * 4));
+    RSS_CU(ctx, L.offsets.reserve(nnz_ext * 4));
+    RSS_CU(ctx, L.bary.reserve(nnz_ext * 4));
     RSS_CU(ctx, L.nbr.reserve((size_t)d1 * L.vcap * sizeof(int2)));
     RSS_CU(ctx, L.norm.reserve((size_t)N * 4));
     RSS_CU(ctx, L.counts.reserve(64));
@@ -527,7 +533,7 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     RSS_CU(ctx, L.val_a.reserve((size_t)(L.vcap + 1) * Mp * 4));
     RSS_CU(ctx, L.val_b.reserve((size_t)(L.vcap + 1) * Mp * 4));
     RSS_CU(ctx, L.val_c.reserve((size_t)(L.vcap + 1) * Mp * 4));
-    RSS_CU(ctx, L.scan_tmp.reserve((scan_tmp_elems(nnz > hcap ? nnz : hcap) + 8) * 4));
+    RSS_CU(ctx, L.scan_tmp.reserve((scan_tmp_elems(nnz_ext > hcap ? nnz_ext : hcap) + 8) * 4));
     uint32_t* counts = L.counts.as<uint32_t>();
     RSS_CU(ctx, cudaMemsetAsync(L.table.ptr, 0xFF, (size_t)hcap * sizeof(Key128), st));
     RSS_CU(ctx, cudaMemsetAsync(L.first_ref.ptr, 0xFF, (size_t)hcap * 4, st));
@@ -551,14 +557,14 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
         default: launch_embed<7>(ctx, st, feat, N, L); break;
     }
     // vertex numbering by first appearance: flags over the (point, corner) pairs -> exclusive scan; counts[0] = V
-    RSS_LAUNCH(ctx, first_flags_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
+    RSS_LAUNCH(ctx, first_flags_kernel, rss_div_up((long long)nnz_ext, 256), 256, 0, st, L.offsets.as<int>(), nnz_ext,
                L.first_ref.as<uint32_t>(), counts, L.rank.as<uint32_t>());
-    exclusive_scan_u32(L.rank.as<uint32_t>(), L.rank.as<uint32_t>(), nnz, L.scan_tmp.as<uint32_t>(), counts, st,
+    exclusive_scan_u32(L.rank.as<uint32_t>(), L.rank.as<uint32_t>(), nnz_ext, L.scan_tmp.as<uint32_t>(), counts, st,
                        &ctx->launches);
-    RSS_LAUNCH(ctx, assign_ids_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
+    RSS_LAUNCH(ctx, assign_ids_kernel, rss_div_up((long long)nnz_ext, 256), 256, 0, st, L.offsets.as<int>(), nnz_ext,
                L.first_ref.as<uint32_t>(), L.rank.as<uint32_t>(), L.table.as<Key128>(), L.vcap, L.slot_id.as<uint32_t>(),
                L.vkeys.as<Key128>(), counts);
-    RSS_LAUNCH(ctx, remap_offsets_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,
+    RSS_LAUNCH(ctx, remap_offsets_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,  // real pairs only
                L.slot_id.as<uint32_t>(), want_csr ? L.deg.as<uint32_t>() : (uint32_t*)nullptr, counts, L.vcap);
     switch (d) {
         case 1: launch_neighbors<1>(ctx, st, L); break;

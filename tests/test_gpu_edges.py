@@ -1,0 +1,149 @@
+"""GPU tests of the boundary's edge cases and error behaviour: every lattice dimension and label count the ABI accepts,
+several pairwise terms, tiny and ragged problem sizes, and the status codes a caller of the reference classes would hit
+(missing config key = Utils::KeyNotFoundException, malformed model, call-order violations)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CONFIG, FOREST
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import rovinasemanticsegmentation_b200 as rss
+    c = rss.Context(CONFIG, FOREST, 0)
+    yield c
+    c.close()
+
+
+def _problem(N, M, d, seed):
+    rng = np.random.default_rng(seed)
+    # smooth features so that points share lattice vertices (a real filter, not an identity)
+    t = np.linspace(0, 6, N, dtype=np.float64)
+    f = np.stack([np.sin(0.7 * (k + 1) * t + k) * (2.0 + k) for k in range(d)], axis=1) + rng.normal(0, 0.05, (N, d))
+    lab = (np.floor(t * 1.7).astype(int)) % M
+    from rovinasemanticsegmentation_b200 import synth
+    U = synth.unary_from_labels(lab, M, seed) if M > 1 else np.zeros((N, 1), np.float32)
+    return f.astype(np.float32), U
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7])
+def test_every_lattice_dimension(ctx, orc, d):
+    N, M = 5003, 6  # ragged size: not a multiple of the tile, the warp or 4
+    f, U = _problem(N, M, d, d)
+    Q0 = orc.crf_inference(U, [(f, 4.0)], 6)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise(f, 4.0)
+    Q1 = crf.inference(6)
+    assert np.abs(Q0 - Q1).max() <= 1e-4
+    crf.close()
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 12, 13, 21, 24, 32])
+def test_label_counts(ctx, orc, M):
+    N = 4097
+    f, U = _problem(N, M, 3, M)
+    Q0 = orc.crf_inference(U, [(f, 5.0)], 5)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise(f, 5.0)
+    Q1, lab = crf.inference(5, want_labels=True)
+    assert np.abs(Q0 - Q1).max() <= 1e-4
+    assert (Q0.argmax(1) == lab).mean() >= 0.999
+    crf.close()
+
+
+def test_three_and_four_pairwise_terms(ctx, orc):
+    N, M = 6000, 7
+    fs = [_problem(N, M, d, 10 + d)[0] for d in (2, 3, 5, 6)]
+    U = _problem(N, M, 2, 99)[1]
+    for K in (3, 4):
+        kern = [(fs[k], 1.0 + k) for k in range(K)]
+        Q0 = orc.crf_inference(U, kern, 5)
+        crf = ctx.crf(N, M)
+        crf.set_unary(U)
+        for f, w in kern:
+            crf.add_pairwise(f, w)
+        assert np.abs(Q0 - crf.inference(5)).max() <= 1e-4
+        crf.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 33, 255, 257])
+def test_tiny_point_sets(ctx, orc, N):
+    M = 4
+    f, U = _problem(N, M, 3, N)
+    Q0 = orc.crf_inference(U, [(f, 3.0)], 4)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise(f, 3.0)
+    assert np.abs(Q0 - crf.inference(4)).max() <= 1e-4
+    crf.close()
+
+
+def test_image_grid_sizes_fused_path(ctx, orc):
+    """DenseCRF2D on image sizes that are not multiples of the 32-pixel tile (ragged 2-D tiles of the fused path)."""
+    from rovinasemanticsegmentation_b200 import synth
+    for W, H, M in ((70, 45, 5), (33, 17, 9), (100, 3, 2)):
+        rgb, _ = synth.frame(W + H, W, H)
+        U = synth.unary_from_labels((np.arange(W * H) // 97) % M, M, 1)
+        crf = ctx.crf(W * H, M)
+        crf.set_unary(U)
+        crf.add_pairwise_gaussian(W, H, 3, 3, 3.0)
+        crf.add_pairwise_bilateral(W, H, 30, 30, 13, 13, 13, rgb, 10.0)
+        Q1 = crf.inference(5)
+        Q0 = orc.crf_inference(U, [(orc.features_gaussian2d(W, H, 3, 3), 3.0),
+                                   (orc.features_bilateral2d(W, H, 30, 30, 13, 13, 13, rgb), 10.0)], 5)
+        assert np.abs(Q0 - Q1).max() <= 1e-4, (W, H, M)
+        crf.close()
+
+
+def test_error_behaviour(ctx, tmp_path):
+    import rovinasemanticsegmentation_b200 as rss
+    # missing mandatory key -> the reference's KeyNotFoundException message (include/config.h:13-24)
+    cfg = json.load(open(CONFIG))
+    del cfg["patch_size"]
+    p = tmp_path / "bad.json"
+    p.write_text(json.dumps(cfg))
+    with pytest.raises(rss.RssError) as e:
+        rss.Context(str(p), FOREST, 0)
+    assert e.value.status == 3 and "The key: 'patch_size' was not found" in str(e.value)
+    # unreadable files
+    with pytest.raises(rss.RssError) as e:
+        rss.Context(str(tmp_path / "nope.json"), FOREST, 0)
+    assert e.value.status == 2
+    with pytest.raises(rss.RssError) as e:
+        rss.Context(CONFIG, str(tmp_path / "nope.dat"), 0)
+    assert e.value.status == 2
+    # truncated model -> RSS_ERR_MODEL
+    blob = open(FOREST, "rb").read()
+    t = tmp_path / "trunc.dat"
+    t.write_bytes(blob[: len(blob) // 3])
+    with pytest.raises(rss.RssError) as e:
+        rss.Context(CONFIG, str(t), 0)
+    assert e.value.status == 4
+    # no such device
+    with pytest.raises(rss.RssError) as e:
+        rss.Context(CONFIG, FOREST, 9999)
+    assert e.value.status == 1
+    # call order: predict on resident features that do not exist
+    with rss.Context(CONFIG, FOREST, 0) as c2:
+        with pytest.raises(rss.RssError) as e:
+            c2.forest_predict(n=10)
+        assert e.value.status == 7
+    # context without a model refuses to predict
+    with rss.Context(CONFIG, None, 0) as c3:
+        with pytest.raises(rss.RssError) as e:
+            c3.forest_predict(np.zeros((4, 366), np.float32))
+        assert e.value.status == 7
+    # CRF argument checks
+    with pytest.raises(rss.RssError):
+        ctx.crf(100, 40)  # more than 32 labels
+    crf = ctx.crf(100, 3)
+    with pytest.raises(rss.RssError):
+        crf.add_pairwise(np.zeros((100, 9), np.float32), 1.0)  # d > 7
+    crf.close()
