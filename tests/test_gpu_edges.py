@@ -44,6 +44,22 @@ def test_every_lattice_dimension(ctx, orc, d):
     crf.close()
 
 
+def test_int16_key_wraparound(ctx, orc):
+    """Lattice keys are `short` in the reference and silently wrap (permutohedral.cpp:57,270): same partition here."""
+    N, M = 4000, 3
+    f, U = _problem(N, M, 3, 5)
+    f = (f * np.float32(4000.0)).astype(np.float32)  # elevated coordinates far beyond +-32767
+    lat = orc.Lattice(f)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise(f, 2.0)
+    assert crf.lattice_size(0) == lat.V
+    x = np.random.default_rng(1).random((N, M), dtype=np.float32)
+    ref = lat.compute(x)
+    assert np.abs(crf.filter(x) - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    crf.close()
+
+
 @pytest.mark.parametrize("M", [1, 2, 3, 4, 5, 12, 13, 21, 24, 32])
 def test_label_counts(ctx, orc, M):
     N = 4097
