@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     const int hshift = 32 - (31 - __clz(HC));
     const int tile = blockIdx.x;
     const int TP = tm.TP;
+    const TileOrigin org = tile_origin(tm, tile);
     const int npairs = TP * D1;  // slots; points outside the image / beyond N are skipped
     const size_t tb = (size_t)tile * TP * D1;
     if (counts[1]) {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     if (threadIdx.x <= TILE_SEG) hist[threadIdx.x] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < npairs; i += 256) {
-        const int lp = i / D1, p = tile_point(tm, tile, lp);
+        const int lp = i / D1, p = tile_point(tm, org, lp);
         if (p < 0) continue;
         const int key = offsets[(size_t)p * D1 + (i - lp * D1)];
         unsigned h = ((unsigned)key * 2654435761u) >> hshift;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npairs; i += 256) {
-        const int lp = i / D1, p = tile_point(tm, tile, lp);
+        const int lp = i / D1, p = tile_point(tm, org, lp);
         if (p < 0) continue;
         const int pos = atomicAdd(&hcnt[pslot[i]], 1);
         float w = bary[(size_t)p * D1 + (i - lp * D1)];
@@ -257,6 +258,13 @@ __device__ __forceinline__ void slice_lattice(const FusedLat& L, const PointIn<D
     t.x = fmaf(c, acc.x, t.x); t.y = fmaf(c, acc.y, t.y); t.z = fmaf(c, acc.z, t.z); t.w = fmaf(c, acc.w, t.w);
 }
 
+// exp(x) for x <= 0 as one multiply and one ex2.approx.ftz (|rel err| < 2e-6; the CRF tolerance is 1e-4 abs; results
+// below 2^-126 flush to zero, which the normalisation cannot tell from the true value)
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 template <int G>
 __device__ __forceinline__ float group_gather_max(float v, int gbase) {
     float m = v;
@@ -346,6 +354,7 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
     const int sub = lane / G, g = lane - sub * G, gbase = sub * G;
     const bool lane_on = sub < cpw;
     const int tile = blockIdx.x, TP = tm.TP, N = tm.N;
+    const TileOrigin org = tile_origin(tm, tile);
     const bool do_slice = mode & 1, do_splat = mode & 2, store_q = mode & 4;
     const int c0 = 4 * g;
     // entry metadata of this tile's splat (list end, vertex) -> shared memory; consumed after phase 1
@@ -371,14 +380,12 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
     const unsigned lmask = ls.group_lmask[g];
     const unsigned vm = ls.group_valid[g];
     const int my_l = ls.group_layer[g];
-    float peer_bias[G], peer_w[G];
+    // bit i: lane i of my group holds channels of MY layer (a pad-only lane keeps itself as its only peer so that its
+    // discarded result stays finite)
+    unsigned peer_mask = 0;
 #pragma unroll
-    for (int i = 0; i < G; i++) {
-        // a pad-only lane (my_l < 0) keeps itself as its only peer so that its (discarded) result stays finite
-        const bool peer = my_l >= 0 ? ls.group_layer[i] == my_l : i == g;
-        peer_bias[i] = peer ? 0.f : -INFINITY;
-        peer_w[i] = peer ? 1.f : 0.f;
-    }
+    for (int i = 0; i < G; i++)
+        if (my_l >= 0 ? ls.group_layer[i] == my_l : i == g) peer_mask |= 1u << i;
 
     // software pipeline: the streaming inputs (unary, vertex ids, barycentric weights, norms) of step s + 1 are requested
     // before step s gathers its value rows, so one DRAM/L2 round trip is hidden behind the other.  Two input buffers
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
     };
     auto load_step = [&](int s, StepIn& in) {
         const int lp = (s * 8 + wib) * cpw + sub;
-        const int p = lane_on ? tile_point(tm, tile, lp) : -1;
+        const int p = lane_on ? tile_point(tm, org, lp) : -1;
         in.valid = p >= 0;
         in.p = p;
         in.u = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -421,16 +428,22 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
             for (int k = 0; k < 4; k++) mx = fmaxf(mx, (vm >> k) & 1u ? tv[k] : -INFINITY);
             float m = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < G; i++) m = fmaxf(m, __shfl_sync(0xffffffffu, mx, (gbase + i) & 31) + peer_bias[i]);
+            for (int i = 0; i < G; i++) {
+                const float o = __shfl_sync(0xffffffffu, mx, (gbase + i) & 31);
+                m = fmaxf(m, (peer_mask >> i) & 1u ? o : -INFINITY);
+            }
             float e[4], sl = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                e[k] = (vm >> k) & 1u ? __expf(tv[k] - m) : 0.f;  // ex2.approx: |rel err| < 2e-6, the tolerance is 1e-4 abs
+                e[k] = (vm >> k) & 1u ? fast_exp(tv[k] - m) : 0.f;
                 sl += e[k];
             }
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < G; i++) sum = fmaf(__shfl_sync(0xffffffffu, sl, (gbase + i) & 31), peer_w[i], sum);
+            for (int i = 0; i < G; i++) {
+                const float o = __shfl_sync(0xffffffffu, sl, (gbase + i) & 31);
+                sum += (peer_mask >> i) & 1u ? o : 0.f;
+            }
             const float rs = __fdividef(1.0f, sum);
 #pragma unroll
             for (int k = 0; k < 4; k++) qv[k] = e[k] * rs;
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(cons
                 float e[4], sl = 0.f;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    e[k] = (m4 >> k) & 1u ? __expf(tv[k] - m) : 0.f;
+                    e[k] = (m4 >> k) & 1u ? fast_exp(tv[k] - m) : 0.f;
                     sl += e[k];
                 }
                 const float rs = __fdividef(1.0f, group_gather_sum<G>(sl, gbase));

@@ -11,17 +11,37 @@ constexpr int FUSED_MAX_LAT = 2;
 // TW x TH pixel block - neighbouring pixels in BOTH directions share lattice vertices, so a block touches several
 // times fewer distinct vertices than a strip of the same size (fewer splat atomics, better L1 reuse of value rows).
 struct TileMap {
-    int N, TP, W, H, TW, TH, tiles_x, ntiles;
+    int N, TP, W, H, TW, TH, tiles_x, ntiles;  // TW is a power of two
 };
-__host__ __device__ __forceinline__ int tile_point(const TileMap& m, int tile, int lp) {
+// per-CTA constants of the mapping (the divisions happen once per CTA, not once per point)
+struct TileOrigin {
+    int x0, y0;        // first pixel of a 2-D tile
+    long long base;    // first point of a 1-D tile
+    int tw_shift;      // log2(TW)
+};
+__device__ __forceinline__ TileOrigin tile_origin(const TileMap& m, int tile) {
+    TileOrigin o;
+    o.x0 = o.y0 = 0;
+    o.base = 0;
+    o.tw_shift = 0;
+    if (m.W == 0) {
+        o.base = (long long)tile * m.TP;
+    } else {
+        const int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
+        o.x0 = tx * m.TW;
+        o.y0 = ty * m.TH;
+        o.tw_shift = 31 - __clz(m.TW);
+    }
+    return o;
+}
+__device__ __forceinline__ int tile_point(const TileMap& m, const TileOrigin& o, int lp) {
     if (lp >= m.TP) return -1;
     if (m.W == 0) {
-        const long long p = (long long)tile * m.TP + lp;
+        const long long p = o.base + lp;
         return p < m.N ? (int)p : -1;
     }
-    const int ty = tile / m.tiles_x, tx = tile - ty * m.tiles_x;
-    const int ly = lp / m.TW, lx = lp - ly * m.TW;
-    const int x = tx * m.TW + lx, y = ty * m.TH + ly;
+    const int ly = lp >> o.tw_shift, lx = lp & (m.TW - 1);
+    const int x = o.x0 + lx, y = o.y0 + ly;
     return (x < m.W && y < m.H) ? y * m.W + x : -1;
 }
 
