@@ -255,7 +255,8 @@ def run_gpu(args, rank, world, local_rank):
     outs = [torch.empty((2, H * W), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(NC)]
     prm = rss.KeyframeParams(KF["sigma_xyz"], KF["w_gauss"], KF["sigma_px"], KF["sigma_rgb"], KF["w_bilateral"],
                              KF["iters"], KF["fill"])
-    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=dev) for _ in range(NC)]  # each > 126 MB L2
+    FLUSH_MIB = 160  # > the 126 MB L2 of a B200
+    flushes = [torch.empty(FLUSH_MIB << 20, dtype=torch.uint8, device=dev) for _ in range(NC)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NC)]
 
     def call(c, rgb, depth, labels):
@@ -306,7 +307,7 @@ def run_gpu(args, rank, world, local_rank):
     lat_ms_prof, _, prof = latency_pass(True)
 
     # ---- (3) throughput: K steps shared by the NC contexts (keyframes are independent units; the reference runs one
-    # worker per stage, here one worker per context).  Every step is preceded by a 256 MiB write on the worker's side
+    # worker per stage, here one worker per context).  Every step is preceded by a 160 MiB write on the worker's side
     # stream (L2 flush).  resident: the context's frame is already in HBM; e2e: pinned host rgb/depth in, labels out.
     def throughput_pass(host_io, steps=None):
         steps = args.steps if steps is None else steps
@@ -394,7 +395,7 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "every step is preceded by a 256 MiB device write (L2 flush)",
+            "config": {"workload": WORKLOAD, "l2": "every step is preceded by a %d MiB device write (L2 flush; L2 = 126 MB)" % FLUSH_MIB,
                        "frames": "%d distinct synthetic frames per rank" % N_FRAMES,
                        "inflight": "%d keyframes in flight per GPU (one context + host thread each)" % NC},
             "clocks": sampler.summary(),

@@ -26,6 +26,11 @@
 #ifndef RSS_TILE_MINB
 #define RSS_TILE_MINB 4  // resident CTAs per SM the point kernel is compiled for (register budget)
 #endif
+#ifndef RSS_TILE_REGS  // explicit register cap instead of the occupancy-derived one
+#define RSS_TILE_BOUNDS __launch_bounds__(256, RSS_TILE_MINB)
+#else
+#define RSS_TILE_BOUNDS __maxnreg__(RSS_TILE_REGS)
+#endif
 #ifndef RSS_TILE_PREFETCH
 #define RSS_TILE_PREFETCH 0  // request the streaming inputs of step s + 1 before step s gathers its rows
 #endif
@@ -341,7 +346,7 @@ __device__ __forceinline__ void gather_entries(const uint2* __restrict__ pr, con
 }
 
 template <int G, int D1A, int D1B>
-__global__ void __launch_bounds__(256, RSS_TILE_MINB) meanfield_tile_kernel(const __grid_constant__ FusedArgs a,
+__global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ FusedArgs a,
                                                              const float* __restrict__ unary, float* __restrict__ Q,
                                                              uint8_t* __restrict__ labels,
                                                              const __grid_constant__ TileMap tm, int steps,
@@ -651,7 +656,10 @@ static int fused_tile_steps(int G, int TP) {  // warp-steps a CTA needs for TP p
 // The point kernel is latency-bound per CTA, so ONE full wave of resident CTAs is the sweet spot: when the default
 // tile size would need slightly more tiles than fit at once (sm_count * RSS_TILE_MINB), the tiles grow (up to
 // TILE_MAX_POINTS) until they fit.
-constexpr int TILE_MAX_POINTS = 576;
+#ifndef RSS_TILE_MAX_POINTS
+#define RSS_TILE_MAX_POINTS 576
+#endif
+constexpr int TILE_MAX_POINTS = RSS_TILE_MAX_POINTS;
 TileMap fused_tile_map(int G, int N, int W, int H, int sm_count) {
     TileMap m;
     m.N = N;
