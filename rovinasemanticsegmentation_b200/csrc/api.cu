@@ -122,11 +122,6 @@ struct Reader {
         p += bytes;
         return true;
     }
-    bool skip(size_t bytes) {
-        if ((size_t)(e - p) < bytes) { ok = false; return false; }
-        p += bytes;
-        return true;
-    }
 };
 }  // namespace
 
@@ -593,7 +588,6 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 // segmenter.cpp:349-434 on the device; leaves posteriors [layer][y][x][class] resident
 rss_status frame_segment(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth, int W, int H, const float* Kinv,
                          const float* R, const float* t, float fill) {
-    FrameState& f = ctx->fr;
     const HostConfig& cfg = ctx->cfg;
     const ForestDev& F = ctx->forest;
     if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");

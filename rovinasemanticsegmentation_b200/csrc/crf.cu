@@ -11,7 +11,6 @@
 #include <cmath>
 #include <cstring>
 
-#include <cstdlib>
 
 #include "kernels.hpp"
 #include "lattice.cuh"

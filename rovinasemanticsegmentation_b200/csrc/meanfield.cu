@@ -1,23 +1,22 @@
-// Fused mean-field iteration for point sets whose order is spatially coherent (image raster order, the keyframe
-// path): ONE point-parallel kernel per iteration does slice (of the previous iteration's blurred tables) + Potts +
-// unary + per-layer soft-max + the SPLAT of the new marginals for the next iteration, plus one cooperative launch
-// that blurs every lattice of the CRF along all of its axes.  Reference: third-party/densecrf/src/densecrf.cpp:98-131
-// (expAndNormalize, inference), pairwise.cpp:63-80 (DenseKernel::filter), permutohedral.cpp:529-589 (sseCompute).
+// Fused mean-field iteration for point sets whose order is spatially coherent (image raster order: the keyframe path,
+// DenseCRF2D; any point set whose consecutive points share lattice vertices).  Per iteration there are two launches:
+//   meanfield_tile_kernel   slice of the previous iteration's blurred value tables + Potts + unary + per-layer soft-max
+//                           (+ gated argmax / Q store on the last pass) AND the splat of the new marginals;
+//   blur_multi_coop_kernel  every axis of every lattice of the CRF, one cooperative launch with grid barriers.
+// Reference: third-party/densecrf/src/densecrf.cpp:98-131 (expAndNormalize, inference), pairwise.cpp:63-80
+// (DenseKernel::filter), labelcompatibility.cpp:46-48 (Potts), permutohedral.cpp:529-589 (sseCompute).
 //
-// Work decomposition of the point kernel: a thread is (chunk, channel group).  A chunk is a run of Pc CONSECUTIVE
-// points that the thread walks serially; the G = Mp/4 lanes of a chunk hold the point's label vector as one float4
-// each, so a value-table row (Mp floats) is read by G adjacent lanes as one contiguous 16*G-byte access.
-//   slice:    t -= -w * norm_i * sum_j (bary_ij * alpha) * blurred[vertex_ij]        (row gathers hit L1/L2)
-//   soft-max: per label layer across the G lanes (fixed-order all-gather through shuffles)
-//   splat:    per simplex corner j the thread keeps (current vertex, float4 accumulator); while consecutive points
-//             stay on the same vertex it only accumulates in registers, when the vertex changes it flushes ONE
-//             red.global.add.v4.f32.  Neighbouring pixels share lattice vertices (remainder-j corner of adjacent
-//             simplices is the same lattice point), so the atomic traffic is (number of runs), not (number of
-//             nonzeros), and no CSR of the splat matrix, no re-read of Q and no separate splat launch are needed.
+// A tile (one CTA of the point kernel) is a block of ~512 points: a 32 x TH pixel block for image CRFs, else a run of
+// consecutive points.  Phase 1 keeps the tile's marginals in shared memory; phase 2 gathers them per (lattice vertex
+// touched by the tile) through a tile-local CSR built once per lattice (tile_csr_build_kernel) and issues one
+// red.global.add.v4.f32 per (segment of <= 32 pairs, channel group).  So Q is never re-read from L2, there is no
+// separate splat launch, and the number of global atomics is (distinct vertices per tile), not (nonzeros) - which is
+// what makes noisy images cheap: +-8 colour noise sends 64 % of consecutive pixels to a different bilateral vertex.
 // Value tables rotate through three buffers per lattice: `res` (blurred result being sliced), `tgt` (all zero, receives
-// the splat) and `spare`; the blur ping-pongs between tgt and spare and zeroes the old `res`, which becomes the next tgt.
+// the splat) and `spare`; the blur ping-pongs between tgt and spare and clears the old `res`, the next tgt.
+//
+// Compile-time tuning knobs (build.py: RSS_NVCC_DEFS="-DNAME=value"), defaults measured on B200:
 #include <algorithm>
-#include <cstdlib>
 
 #include "kernels.hpp"
 #include "lattice.cuh"
@@ -30,9 +29,6 @@
 #define RSS_TILE_BOUNDS __launch_bounds__(256, RSS_TILE_MINB)
 #else
 #define RSS_TILE_BOUNDS __maxnreg__(RSS_TILE_REGS)
-#endif
-#ifndef RSS_TILE_PREFETCH
-#define RSS_TILE_PREFETCH 0  // request the streaming inputs of step s + 1 before step s gathers its rows
 #endif
 #ifndef RSS_BLUR_U
 #define RSS_BLUR_U 2      // independent (vertex, channel group) items a blur thread keeps in flight
@@ -107,7 +103,6 @@ constexpr int TILE_MAX_PAIRS = 4096;
 #endif
 constexpr int TILE_SEG = RSS_TILE_SEG;  // pairs per splat segment (one thread walks one segment serially)
 constexpr int TILE_CHUNK = 8;           // pairs requested at once by the gather
-constexpr int TILE_SMEM_BYTES = 2 * TILE_HASH * 4 + TILE_MAX_PAIRS * 2;
 
 __device__ __forceinline__ int2 block_excl_scan2(int a, int b, int2* total) {  // 256 threads
     __shared__ int2 wsum[8];
@@ -392,9 +387,7 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
     for (int i = 0; i < G; i++)
         if (my_l >= 0 ? ls.group_layer[i] == my_l : i == g) peer_mask |= 1u << i;
 
-    // software pipeline: the streaming inputs (unary, vertex ids, barycentric weights, norms) of step s + 1 are requested
-    // before step s gathers its value rows, so one DRAM/L2 round trip is hidden behind the other.  Two input buffers
-    // alternate (the loop is unrolled by two), so no register copies are needed.
+    // one warp-step = 32 / G points per warp: load the streaming inputs, then gather / soft-max / store
     struct StepIn {
         float4 u;
         PointIn<D1A> A;
@@ -499,24 +492,13 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
             }
         }
     };
-#if RSS_TILE_PREFETCH
-    StepIn in0, in1;
-    load_step(0, in0);
-    for (int s = 0; s < steps; s += 2) {
-        if (s + 1 < steps) load_step(s + 1, in1);
-        run_step(s, in0);
-        if (s + 1 < steps) {
-            if (s + 2 < steps) load_step(s + 2, in0);
-            run_step(s + 1, in1);
-        }
-    }
-#else
-    for (int s = 0; s < steps; s++) {  // no register prefetch: fewer registers, more resident warps hide the latency
+    // (a register double-buffer that requests step s + 1 before step s gathers its rows was measured slower: it costs
+    // half of the resident warps, and phase 1 is issue-bound, not latency-bound)
+    for (int s = 0; s < steps; s++) {
         StepIn in0;
         load_step(s, in0);
         run_step(s, in0);
     }
-#endif
     if (!do_splat) return;
     __syncthreads();
     // phase 2: tile-local gather splat out of shared memory
@@ -763,13 +745,9 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
 #undef RSS_TCB
 }
 
-int blur_multi_grid(const rss_ctx* c) {
-    static const char* e = getenv("RSS_BLUR_GRID");
-    return e && atoi(e) > 0 ? atoi(e) : c->sm_count;
-}
+int blur_multi_grid(const rss_ctx* c) { return c->sm_count; }  // one CTA per SM
 void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
-    static const char* eb_ = getenv("RSS_BLUR_BLOCK");
-    const int grid = blur_multi_grid(c), block = std::min(RSS_BLUR_MAXT, eb_ && atoi(eb_) > 0 ? atoi(eb_) : 128);
+    const int grid = blur_multi_grid(c), block = RSS_BLUR_MAXT;
     void* args[] = {&a, &G, &barrier, &barrier_base};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }
