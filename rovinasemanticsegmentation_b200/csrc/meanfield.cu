@@ -96,8 +96,6 @@ __device__ __forceinline__ void red_add_v4(float* dst, const float4 v) {
 // kernel is pre-normalised (DenseKernel::filter, pairwise.cpp:65-66), so the gather needs no norm lookup.
 // Entry meta: x = (start of the segment in the tile's pair array) | (length << 16), y = vertex id.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TILE_HASH = 8192;      // largest shared-memory hash: >= 2 * max pairs per tile (512 points * 8 corners)
-constexpr int TILE_MAX_PAIRS = 4096;
 #ifndef RSS_TILE_SEG
 #define RSS_TILE_SEG 32
 #endif
