@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -138,8 +139,7 @@ struct rss_ctx {
     rss::PinBuf pin_in, pin_out, pin_small;
     rss_timings tim = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
-    unsigned fused_attr_mask = 0;  // meanfield_tile_kernel instances whose dynamic shared memory limit was raised
-    unsigned tile_attr_mask = 0;  // tile_csr_build_kernel<D> instances whose dynamic shared memory limit was raised
+    std::set<const void*> smem_attr_done;  // kernels whose dynamic shared memory limit was raised on this device
     std::string err;
     rss_crf* keyframe_crf = nullptr;  // cached CRF of rss_segment_keyframe
     // optional per-kernel timing (rss_profile_enable)

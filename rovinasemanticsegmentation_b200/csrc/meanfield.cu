@@ -37,11 +37,17 @@
 #define RSS_BLUR_MAXT 128  // CTA size of the cooperative blur: small register / thread footprint on purpose, so that
                            // kernels of OTHER keyframes in flight run on the SMs while its CTAs wait at the grid barriers
 #endif
+#ifndef RSS_TILE_SMEM_PAIRS
+#define RSS_TILE_SMEM_PAIRS 1  // stage the tile's splat pair lists in shared memory (cp.async during phase 1)
+#endif
+#ifndef RSS_TILE_SINGLE_WAVE
+#define RSS_TILE_SINGLE_WAVE 0  // grow the tiles until all CTAs of the point kernel are resident at once
+#endif
 #ifndef RSS_TILE_IU
 #define RSS_TILE_IU 1  // splat segments a thread walks at once
 #endif
 #ifndef RSS_TILE_POINTS
-#define RSS_TILE_POINTS 512  // target points per tile (<= 512: the tile CSR build kernel's hash capacity)
+#define RSS_TILE_POINTS 288  // target points per tile (<= 512: the tile CSR build kernel's hash capacity)
 #endif
 
 namespace rss {
@@ -283,7 +289,7 @@ __device__ __forceinline__ float group_gather_sum(float v, int gbase) {  // same
 // Every thread walks IU segments at once (independent load streams); segments are sorted by length, so the lanes of
 // a warp finish together.
 template <int G, int IU>
-__device__ __forceinline__ void gather_entries(const uint2* __restrict__ pr, const int2* meta, int cap,
+__device__ __forceinline__ void gather_entries(const uint2* pr, const int2* meta, int cap,
                                                const int2* __restrict__ meta_g, int ne, float* __restrict__ vout,
                                                const float4* qtile) {
     constexpr int Mp = 4 * G;
@@ -318,7 +324,7 @@ __device__ __forceinline__ void gather_entries(const uint2* __restrict__ pr, con
             for (int u = 0; u < IU; u++)
 #pragma unroll
                 for (int i = 0; i < TILE_CHUNK; i++)
-                    if (c0 + i < len[u]) pw[u][i] = __ldg(pp[u] + c0 + i);
+                    if (c0 + i < len[u]) pw[u][i] = pp[u][c0 + i];
 #pragma unroll
             for (int i = 0; i < TILE_CHUNK; i++) {
 #pragma unroll
@@ -373,6 +379,21 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
             for (int e = threadIdx.x; e < capB; e += 256) metaB[e] = __ldg(a.ent_meta[1] + tbB + e);
         }
     }
+#if RSS_TILE_SMEM_PAIRS
+    // the tile's pair lists -> shared memory with cp.async: the copy runs during phase 1 and phase 2 never waits for L2
+    uint2* spairsA = reinterpret_cast<uint2*>(metaA + 2 * TP);
+    uint2* spairsB = spairsA + TP * D1A;
+    if (do_splat) {
+        auto stage = [&](uint2* dst, const uint2* src, int n) {  // n pairs, 16 bytes (two pairs) per copy
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(dst);
+            for (int o = threadIdx.x * 2; o < n; o += 512)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + o * 8), "l"(src + o) : "memory");
+        };
+        stage(spairsA, a.pairs[0] + (size_t)tile * TP * D1A, TP * D1A);
+        if constexpr (D1B > 0) stage(spairsB, a.pairs[1] + (size_t)tile * TP * D1B, TP * D1B);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#endif
     // per channel group (host-precomputed, FusedLayers): which of my four channels belong to which layer (one nibble per
     // layer), and for aligned layers my layer, my valid channels and which lanes of the group share the layer
     const unsigned lmask = ls.group_lmask[g];
@@ -498,15 +519,26 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
         run_step(s, in0);
     }
     if (!do_splat) return;
+#if RSS_TILE_SMEM_PAIRS
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     __syncthreads();
     // phase 2: tile-local gather splat out of shared memory
     {
         const size_t tbA = (size_t)tile * TP * D1A;
+#if RSS_TILE_SMEM_PAIRS
+        gather_entries<G, RSS_TILE_IU>(spairsA, metaA, capA, a.ent_meta[0] + tbA, neA, a.lat[0].vout, qtile);
+#else
         gather_entries<G, RSS_TILE_IU>(a.pairs[0] + tbA, metaA, capA, a.ent_meta[0] + tbA, neA, a.lat[0].vout, qtile);
+#endif
     }
     if constexpr (D1B > 0) {
         const size_t tbB = (size_t)tile * TP * D1B;
+#if RSS_TILE_SMEM_PAIRS
+        gather_entries<G, RSS_TILE_IU>(spairsB, metaB, capB, a.ent_meta[1] + tbB, neB, a.lat[1].vout, qtile);
+#else
         gather_entries<G, RSS_TILE_IU>(a.pairs[1] + tbB, metaB, capB, a.ent_meta[1] + tbB, neB, a.lat[1].vout, qtile);
+#endif
     }
 }
 
@@ -647,7 +679,7 @@ TileMap fused_tile_map(int G, int N, int W, int H, int sm_count) {
     if (W > 0 && H > 0 && (long long)W * H == N) {
         m.W = W; m.H = H; m.TW = 32; m.TH = RSS_TILE_POINTS / 32;
         m.tiles_x = (W + m.TW - 1) / m.TW;
-        if (m.tiles_x <= slots) {
+        if (RSS_TILE_SINGLE_WAVE && m.tiles_x <= slots) {
             const int rows_fit = slots / m.tiles_x;                 // tile rows of one wave
             const int th = (H + rows_fit - 1) / rows_fit;           // tile height that makes the image fit in one wave
             if (th > m.TH && th * m.TW <= TILE_MAX_POINTS) m.TH = th;
@@ -660,7 +692,7 @@ TileMap fused_tile_map(int G, int N, int W, int H, int sm_count) {
         m.TP = per_step * std::max(1, (RSS_TILE_POINTS + per_step / 2) / per_step);
         const long long fit = ((long long)N + slots - 1) / slots;  // points per tile for one wave
         const int tp_fit = (int)((fit + per_step - 1) / per_step) * per_step;
-        if (tp_fit > m.TP && tp_fit <= TILE_MAX_POINTS) m.TP = tp_fit;
+        if (RSS_TILE_SINGLE_WAVE && tp_fit > m.TP && tp_fit <= TILE_MAX_POINTS) m.TP = tp_fit;
         m.ntiles = (int)(((long long)N + m.TP - 1) / m.TP);
     }
     return m;
@@ -683,12 +715,11 @@ static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d
 #define RSS_TILE(A, B)                                                                                                  \
     do {                                                                                                                \
         auto kfn = meanfield_tile_kernel<G, A, B>;                                                                      \
-        const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2);                                \
-        const unsigned bit__ = 1u << (G * 4 + (B ? 1 : 0) + (A > 4 ? 2 : 0));                                          \
-        if (!(c->fused_attr_mask & bit__)) { /* once per context (= per device): shared memory limit and carveout */    \
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+        const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2) +        \
+                            (RSS_TILE_SMEM_PAIRS ? (size_t)TP * (A + B) * sizeof(uint2) : 0);                                            \
+        if (c->smem_attr_done.insert((const void*)kfn).second) { /* once per context (= per device) and instantiation */ \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                        \
             cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
-            c->fused_attr_mask |= bit__;                                                                                \
         }                                                                                                               \
         RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, tm, steps, ls, mode); \
     } while (0)
@@ -724,10 +755,8 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
     const size_t tsm = (size_t)2 * HC * 4 + (size_t)TP * d1 * 2;
 #define RSS_TCB(D)                                                                                                      \
     do {                                                                                                                \
-        if (!(c->tile_attr_mask & (1u << D))) {  /* once per context (= per device) */                                  \
-            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   \
-            c->tile_attr_mask |= 1u << D;                                                                               \
-        }                                                                                                               \
+        if (c->smem_attr_done.insert((const void*)tile_csr_build_kernel<D>).second)  /* once per context (= per device) */ \
+            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);     \
         RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, tsm, st, offsets, bary, norm, tm, row_bytes, HC, counts, pairs,    \
                    ent_meta, tile_nent);                                                                                \
     } while (0)

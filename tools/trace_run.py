@@ -9,7 +9,9 @@ prm = rss.KeyframeParams(0.05, 3.0, 80.0, 13.0, 10.0, 10, 0.0)
 for k in range(4): ctx.segment_keyframe(rgb, depth, Kinv, R, t, prm)
 buf = (C.c_ulonglong * 128)()
 ctx._lib.rss_debug_trace(buf)
-a = np.array(buf[:], dtype=np.int64).reshape(4, 32)
-for b in (0, 1):
-    tr = a[b]; t0 = tr[0]
-    print("blur block", b, " ".join("%d:%.1f" % (i, (tr[i] - t0) / 1000.0) for i in range(14) if tr[i] > 0))
+a = np.array(buf[:], dtype=np.int64).reshape(4, 2, 16)
+names = ["start", "setup", "phase1", "sync", "splatA", "splatB"]
+for mode in (2, 3, 1):
+    for b in (0, 1):
+        tr = a[mode, b]; t0 = tr[0]
+        print("mode", mode, "block", "0" if b == 0 else "900", " ".join("%s:%.1f" % (names[i], (tr[i] - t0) / 1000.0) for i in range(6) if tr[i] > 0))
