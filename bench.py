@@ -186,9 +186,12 @@ def algo_bytes(name, env):
         "scalar_features_kernel": 8 * Ns + 2 * Ns + 12 * Ns + 12 * Ns,
         # R1, R2 (classifier.cpp, segmenter.cpp:355-431)
         "forest_traverse_kernel": 4 * D * Ns + 16 * env["nodes"] + 4 * T * Ns,
+        # frame path: features evaluated on demand - the Lab image, the depth image and the cloud in, leaf ids out
+        "forest_traverse_frame_kernel": 3 * Wb * Hb + 2 * N + 16 * N + 8 * Ns + 16 * env["nodes"] + 4 * T * Ns,
         "forest_posterior_kernel": 4 * T * Ns + 4 * M * env["leaves"] + 4 * M * Ns,
         "fill_kernel": 4 * M * (N // 4), "lowres_scatter_kernel": 8 * M * Ns + 8 * Ns,
-        "upsample_kernel": 4 * M * (N // 4) + 4 * M * N,
+        "upsample_kernel": 4 * M * (N // 4) + 4 * M * N, "upsample_kernel<true>": 4 * M * (N // 4) + 4 * M * N,
+        "upsample_kernel<false>": 4 * M * (N // 4) + 4 * M * N,
         "unary_from_posteriors_kernel": 8 * M * N,
         # C0 lattice construction (permutohedral.cpp:140-321)
         "lattice_embed_kernel<D>": mean(lambda d, V: 4 * d * N + 8 * (d + 1) * N + 2 * d * V),

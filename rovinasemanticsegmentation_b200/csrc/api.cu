@@ -273,6 +273,11 @@ static rss_status upload_tables(rss_ctx* ctx) {
             ty[(size_t)h * r + d] = b;
         }
     }
+    // patch pixel k -> (dx, dy) for the on-demand feature evaluation of the frame path
+    std::vector<uint16_t> fxy((size_t)r * r);
+    for (int k = 0; k < r * r; k++) fxy[k] = (uint16_t)((k % r) | ((k / r) << 8));
+    RSS_CU(ctx, ctx->feat_xy.reserve(fxy.size() * sizeof(uint16_t)));
+    RSS_CU(ctx, cudaMemcpy(ctx->feat_xy.ptr, fxy.data(), fxy.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     RSS_CU(ctx, ctx->tapx.reserve(tx.size() * sizeof(ResizeTap)));
     RSS_CU(ctx, ctx->tapy.reserve(ty.size() * sizeof(ResizeTap)));
     RSS_CU(ctx, cudaMemcpy(ctx->tapx.ptr, tx.data(), tx.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
@@ -289,7 +294,7 @@ static void free_ctx(rss_ctx* ctx) {
                       &f.normals, &f.grad, &f.fin, &f.flags, &f.sidx, &f.scan_tmp, &f.xs, &f.ys, &f.slabels,
                       &f.n_dev, &f.feats, &f.leaf_ids, &f.post, &f.lowres, &f.posteriors, &ctx->forest.nodes,
                       &ctx->forest.tree_off_dev, &ctx->forest.leaves, &ctx->lab_gamma, &ctx->lab_cbrt, &ctx->tapx,
-                      &ctx->tapy};
+                      &ctx->tapy, &ctx->feat_xy};
     for (DevBuf* b : bufs) b->release();
     ctx->pin_in.release();
     ctx->pin_out.release();
@@ -516,8 +521,9 @@ rss_status frame_prepare(rss_ctx* ctx, const float* Kinv, const float* R, const 
 }
 
 // sample selection + compaction + materialised features for the compacted list
+// materialize = false (frame path): only the sample list; the forest evaluates features on demand
 rss_status frame_extract(rss_ctx* ctx, int stride, float dmin, float dmax, int extract_type, const int8_t* labels_dev,
-                         int n_label_layers) {
+                         int n_label_layers, bool materialize = true) {
     FrameState& f = ctx->fr;
     const HostConfig& cfg = ctx->cfg;
     const int W = f.W, H = f.H, D = cfg.feature_length();
@@ -530,7 +536,7 @@ rss_status frame_extract(rss_ctx* ctx, int stride, float dmin, float dmax, int e
     RSS_CU(ctx, f.n_dev.reserve(16));
     RSS_CU(ctx, f.xs.reserve(cap * 4));
     RSS_CU(ctx, f.ys.reserve(cap * 4));
-    RSS_CU(ctx, f.feats.reserve(cap * D * sizeof(float)));
+    if (materialize) RSS_CU(ctx, f.feats.reserve(cap * D * sizeof(float)));
     RSS_CU(ctx, ctx->pin_small.reserve(64));
     if (n_label_layers > 0) RSS_CU(ctx, f.slabels.reserve(cap * n_label_layers * 4));
     const float dmin_mm = (float)(dmin * 1000.0), dmax_mm = (float)(dmax * 1000.0);  // feature_extractor.h:43-44
@@ -544,6 +550,8 @@ rss_status frame_extract(rss_ctx* ctx, int stride, float dmin, float dmax, int e
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     const int n = (int)*ctx->pin_small.as<uint32_t>();
     f.n_samples = n;
+    f.have_feats = false;
+    if (!materialize) return RSS_OK;
     int pos = 0, pos_depth = -1, pos_height = -1, pos_normal = -1;
     if (cfg.use_color) {
         launch_patch_features(ctx, ctx->s0, f.lab.as<uchar4>(), f.depth.as<uint16_t>(), W, H, cfg.patch_size,
@@ -560,6 +568,31 @@ rss_status frame_extract(rss_ctx* ctx, int stride, float dmin, float dmax, int e
                                f.feats.as<float>(), D, pos_depth, pos_height, pos_normal);
     RSS_CU(ctx, cudaGetLastError());
     f.have_feats = true;
+    return RSS_OK;
+}
+
+// forest straight from the frame: features evaluated on demand (features.cu), then the summed leaf rows
+rss_status frame_predict_from_frame(rss_ctx* ctx, int n) {
+    FrameState& f = ctx->fr;
+    const ForestDev& F = ctx->forest;
+    const HostConfig& cfg = ctx->cfg;
+    if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
+    RSS_CU(ctx, f.leaf_ids.reserve((size_t)F.T * (n > 0 ? n : 1) * 4));
+    RSS_CU(ctx, f.post.reserve((size_t)(n > 0 ? n : 1) * F.sumC * 4));
+    int pos = 0, pos_depth = -1, pos_height = -1, pos_normal = -1;
+    const int ncolor = cfg.use_color ? 3 * cfg.patch_size_reduce * cfg.patch_size_reduce : 0;
+    pos = ncolor;
+    if (cfg.use_depth) pos_depth = pos++;
+    if (cfg.use_height) pos_height = pos++;
+    if (cfg.use_normal) pos_normal = pos++;
+    launch_forest_traverse_frame(ctx, ctx->s0, F.nodes.as<Node>(), F.tree_off_dev.as<int>(), F.T, f.lab.as<uchar4>(),
+                                 f.depth.as<uint16_t>(), f.xyz.as<float4>(), f.dist_b.as<float>(), f.integ.as<double>(),
+                                 f.integ_cnt.as<int>(), ctx->tapx.as<ResizeTap>(), ctx->tapy.as<ResizeTap>(),
+                                 ctx->feat_xy.as<uint16_t>(), f.W, f.H, cfg.patch_size, cfg.patch_size_reduce, ncolor,
+                                 pos_depth, pos_height, pos_normal, f.xs.as<int>(), f.ys.as<int>(), n, n, f.leaf_ids.as<int>());
+    launch_forest_posterior(ctx, ctx->s0, F.nodes.as<Node>(), F.tree_off_dev.as<int>(), F.T, F.leaves.as<float>(),
+                            F.sumC, f.leaf_ids.as<int>(), n, n, f.post.as<float>());
+    RSS_CU(ctx, cudaGetLastError());
     return RSS_OK;
 }
 
@@ -623,11 +656,11 @@ rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out, int 
     const HostConfig& cfg = ctx->cfg;
     const ForestDev& F = ctx->forest;
     const int stride = cfg.rf_stride, W = f.W, H = f.H;
-    rss_status st = frame_extract(ctx, stride, cfg.depth_min, cfg.depth_max, RSS_NO_LABEL, nullptr, 0);
+    rss_status st = frame_extract(ctx, stride, cfg.depth_min, cfg.depth_max, RSS_NO_LABEL, nullptr, 0, false);
     if (st != RSS_OK) return st;
     cudaEventRecord(ctx->ev[2], ctx->s0);
     const int n = f.n_samples;
-    st = frame_predict(ctx, f.feats.as<float>(), n);
+    st = frame_predict_from_frame(ctx, n);
     if (st != RSS_OK) return st;
     cudaEventRecord(ctx->ev[3], ctx->s0);
     const size_t low_elems = (size_t)f.gw * f.gh * F.sumC;

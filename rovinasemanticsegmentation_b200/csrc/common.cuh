@@ -136,6 +136,7 @@ struct rss_ctx {
     rss::FrameState fr;
     rss::DevBuf lab_gamma, lab_cbrt;  // u16 LUTs of cvtColor(BGR2Lab)
     rss::DevBuf tapx, tapy;           // ResizeTap[(P+1)][r]
+    rss::DevBuf feat_xy;              // u16[r*r]: patch pixel k -> dx | dy << 8
     rss::PinBuf pin_in, pin_out, pin_small;
     rss_timings tim = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;

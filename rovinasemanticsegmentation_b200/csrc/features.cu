@@ -217,6 +217,85 @@ __global__ void __launch_bounds__(256) scalar_features_kernel(const uint16_t* __
         f[pos_normal] = isnan(nrm.x) ? -2.0f : (float)acos(fabs((double)nrm.z));
     }
 }
+// ------------------------------------------------------------------------------------------------
+// Forest traversal straight from the frame (segment_frame / keyframe path): DecisionTree::findLeafNode
+// (classifier.cpp:97-117) where x[f] is EVALUATED ON DEMAND from the Lab image, the depth image, the cloud and the
+// integral images instead of being read from a materialised [n][366] matrix.  A tree touches at most 31 of the 366
+// features of a sample, so this skips ~90 % of the resize arithmetic and the 112 MB feature matrix never exists
+// ("~6 MB if fused with F2").  The value of a feature is computed by exactly the same integer / float
+// operations as patch_features_kernel and scalar_features_kernel, so leaf ids stay bit-exact.
+// One thread per (sample, tree); feat_xy[k] = dx | dy << 8 of patch pixel k.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Node load_node_ro(const Node* p) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    Node n;
+    n.feat = v.x; n.thr = __int_as_float(v.y); n.left = v.z; n.leaf = v.w;
+    return n;
+}
+__global__ void __launch_bounds__(256) forest_traverse_frame_kernel(
+    const Node* __restrict__ nodes, const int* __restrict__ tree_off, int T, const uchar4* __restrict__ lab,
+    const uint16_t* __restrict__ depth, const float4* __restrict__ xyz, const float* __restrict__ dist,
+    const double* __restrict__ integ, const int* __restrict__ cnt, const ResizeTap* __restrict__ tapx,
+    const ResizeTap* __restrict__ tapy, const uint16_t* __restrict__ feat_xy, int W, int H, int P, int r, int ncolor,
+    int pos_depth, int pos_height, int pos_normal, const int* __restrict__ xs, const int* __restrict__ ys, int n, int ld,
+    int* __restrict__ leaf_ids) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * T) return;
+    const int s = (int)(gid / T), t = (int)(gid - (long long)s * T);
+    const Node* tree = nodes + tree_off[t];
+    const int x = xs[s], y = ys[s];
+    const size_t i = (size_t)y * W + x;
+    const int Wb = W + 2 * P;
+    const float dm = __fdiv_rn((float)depth[i], 1000.0f);
+    const int half = patch_half(P, dm);
+    const uchar4* roi = lab + (size_t)(y + P - half) * Wb + (x + P - half);
+    const ResizeTap* tx_h = tapx + half * r;
+    const ResizeTap* ty_h = tapy + half * r;
+    bool have_normal = false;
+    float normal_feature = 0.f;
+    int node = 0;
+    Node nd = load_node_ro(tree);
+    while (nd.left != 0) {
+        float v;
+        const int f = nd.feat;
+        if (f < ncolor) {
+            const int k = f / 3, ch = f - 3 * k;
+            const int xy = __ldg(feat_xy + k);
+            const ResizeTap tx = tx_h[xy & 255], ty = ty_h[xy >> 8];
+            const uchar4 p00 = __ldg(roi + (size_t)ty.i0 * Wb + tx.i0), p01 = __ldg(roi + (size_t)ty.i0 * Wb + tx.i1);
+            const uchar4 p10 = __ldg(roi + (size_t)ty.i1 * Wb + tx.i0), p11 = __ldg(roi + (size_t)ty.i1 * Wb + tx.i1);
+            const int a = ch == 0 ? p00.x : (ch == 1 ? p00.y : p00.z), b = ch == 0 ? p01.x : (ch == 1 ? p01.y : p01.z);
+            const int c = ch == 0 ? p10.x : (ch == 1 ? p10.y : p10.z), d = ch == 0 ? p11.x : (ch == 1 ? p11.y : p11.z);
+            v = (float)sat_u8(resize_blend(a, b, c, d, tx.w0, tx.w1, ty.w0, ty.w1));
+        } else if (f == pos_depth) {
+            v = dm;
+        } else if (f == pos_height) {
+            v = xyz[i].z;
+        } else {
+            if (!have_normal) {
+                const float3 nrm = pcl_normal_at(xyz, dist, integ, cnt, W, H, x, y);
+                normal_feature = isnan(nrm.x) ? -2.0f : (float)acos(fabs((double)nrm.z));
+                have_normal = true;
+            }
+            v = normal_feature;
+        }
+        node = v < nd.thr ? nd.left : nd.left + 1;
+        nd = load_node_ro(tree + node);
+    }
+    leaf_ids[(size_t)t * ld + s] = node;
+}
+void launch_forest_traverse_frame(rss_ctx* c, cudaStream_t st, const Node* nodes, const int* tree_off, int T,
+                                  const uchar4* lab, const uint16_t* depth, const float4* xyz, const float* dist,
+                                  const double* integ, const int* cnt, const ResizeTap* tapx, const ResizeTap* tapy,
+                                  const uint16_t* feat_xy, int W, int H, int P, int r, int ncolor, int pos_depth,
+                                  int pos_height, int pos_normal, const int* xs, const int* ys, int n, int ld,
+                                  int* leaf_ids) {
+    if (n <= 0) return;
+    RSS_LAUNCH(c, forest_traverse_frame_kernel, rss_div_up((long long)n * T, 256), 256, 0, st, nodes, tree_off, T, lab,
+               depth, xyz, dist, integ, cnt, tapx, tapy, feat_xy, W, H, P, r, ncolor, pos_depth, pos_height, pos_normal, xs,
+               ys, n, ld, leaf_ids);
+}
+
 void launch_scalar_features(rss_ctx* c, cudaStream_t st, const uint16_t* depth, const float4* xyz,
                             const float* dist, const double* integ, const int* integ_cnt, int W, int H,
                             const int* xs, const int* ys, int n, float* feats, int D, int pos_depth,

@@ -128,6 +128,8 @@ void launch_lowres_scatter(rss_ctx* c, cudaStream_t st, const float* post, int s
 // the index is clamped, vertically the two row indices are clipped and the fraction kept; horizontal pass
 // first (S0*a0 + S1*a1), then vertical (H0*b0 + H1*b1), each product and sum rounded to float.
 // ------------------------------------------------------------------------------------------------
+// One thread per OUTPUT PIXEL: the source coordinates, weights and row pointers are computed once and reused for all
+// classes of all layers (a thread per output element would redo the double-precision coordinate arithmetic sumC times).
 // UNARY = false: out is the flattened [layer][y][x][class] vector.  UNARY = true (keyframe path): the value is negated
 // (energy = -log-posterior, src/segmenter.cpp:642) and written straight into the CRF's [pixel][Mp] unary layout, which
 // saves the separate posterior -> unary pass; -x is exact, so the energies are bit-identical to the two-pass route.
@@ -135,29 +137,9 @@ template <bool UNARY>
 __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ lowres, int gw, int gh, int W,
                                                        int H, LayerDims ld, int sumC, int Mp, double scale_x,
                                                        double scale_y, float* __restrict__ out) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)W * H * sumC;
-    if (gid >= total) return;
-    int l = 0, cl;
-    long long px;
-    if (UNARY) {  // gid enumerates [pixel][class over all layers]
-        px = gid / sumC;
-        const int c = (int)(gid - px * sumC);
-        while (l + 1 < ld.L && c >= ld.coff[l + 1]) l++;
-        cl = c - ld.coff[l];
-    } else {      // gid enumerates the flattened output: layer-major
-        long long rem = gid;
-        while (l + 1 < ld.L && rem >= (long long)W * H * ld.C[l]) {
-            rem -= (long long)W * H * ld.C[l];
-            l++;
-        }
-        cl = (int)(rem % ld.C[l]);
-        px = rem / ld.C[l];
-    }
-    const int C = ld.C[l];
-    const int x = (int)(px % W), y = (int)(px / W);
-    const float* src = lowres + (size_t)gw * gh * ld.coff[l];
-
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    const int y = p / W, x = p - y * W;
     float fx = (float)(((double)x + 0.5) * scale_x - 0.5);
     int sx = (int)floorf(fx);
     fx = __fsub_rn(fx, (float)sx);
@@ -169,13 +151,21 @@ __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__
     fy = __fsub_rn(fy, (float)sy);
     const int y0 = min(max(sy, 0), gh - 1), y1 = min(max(sy + 1, 0), gh - 1);
     const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
-    const float* r0 = src + (size_t)y0 * gw * C;
-    const float* r1 = src + (size_t)y1 * gw * C;
-    const float h0 = __fadd_rn(__fmul_rn(__ldg(r0 + (size_t)sx * C + cl), a0), __fmul_rn(__ldg(r0 + (size_t)sx1 * C + cl), a1));
-    const float h1 = __fadd_rn(__fmul_rn(__ldg(r1 + (size_t)sx * C + cl), a0), __fmul_rn(__ldg(r1 + (size_t)sx1 * C + cl), a1));
-    const float v = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
-    if (UNARY) out[(size_t)px * Mp + ld.coff[l] + cl] = -v;
-    else out[gid] = v;
+    for (int l = 0; l < ld.L; l++) {
+        const int C = ld.C[l];
+        const float* src = lowres + (size_t)gw * gh * ld.coff[l];
+        const float* r00 = src + ((size_t)y0 * gw + sx) * C;
+        const float* r01 = src + ((size_t)y0 * gw + sx1) * C;
+        const float* r10 = src + ((size_t)y1 * gw + sx) * C;
+        const float* r11 = src + ((size_t)y1 * gw + sx1) * C;
+        float* o = UNARY ? out + (size_t)p * Mp + ld.coff[l] : out + (size_t)W * H * ld.coff[l] + (size_t)p * C;
+        for (int cl = 0; cl < C; cl++) {
+            const float h0 = __fadd_rn(__fmul_rn(__ldg(r00 + cl), a0), __fmul_rn(__ldg(r01 + cl), a1));
+            const float h1 = __fadd_rn(__fmul_rn(__ldg(r10 + cl), a0), __fmul_rn(__ldg(r11 + cl), a1));
+            const float v = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+            o[cl] = UNARY ? -v : v;
+        }
+    }
 }
 void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, int gh, int W, int H, int L,
                      const int* C, float* posteriors, int unary_stride) {
@@ -183,7 +173,7 @@ void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, i
     int sumC = 0;
     for (int l = 0; l < L; l++) sumC += C[l];
     const double scale_x = 1.0 / ((double)W / (double)gw), scale_y = 1.0 / ((double)H / (double)gh);
-    const long long total = (long long)W * H * sumC;
+    const long long total = (long long)W * H;  // one thread per output pixel
     if (unary_stride > 0)
         RSS_LAUNCH(c, upsample_kernel<true>, rss_div_up(total, 256), 256, 0, st, lowres, gw, gh, W, H, d, sumC, unary_stride,
                    scale_x, scale_y, posteriors);

@@ -26,6 +26,14 @@ void launch_scalar_features(rss_ctx* c, cudaStream_t st, const uint16_t* depth, 
                             const int* xs, const int* ys, int n, float* feats, int D, int pos_depth,
                             int pos_height, int pos_normal);
 
+// forest traversal with the features evaluated on demand from the frame (no materialised feature matrix)
+void launch_forest_traverse_frame(rss_ctx* c, cudaStream_t st, const Node* nodes, const int* tree_off, int T,
+                                  const uchar4* lab, const uint16_t* depth, const float4* xyz, const float* dist,
+                                  const double* integ, const int* cnt, const ResizeTap* tapx, const ResizeTap* tapy,
+                                  const uint16_t* feat_xy, int W, int H, int P, int r, int ncolor, int pos_depth,
+                                  int pos_height, int pos_normal, const int* xs, const int* ys, int n, int ld,
+                                  int* leaf_ids);
+
 // ---- normals.cu (PCL IntegralImageNormalEstimation, AVERAGE_3D_GRADIENT) ---------------------------
 // dist_b receives the final distance map; grad: float[6][H*W], fin: u8[2][H*W] scratch
 void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int W, int H, float* dist_a,
