@@ -37,9 +37,6 @@
 #define RSS_BLUR_MAXT 128  // CTA size of the cooperative blur: small register / thread footprint on purpose, so that
                            // kernels of OTHER keyframes in flight run on the SMs while its CTAs wait at the grid barriers
 #endif
-#ifndef RSS_TILE_SMEM_PAIRS
-#define RSS_TILE_SMEM_PAIRS 1  // stage the tile's splat pair lists in shared memory (cp.async during phase 1)
-#endif
 #ifndef RSS_TILE_SINGLE_WAVE
 #define RSS_TILE_SINGLE_WAVE 0  // grow the tiles until all CTAs of the point kernel are resident at once
 #endif
@@ -361,39 +358,47 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
     const TileOrigin org = tile_origin(tm, tile);
     const bool do_slice = mode & 1, do_splat = mode & 2, store_q = mode & 4;
     const int c0 = 4 * g;
-    // entry metadata of this tile's splat (list end, vertex) -> shared memory; consumed after phase 1
-    // (2 * TP slots shared by the lattices; entries beyond the staged ones are read from global memory)
+    // The tile's splat inputs - segment metadata (start | length, vertex) and the pair lists - go to shared memory with
+    // TMA bulk copies (cp.async.bulk, completion on an mbarrier): ONE thread issues four copies, they run during
+    // phase 1, and phase 2 never waits for L2.  The metadata region holds 2 * TP segments shared by the lattices;
+    // segments beyond the staged ones (never seen in practice) are read from global memory.
+    __shared__ alignas(8) unsigned long long stage_bar;
     int2* metaA = reinterpret_cast<int2*>(qtile + (size_t)TP * G);
     int2* metaB = metaA;
+    uint2* spairsA = reinterpret_cast<uint2*>(metaA + 2 * TP);
+    uint2* spairsB = spairsA + TP * D1A;
     int neA = 0, neB = 0, capA = 0, capB = 0;
     if (do_splat) {
         neA = __ldg(a.tile_nent[0] + tile);
         capA = min(neA, 2 * TP);
-        const size_t tbA = (size_t)tile * TP * D1A;
-        for (int e = threadIdx.x; e < capA; e += 256) metaA[e] = __ldg(a.ent_meta[0] + tbA + e);
         if constexpr (D1B > 0) {
             neB = __ldg(a.tile_nent[1] + tile);
-            metaB = metaA + capA;
-            capB = min(neB, 2 * TP - capA);
-            const size_t tbB = (size_t)tile * TP * D1B;
-            for (int e = threadIdx.x; e < capB; e += 256) metaB[e] = __ldg(a.ent_meta[1] + tbB + e);
+            metaB = metaA + ((capA + 1) & ~1);  // keep 16-byte alignment for the bulk copy
+            capB = min(neB, 2 * TP - ((capA + 1) & ~1));
+        }
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            auto bulk = [&](void* dst, const void* src, unsigned bytes) {
+                if (bytes == 0) return;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(dst)),
+                             "l"(src), "r"(bytes), "r"(bar)
+                             : "memory");
+            };
+            // sizes rounded up to 16 bytes: the arrays have TP * D1 (even) slots per tile, so the extra 8 bytes exist
+            const unsigned szMA = ((unsigned)capA * 8 + 15) & ~15u, szMB = ((unsigned)capB * 8 + 15) & ~15u;
+            const unsigned szPA = (unsigned)TP * D1A * 8, szPB = (unsigned)TP * D1B * 8;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(szMA + szMB + szPA + szPB) : "memory");
+            bulk(metaA, a.ent_meta[0] + (size_t)tile * TP * D1A, szMA);
+            bulk(spairsA, a.pairs[0] + (size_t)tile * TP * D1A, szPA);
+            if constexpr (D1B > 0) {
+                bulk(metaB, a.ent_meta[1] + (size_t)tile * TP * D1B, szMB);
+                bulk(spairsB, a.pairs[1] + (size_t)tile * TP * D1B, szPB);
+            }
         }
     }
-#if RSS_TILE_SMEM_PAIRS
-    // the tile's pair lists -> shared memory with cp.async: the copy runs during phase 1 and phase 2 never waits for L2
-    uint2* spairsA = reinterpret_cast<uint2*>(metaA + 2 * TP);
-    uint2* spairsB = spairsA + TP * D1A;
-    if (do_splat) {
-        auto stage = [&](uint2* dst, const uint2* src, int n) {  // n pairs, 16 bytes (two pairs) per copy
-            const unsigned sbase = (unsigned)__cvta_generic_to_shared(dst);
-            for (int o = threadIdx.x * 2; o < n; o += 512)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + o * 8), "l"(src + o) : "memory");
-        };
-        stage(spairsA, a.pairs[0] + (size_t)tile * TP * D1A, TP * D1A);
-        if constexpr (D1B > 0) stage(spairsB, a.pairs[1] + (size_t)tile * TP * D1B, TP * D1B);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-#endif
     // per channel group (host-precomputed, FusedLayers): which of my four channels belong to which layer (one nibble per
     // layer), and for aligned layers my layer, my valid channels and which lanes of the group share the layer
     const unsigned lmask = ls.group_lmask[g];
@@ -519,26 +524,22 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
         run_step(s, in0);
     }
     if (!do_splat) return;
-#if RSS_TILE_SMEM_PAIRS
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-    __syncthreads();
+    __syncthreads();  // the tile's marginals are complete (and thread 0's mbarrier.init is visible)
+    {                 // wait for the bulk copies (phase 0 of the barrier)
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
     // phase 2: tile-local gather splat out of shared memory
     {
         const size_t tbA = (size_t)tile * TP * D1A;
-#if RSS_TILE_SMEM_PAIRS
         gather_entries<G, RSS_TILE_IU>(spairsA, metaA, capA, a.ent_meta[0] + tbA, neA, a.lat[0].vout, qtile);
-#else
-        gather_entries<G, RSS_TILE_IU>(a.pairs[0] + tbA, metaA, capA, a.ent_meta[0] + tbA, neA, a.lat[0].vout, qtile);
-#endif
     }
     if constexpr (D1B > 0) {
         const size_t tbB = (size_t)tile * TP * D1B;
-#if RSS_TILE_SMEM_PAIRS
         gather_entries<G, RSS_TILE_IU>(spairsB, metaB, capB, a.ent_meta[1] + tbB, neB, a.lat[1].vout, qtile);
-#else
-        gather_entries<G, RSS_TILE_IU>(a.pairs[1] + tbB, metaB, capB, a.ent_meta[1] + tbB, neB, a.lat[1].vout, qtile);
-#endif
     }
 }
 
@@ -716,7 +717,7 @@ static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d
     do {                                                                                                                \
         auto kfn = meanfield_tile_kernel<G, A, B>;                                                                      \
         const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2) +        \
-                            (RSS_TILE_SMEM_PAIRS ? (size_t)TP * (A + B) * sizeof(uint2) : 0);                                            \
+                            (size_t)TP * (A + B) * sizeof(uint2);                                            \
         if (c->smem_attr_done.insert((const void*)kfn).second) { /* once per context (= per device) and instantiation */ \
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                        \
             cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
