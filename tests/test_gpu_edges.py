@@ -163,3 +163,34 @@ def test_error_behaviour(ctx, tmp_path):
     with pytest.raises(rss.RssError):
         crf.add_pairwise(np.zeros((100, 9), np.float32), 1.0)  # d > 7
     crf.close()
+
+
+def test_three_layer_forest_keyframe(orc):
+    """A forest with three label layers of 4 + 7 + 5 classes (16 labels = 4 channel groups, unaligned layer boundaries):
+    bit-exact posteriors, and the keyframe call through the generic (non-tile) mean-field path."""
+    import os
+    import rovinasemanticsegmentation_b200 as rss
+    from conftest import GOLDEN
+    from rovinasemanticsegmentation_b200 import synth
+    cfg, forest = os.path.join(GOLDEN, "config_3layer.json"), os.path.join(GOLDEN, "forest_3layer.dat")
+    W, H = 160, 120
+    rgb, depth = synth.frame(61, W, H)
+    Kinv, R, t = synth.calibration(W, H)
+    ofor = orc.Forest(forest)
+    with rss.Context(cfg, forest, 0) as c:
+        assert list(c.info.class_counts[:3]) == [4, 7, 5] and list(c.info.unknown_label[:3]) == [3, 6, 4]
+        post = c.segment_frame(rgb, depth, Kinv, R, t, 0.0)
+        post0 = orc.segment_frame(orc.default_config(), ofor, 2, rgb, depth, Kinv, R, t, 0.5, 15.0, 0.0)
+        assert post0.tobytes() == post.tobytes()
+        prm = rss.KeyframeParams(0.05, 3.0, 80.0, 13.0, 10.0, 6, 0.0)
+        labels, Q = c.segment_keyframe(rgb, depth, Kinv, R, t, prm, want_Q=True)
+    xyz = orc.cloud(depth, Kinv, R, t, 0.5, 15.0).reshape(-1, 3)
+    xyz[np.isnan(xyz[:, 0])] = t
+    f3 = (xyz * np.float32(1.0 / 0.05)).astype(np.float32)
+    f5 = orc.features_bilateral2d(W, H, 80, 80, 13, 13, 13, rgb)
+    off, N = 0, W * H
+    for l, (M, unk) in enumerate(((4, 3), (7, 6), (5, 4))):
+        Q0 = orc.crf_inference(-post0[off:off + N * M].reshape(N, M), [(f3, 3.0), (f5, 10.0)], 6)
+        assert np.abs(Q0 - Q[off:off + N * M].reshape(N, M)).max() <= 1e-4
+        assert (orc.gated_argmax(Q0, unk) == labels[l]).mean() >= 0.999
+        off += N * M

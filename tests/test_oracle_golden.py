@@ -76,3 +76,21 @@ def test_live_reference_forest_and_lattice(orc):
     assert a.V == b.V
     x = np.random.default_rng(0).random((20001, 8), dtype=np.float32)
     assert np.array_equal(a.compute(x), b.compute(x))
+
+
+def test_three_layer_forest_matches_live_reference(orc):
+    """The small 3-layer forest (4 + 7 + 5 classes, tests/golden/make_forest_3layer.py): oracle == compiled reference."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "forest_3layer.dat")
+    mine = orc.Forest(path)
+    assert (mine.T, mine.L, mine.classes) == (3, 3, [4, 7, 5])
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    from rovinasemanticsegmentation_b200 import synth
+    Kinv, R, t = synth.calibration()
+    rgb, depth = synth.frame(78)
+    feats, xs, ys = orc.extract(orc.default_config(), 6, rgb, depth, Kinv, R, t, 0.5, 15.0)
+    l0, p0 = mine.predict(feats)
+    l1, p1 = orc.RefForest(path).predict(feats, mine.sumC)
+    assert np.array_equal(l0, l1) and np.array_equal(p0, p1)
