@@ -194,3 +194,78 @@ def test_three_layer_forest_keyframe(orc):
         assert np.abs(Q0 - Q[off:off + N * M].reshape(N, M)).max() <= 1e-4
         assert (orc.gated_argmax(Q0, unk) == labels[l]).mean() >= 0.999
         off += N * M
+
+
+def _rewrite_single_label(src, dst, layer_classes, keep_layer):
+    """Rewrites a multi-label libforest file (io.h:43-108) as a classic single-label one: the same trees, the leaves'
+    `histograms` hold the rows of `keep_layer`, `multi_histograms` are empty (what RandomForestLearner writes)."""
+    import struct
+    b = open(src, "rb").read()
+    o = 0
+
+    def i32():
+        nonlocal o
+        v = struct.unpack_from("<i", b, o)[0]
+        o += 4
+        return v
+
+    out = bytearray()
+    T = i32()
+    out += struct.pack("<i", T)
+    for _ in range(T):
+        n = i32()
+        out += struct.pack("<i", n) + b[o:o + 4 * n]; o += 4 * n          # splitFeatures
+        assert i32() == n
+        out += struct.pack("<i", n) + b[o:o + 4 * n]; o += 4 * n          # thresholds
+        assert i32() == n
+        left = struct.unpack_from("<%di" % n, b, o)
+        out += struct.pack("<i", n) + b[o:o + 4 * n]; o += 4 * n          # leftChild
+        assert i32() == n
+        for _k in range(n):
+            assert i32() == 0                                             # plain histograms are empty in a multi forest
+        assert i32() == n
+        rows = []
+        for k in range(n):
+            L = i32()
+            row = None
+            for l in range(L):
+                c = i32()
+                vals = b[o:o + 4 * c]; o += 4 * c
+                if l == keep_layer:
+                    assert c == layer_classes[l]
+                    row = vals
+            rows.append(row)
+        out += struct.pack("<i", n)
+        for k in range(n):
+            if left[k] == 0:
+                out += struct.pack("<i", layer_classes[keep_layer]) + rows[k]
+            else:
+                out += struct.pack("<i", 0)
+        out += struct.pack("<i", n)
+        for k in range(n):
+            out += struct.pack("<i", 0)
+    assert o == len(b)
+    open(dst, "wb").write(bytes(out))
+
+
+def test_single_label_forest_file(tmp_path):
+    """A classic single-label libforest model (plain `histograms`, RandomForest::classLogPosterior,
+    classifier.cpp:166-184) loads and predicts: same trees as the 3-layer forest, so its posteriors must equal that
+    forest's layer-1 columns bit for bit."""
+    import os
+    import rovinasemanticsegmentation_b200 as rss
+    from conftest import GOLDEN
+    from rovinasemanticsegmentation_b200 import synth
+    multi = os.path.join(GOLDEN, "forest_3layer.dat")
+    single = str(tmp_path / "single.dat")
+    _rewrite_single_label(multi, single, [4, 7, 5], 1)
+    rgb, depth = synth.frame(62, 160, 120)
+    Kinv, R, t = synth.calibration(160, 120)
+    with rss.Context(os.path.join(GOLDEN, "config_3layer.json"), multi, 0) as c:
+        f, xs, ys = c.extract_features(rgb, depth, Kinv, R, t, 2, 0.5, 15.0)
+        leaf_m, post_m = c.forest_predict(n=f.shape[0])
+    with rss.Context(os.path.join(GOLDEN, "config_3layer.json"), single, 0) as c:
+        assert (c.info.layer_count, c.info.total_classes) == (1, 7)
+        leaf_s, post_s = c.forest_predict(f)
+    assert np.array_equal(leaf_m, leaf_s)
+    assert post_s.tobytes() == np.ascontiguousarray(post_m[:, 4:11]).tobytes()
