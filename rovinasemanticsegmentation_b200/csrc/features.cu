@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) scalar_features_kernel(const uint16_t* __
 // features of a sample, so this skips ~90 % of the resize arithmetic and the 112 MB feature matrix never exists
 // ("~6 MB if fused with F2").  The value of a feature is computed by exactly the same integer / float
 // operations as patch_features_kernel and scalar_features_kernel, so leaf ids stay bit-exact.
-// One thread per (sample, tree); feat_xy[k] = dx | dy << 8 of patch pixel k.
+// One thread per (tree, sample); feat_xy[k] = dx | dy << 8 of patch pixel k.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ Node load_node_ro(const Node* p) {
     const int4 v = __ldg(reinterpret_cast<const int4*>(p));
@@ -232,7 +232,10 @@ __device__ __forceinline__ Node load_node_ro(const Node* p) {
     n.feat = v.x; n.thr = __int_as_float(v.y); n.left = v.z; n.leaf = v.w;
     return n;
 }
-__global__ void __launch_bounds__(256) forest_traverse_frame_kernel(
+#ifndef RSS_FOREST_MINB
+#define RSS_FOREST_MINB 4  // resident CTAs per SM: the traversal is a chain of dependent loads, more warps hide it
+#endif
+__global__ void __launch_bounds__(256, RSS_FOREST_MINB) forest_traverse_frame_kernel(
     const Node* __restrict__ nodes, const int* __restrict__ tree_off, int T, const uchar4* __restrict__ lab,
     const uint16_t* __restrict__ depth, const float4* __restrict__ xyz, const float* __restrict__ dist,
     const double* __restrict__ integ, const int* __restrict__ cnt, const ResizeTap* __restrict__ tapx,
@@ -241,7 +244,9 @@ __global__ void __launch_bounds__(256) forest_traverse_frame_kernel(
     int* __restrict__ leaf_ids) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)n * T) return;
-    const int s = (int)(gid / T), t = (int)(gid - (long long)s * T);
+    // tree-major: the 32 lanes of a warp walk the SAME tree for 32 consecutive samples (neighbouring pixels), so near
+    // the root they visit the same nodes, take the same feature branch and read neighbouring pixels
+    const int t = (int)(gid / n), s = (int)(gid - (long long)t * n);
     const Node* tree = nodes + tree_off[t];
     const int x = xs[s], y = ys[s];
     const size_t i = (size_t)y * W + x;

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) forest_traverse_kernel(const Node* __rest
                                                               int* __restrict__ leaf_ids) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)n * T) return;
-    const int s = (int)(gid / T), t = (int)(gid - (long long)s * T);
+    const int t = (int)(gid / n), s = (int)(gid - (long long)t * n);  // tree-major: a warp walks one tree
     const Node* tree = nodes + tree_off[t];
     const float* x = feats + (size_t)s * D;
     int node = 0;
