@@ -414,6 +414,32 @@ def run_gpu(args, rank, world, local_rank):
             "kernels_note": "per-kernel device times from a second single-context pass with event bracketing on "
                             "(%.3f ms/keyframe vs %.3f ms/keyframe without)" % (lat_ms_prof / args.steps, lat_ms / args.steps),
         }
+        if world == 1 and not args.quick:
+            # configs[3] side measurement (not the headline): one local map of 2 M points, both label layers through one
+            # 6-D lattice at the node's kernel widths, 10 mean-field iterations, device time from the library's events
+            NM = 2_000_000
+            xyz, col = synth.local_map(seed=5, n_points=NM)
+            crf = ctx.crf(NM, [8, 9])
+            rng = np.random.default_rng(0)
+            for l, m in enumerate((8, 9)):
+                crf.set_unary(rng.random((NM, m), dtype=np.float32), l)
+            builds = []
+            for rep in range(2):  # the first build also pays for every device allocation of a map of this size
+                if rep:
+                    crf.close()
+                    crf = ctx.crf(NM, [8, 9])
+                    for l, m in enumerate((8, 9)):
+                        crf.set_unary(rng.random((NM, m), dtype=np.float32), l)
+                t0 = time.perf_counter()
+                crf.add_pairwise_xyzrgb(xyz, col, 0.5, 4.0, 10.0)
+                builds.append(time.perf_counter() - t0)
+            build_s = builds[-1]
+            crf.inference(10, unknown=[7, 8], want_Q=False, want_labels=True)
+            line["local_map"] = {"points": NM, "labels": 17, "vertices": crf.lattice_size(0),
+                                 "ms_per_meanfield_iter": ctx.timings()["meanfield_ms"] / 10,
+                                 "lattice_build_ms_incl_h2d": 1000.0 * build_s, "first_build_ms_incl_allocation": 1000.0 * builds[0],
+                                 "note": "generic (unordered point set) path: vertex-major CSR gather splat"}
+            crf.close()
         if world == 1 and not args.no_cpu and not args.quick:
             import oracle
             oracle.build(ref=False)
@@ -433,7 +459,7 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -456,6 +456,10 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
     float* Q = crf->Q.as<float>();
     const float* U = crf->unary.as<float>();
     const int G = Mp / 4;
+    int fi0 = 0, fi1 = -1;
+    // the fused path computes Q0 = expAndNormalize(-unary) inside its first point kernel
+    if (init && iters > 0 && K > 0 && crf_fused_order(crf, &fi0, &fi1))
+        return crf_run_fused(crf, iters, unknown, labels_dev, fi0, fi1);
     if (init) RSS_LAUNCH(ctx, softmax_init_kernel, rss_div_up((long long)N * 8, 256), 256, 0, s0, U, N, G, Mp, ls, Q);
     if (iters <= 0 || K == 0) {
         // no pairwise terms: every iteration reproduces expAndNormalize(-unary), i.e. Q0
@@ -466,8 +470,6 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
         RSS_CU(ctx, cudaGetLastError());
         return RSS_OK;
     }
-    int fi0 = 0, fi1 = -1;
-    if (init && crf_fused_order(crf, &fi0, &fi1)) return crf_run_fused(crf, iters, unknown, labels_dev, fi0, fi1);
     for (int it = 0; it < iters; it++) {
         SliceArgs sa;
         sa.K = K;
