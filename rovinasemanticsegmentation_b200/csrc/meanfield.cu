@@ -341,12 +341,14 @@ __device__ __forceinline__ void gather_entries(const uint2* pr, const int2* meta
     }
 }
 
-template <int G, int D1A, int D1B>
+// MODE is a compile-time constant (2 = first pass, 3 = middle passes, 5 = last pass): the slice / splat / store branches
+// disappear from the instruction stream of each variant.
+template <int G, int D1A, int D1B, int MODE>
 __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ FusedArgs a,
                                                              const float* __restrict__ unary, float* __restrict__ Q,
                                                              uint8_t* __restrict__ labels,
                                                              const __grid_constant__ TileMap tm, int steps,
-                                                             const __grid_constant__ FusedLayers ls, int mode) {
+                                                             const __grid_constant__ FusedLayers ls) {
     extern __shared__ float4 qtile[];  // [TP][G]
     if (a.counts[0][1]) return;  // lattice overflow: the host rebuilds with a larger table and runs again
     if constexpr (D1B > 0) { if (a.counts[1][1]) return; }
@@ -356,7 +358,7 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
     const bool lane_on = sub < cpw;
     const int tile = blockIdx.x, TP = tm.TP, N = tm.N;
     const TileOrigin org = tile_origin(tm, tile);
-    const bool do_slice = mode & 1, do_splat = mode & 2, store_q = mode & 4;
+    constexpr bool do_slice = MODE & 1, do_splat = MODE & 2, store_q = MODE & 4;
     const int c0 = 4 * g;
     // The tile's splat inputs - segment metadata (start | length, vertex) and the pair lists - go to shared memory with
     // TMA bulk copies (cp.async.bulk, completion on an mbarrier): ONE thread issues four copies, they run during
@@ -713,16 +715,22 @@ static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d
                           uint8_t* labels, const TileMap& tm, const FusedLayers& ls, int mode) {
     const int TP = tm.TP, steps = fused_tile_steps(G, TP);
     const int grid = tm.ntiles;
-#define RSS_TILE(A, B)                                                                                                  \
+#define RSS_TILE_M(A, B, M)                                                                                             \
     do {                                                                                                                \
-        auto kfn = meanfield_tile_kernel<G, A, B>;                                                                      \
-        const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2) +        \
-                            (size_t)TP * (A + B) * sizeof(uint2);                                            \
+        auto kfn = meanfield_tile_kernel<G, A, B, M>;                                                                   \
+        const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2) +                           \
+                            (size_t)TP * (A + B) * sizeof(uint2);                                                       \
         if (c->smem_attr_done.insert((const void*)kfn).second) { /* once per context (= per device) and instantiation */ \
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                        \
             cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
         }                                                                                                               \
-        RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, tm, steps, ls, mode); \
+        RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, tm, steps, ls);     \
+    } while (0)
+#define RSS_TILE(A, B)                                                                                                  \
+    do {                                                                                                                \
+        if (mode == 2) RSS_TILE_M(A, B, 2);                                                                             \
+        else if (mode == 3) RSS_TILE_M(A, B, 3);                                                                        \
+        else RSS_TILE_M(A, B, 5);                                                                                       \
     } while (0)
     switch (d1a * 16 + d1b) {
         case 0x46: RSS_TILE(4, 6); break;
@@ -734,6 +742,7 @@ static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d
         default: break;
     }
 #undef RSS_TILE
+#undef RSS_TILE_M
 }
 void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
                             uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode) {
