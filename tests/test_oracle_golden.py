@@ -94,3 +94,24 @@ def test_three_layer_forest_matches_live_reference(orc):
     l0, p0 = mine.predict(feats)
     l1, p1 = orc.RefForest(path).predict(feats, mine.sumC)
     assert np.array_equal(l0, l1) and np.array_equal(p0, p1)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 5, 6, 7])
+def test_lattice_every_dimension_and_padding_vs_live_reference(orc, d):
+    """Oracle lattice == compiled reference for every feature dimension and every N mod 4 (the reference pads its last
+    SSE block with zero-feature points whose vertices exist for the blur, permutohedral.cpp:192-198)."""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(d)
+    for N in (1001, 1002, 1003, 1004):
+        t = np.linspace(0, 5, N)
+        f = (np.stack([np.sin((k + 1) * t + k) * (1.5 + k) for k in range(d)], axis=1) + rng.normal(0, 0.03, (N, d))).astype(np.float32)
+        a, b = orc.Lattice(f), orc.RefLattice(f)
+        assert a.V == b.V, (d, N)
+        oa, ba = a.get()
+        ob, bb = b.get()
+        assert np.array_equal(oa, ob) and np.array_equal(ba, bb)
+        x = rng.random((N, 5), dtype=np.float32)
+        assert np.array_equal(a.compute(x), b.compute(x))
+        ones = np.ones((N, 1), np.float32)
+        assert np.array_equal(a.compute(ones), b.compute(ones))  # the scalar path used for the normalisation
