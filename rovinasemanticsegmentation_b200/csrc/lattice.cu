@@ -364,14 +364,6 @@ __global__ void __launch_bounds__(512) splat_kernel(const int* __restrict__ seg_
 }
 
 // blur along one axis (:555-569): new[v] = old[v] + 0.5 * (old[n1] + old[n2]); a missing neighbour is the zero row
-__device__ __forceinline__ float4 blur_item(const float4 o, const float4 a, const float4 b) {
-    float4 r;
-    r.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(a.x, b.x)));
-    r.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(a.y, b.y)));
-    r.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(a.z, b.z)));
-    r.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(a.w, b.w)));
-    return r;
-}
 // one launch per axis: the large-lattice path (value tables beyond L2 reach of one cluster)
 __global__ void __launch_bounds__(256) blur_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                                    const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
@@ -395,18 +387,6 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p, 
 // (monotonic target, so it never needs resetting).  Value reads use ld.global.cg: the rows were written by other SMs
 // one axis earlier and must come from L2, not from a stale L1 line.  After the last axis the table that does NOT hold
 // the result is zeroed: it is the next iteration's splat target, so an iteration needs no memset launch.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while ((int)(v - target) < 0);
-    }
-    __syncthreads();
-}
 __global__ void __launch_bounds__(512) blur_coop_kernel(float4* __restrict__ a, float4* __restrict__ b,
                                                         const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
                                                         int G, int d1, uint32_t vcap, unsigned int* barrier,

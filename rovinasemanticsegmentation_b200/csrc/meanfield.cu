@@ -547,30 +547,11 @@ __global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ Fu
 
 // ---------------------------------------------------------------------------------------------------------------
 // Blur of every lattice of the CRF in ONE cooperative launch (permutohedral.cpp:555-569).  Phase j blurs axis j of
-// each lattice that has one; phases are separated by a grid barrier on an L2 counter.  The neighbour pair of the next
-// axis is fetched before the barrier (it does not depend on it).  Phase 0 additionally clears `zero` (the table the
+// each lattice that has one; phases are separated by a grid barrier on an L2 counter (lattice.cuh).  Prefetching the
+// neighbour pairs ahead of the rows was measured and does not help: the rows' L2 round trip dominates a round.
+// Phase 0 additionally clears `zero` (the table the
 // point kernel sliced from one iteration ago), which becomes the next splat target - so no phase follows the last axis.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier2(unsigned int* counter, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while ((int)(v - target) < 0);
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ float4 blur3(const float4 o, const float4 x, const float4 y) {
-    float4 r;
-    r.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(x.x, y.x)));
-    r.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(x.y, y.y)));
-    r.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(x.z, y.z)));
-    r.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(x.w, y.w)));
-    return r;
-}
 // one axis of one lattice: items are (vertex, channel group); U independent items per thread are in flight at once
 template <int U>
 __device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4* __restrict__ dst, const int2* __restrict__ nb_j,
@@ -600,7 +581,7 @@ __device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t it = base + u * nthr;
-            if (it < items) __stcg(dst + it, blur3(o[u], x[u], y[u]));
+            if (it < items) __stcg(dst + it, blur_item(o[u], x[u], y[u]));
         }
     }
 }
@@ -623,7 +604,7 @@ __global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __
             if (j == 0 && a.zero[k])
                 for (uint32_t it = tid; it < items; it += nthr) __stcg(a.zero[k] + it, make_float4(0.f, 0.f, 0.f, 0.f));
         }
-        if (j + 1 < maxd1) grid_barrier2(barrier, barrier_base + (unsigned int)(j + 1) * gridDim.x);
+        if (j + 1 < maxd1) grid_barrier(barrier, barrier_base + (unsigned int)(j + 1) * gridDim.x);
     }
 }
 
