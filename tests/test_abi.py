@@ -49,3 +49,21 @@ def test_status_strings(lib):
     lib.rss_status_string.restype = ctypes.c_char_p
     assert lib.rss_status_string(0) == b"ok"
     assert b"CUDA" in lib.rss_status_string(5)
+
+
+def test_cpp_host_side_builds_without_cuda_headers(lib, tmp_path):
+    """The C++ adapters and the multi-GPU worker compile with plain g++ against include/rss.h (no CUDA headers) and
+    link against librss.so; without a GPU the worker fails loudly instead of falling back."""
+    import subprocess
+    from rovinasemanticsegmentation_b200 import build
+    root = os.path.dirname(os.path.dirname(rss.__file__))
+    exe = build.build_host(force=True)
+    assert os.path.exists(exe)
+    chk = str(tmp_path / "adapters_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-o", chk,
+                           os.path.join(root, "tests", "cpp", "adapters_check.cpp"), "-L" + os.path.dirname(rss.LIB_PATH),
+                           "-lrss", "-Wl,-rpath," + os.path.dirname(rss.LIB_PATH)])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "--config", CONFIG, "--forest", FOREST, "--frames", "2"], capture_output=True, text=True)
+        assert r.returncode != 0 and "keyframe_worker:" in r.stderr
