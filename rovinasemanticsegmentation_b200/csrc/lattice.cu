@@ -62,16 +62,13 @@ __device__ __forceinline__ Key128 load_key(const Key128* p) {
 // The probe sequence is bounded (HASH_MAX_PROBES): a table that is too small for the lattice must fail FAST (the host
 // retries with a larger one), not degenerate into full-table scans by millions of threads.
 constexpr uint32_t HASH_MAX_PROBES = 256;
-__device__ __forceinline__ int hash_insert(Key128* table, uint32_t mask, const Key128& key, uint32_t* counts) {
+__device__ __forceinline__ int hash_insert(Key128* table, uint32_t mask, const Key128& key) {
     uint32_t h = key_hash(key) & mask;
     const uint32_t limit = min(mask, HASH_MAX_PROBES);
     for (uint32_t probes = 0; probes <= limit; probes++) {
         if (key_eq(load_key(table + h), key)) return (int)h;
         const Key128 old = atomicCAS(table + h, key_empty(), key);
-        if (key_eq(old, key_empty())) {
-            atomicAdd(counts + 3, 1u);
-            return (int)h;
-        }
+        if (key_eq(old, key_empty())) return (int)h;
         if (key_eq(old, key)) return (int)h;
         h = (h + 1) & mask;
     }
@@ -180,7 +177,7 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
             const int canon = irank[k] <= D - rem ? rem : rem - (D + 1);
             key[k] = irem[k] + canon;
         }
-        const int slot = hash_insert(table, mask, key_pack<D>(key), counts);
+        const int slot = hash_insert(table, mask, key_pack<D>(key));
         if (slot < 0) counts[1] = 1u;
         else atomicMin(first_ref + slot, (uint32_t)i * (D + 1) + rem);  // first (point, corner) pair that touches the vertex
         offsets[(size_t)i * (D + 1) + rem] = slot;

@@ -31,7 +31,7 @@ struct Lattice {
     DevBuf bary;         // float[N][d+1]
     DevBuf nbr;          // int2 [d+1][vcap]  blur neighbours (n1, n2); missing -> zero row (index = vcap)
     DevBuf norm;         // float[N]
-    DevBuf counts;       // uint32[16]: [0] V, [1] overflow flag, [2] segments, [3] inserted, [4] seg total, [8] barrier
+    DevBuf counts;       // uint32[16]: [0] V, [1] overflow flag, [2] segments, [4] seg total, [8] barrier
     DevBuf deg;          // uint32[vcap+1]  row degree, then row_start (in-place scan)
     DevBuf cursor;       // uint32[vcap]
     DevBuf nseg;         // uint32[vcap+1]  segments per row, then segment offsets
