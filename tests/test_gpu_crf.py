@@ -175,3 +175,37 @@ def test_keyframe_fused(ctx, orc):
         assert np.abs(Q0 - Q1).max() <= TOL
         assert (orc.gated_argmax(Q0, unk) == labels[l]).mean() >= 0.999
         off += N * M
+
+
+def test_unary_accumulate_from_resident_posteriors(ctx, orc):
+    """Frame worker -> map worker without a host round trip: rss_segment_frame leaves the posteriors on the device and
+    rss_crf_unary_accumulate(posteriors = NULL) scatters them through the index image (segmenter.cpp:597-616)."""
+    from rovinasemanticsegmentation_b200 import synth
+    W, H = 160, 120
+    rgb, depth = synth.frame(91, W, H)
+    Kinv, R, t = synth.calibration(W, H)
+    N = 5000
+    rng = np.random.default_rng(4)
+    idx = rng.integers(-1, N, W * H).astype(np.int32)
+    post = ctx.segment_frame(rgb, depth, Kinv, R, t, 0.0)               # host copy for the expectation ...
+    crf_a = ctx.crf(N, [8, 9])
+    crf_a.unary_accumulate(idx, post)                                    # ... through the host path
+    ctx.segment_frame(rgb, depth, Kinv, R, t, 0.0, want_host=False)      # resident only
+    crf_b = ctx.crf(N, [8, 9])
+    crf_b.unary_accumulate(idx)                                          # device-resident posteriors
+    xyz, col = synth.local_map(seed=9, n_points=N)
+    for c in (crf_a, crf_b):
+        c.add_pairwise_xyzrgb(xyz, col, 0.5, 4.0, 10.0)
+    Qa, Qb = crf_a.inference(3), crf_b.inference(3)
+    for l in range(2):
+        assert np.abs(Qa[l] - Qb[l]).max() <= 1e-5   # float atomics: the accumulation order differs
+    # and against the oracle
+    un = [np.zeros((N, m), np.float32) for m in (8, 9)]
+    off = 0
+    for l, m in enumerate((8, 9)):
+        orc.unary_accumulate(idx, post[off:off + W * H * m].reshape(W * H, m), un[l])
+        off += W * H * m
+    f6 = orc.features_xyzrgb(xyz, col, 0.5, 4.0)
+    for l in range(2):
+        assert np.abs(orc.crf_inference(-un[l], [(f6, 10.0)], 3) - Qb[l]).max() <= TOL
+    crf_a.close(); crf_b.close()
