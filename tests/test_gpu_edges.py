@@ -269,3 +269,29 @@ def test_single_label_forest_file(tmp_path):
         leaf_s, post_s = c.forest_predict(f)
     assert np.array_equal(leaf_m, leaf_s)
     assert post_s.tobytes() == np.ascontiguousarray(post_m[:, 4:11]).tobytes()
+
+
+@pytest.mark.parametrize("norm_type", [1, 2, 3])  # NORMALIZE_BEFORE, NORMALIZE_AFTER, NORMALIZE_SYMMETRIC (pairwise.cpp:63-80)
+def test_normalization_types(ctx, norm_type):
+    """DenseKernel::filter's three normalisations: out = K (n * in) | n * K in | sqrt(n) * K (sqrt(n) * in) with n = 1 / (K 1).
+    One mean-field step is rebuilt in numpy from the library's own un-normalised filter (rss_crf_filter)."""
+    N, M, w = 6000, 6, 3.0
+    f, U = _problem(N, M, 3, 17)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise(f, w, norm_type)
+    Q1 = crf.inference(1)
+    K1 = crf.filter(np.ones((N, M), np.float32))[:, :1].astype(np.float64)
+    e = np.exp(-(U - U.min(1, keepdims=True)).astype(np.float64))
+    Q0 = (e / e.sum(1, keepdims=True)).astype(np.float32)
+    if norm_type == 1:
+        F = crf.filter((Q0 / (K1 + 1e-20)).astype(np.float32)).astype(np.float64)
+    elif norm_type == 2:
+        F = crf.filter(Q0).astype(np.float64) / (K1 + 1e-20)
+    else:
+        n = 1.0 / np.sqrt(K1 + 1e-20)
+        F = crf.filter((Q0 * n).astype(np.float32)).astype(np.float64) * n
+    tmp = -U.astype(np.float64) + w * F
+    e = np.exp(tmp - tmp.max(1, keepdims=True))
+    assert np.abs(e / e.sum(1, keepdims=True) - Q1).max() <= 1e-4
+    crf.close()
