@@ -99,45 +99,62 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_keyframe(seed):
-    """The oracle's single-thread restatement of one keyframe (how the reference runs inference)."""
+_CPU_FOREST = None
+_CPU_BARRIER = None
+
+
+def _cpu_init(barrier=None):
+    """Pool initialiser: load the checker library and the forest once per worker (outside every timed region)."""
+    global _CPU_FOREST, _CPU_BARRIER
+    import oracle
+    oracle.set_threads(1)
+    _CPU_FOREST = oracle.Forest(FOREST)
+    _CPU_BARRIER = barrier
+
+
+def cpu_keyframe(seed, want_labels=False):
+    """The oracle's single-thread restatement of one keyframe (how the reference runs inference).  Only the compute is
+    timed: frame synthesis and the forest load are outside the clock."""
     import oracle
     from rovinasemanticsegmentation_b200 import synth
-    oracle.set_threads(1)
+    if _CPU_FOREST is None:
+        _cpu_init()
     rgb, depth = synth.frame(seed)
     Kinv, R, t = synth.calibration()
-    forest = oracle.Forest(FOREST)
+    if _CPU_BARRIER is not None:
+        # all pipelines of a round start together (a worker waiting here cannot take a second task, so the tasks of a round
+        # land on distinct workers and the round's time is the slowest pipeline's compute time)
+        _CPU_BARRIER.wait(timeout=300)
     t0 = time.perf_counter()
-    post = oracle.segment_frame(oracle.default_config(), forest, 2, rgb, depth, Kinv, R, t, 0.5, 15.0, KF["fill"])
-    xyz = oracle.cloud(depth, Kinv, R, t, 0.5, 15.0).reshape(-1, 3)
-    xyz[np.isnan(xyz[:, 0])] = t
-    f3 = (xyz * np.float32(1.0 / KF["sigma_xyz"])).astype(np.float32)
-    f5 = oracle.features_bilateral2d(W, H, KF["sigma_px"], KF["sigma_px"], KF["sigma_rgb"], KF["sigma_rgb"],
-                                     KF["sigma_rgb"], rgb)
-    off, N = 0, W * H
-    for M, unk in ((8, 7), (9, 8)):
-        Q = oracle.crf_inference(-post[off:off + N * M].reshape(N, M), [(f3, KF["w_gauss"]), (f5, KF["w_bilateral"])],
-                                 KF["iters"])
-        oracle.gated_argmax(Q, unk)
-        off += N * M
-    return time.perf_counter() - t0
+    labels, _, _ = oracle.keyframe(_CPU_FOREST, rgb, depth, Kinv, R, t, **KF)
+    dt = time.perf_counter() - t0
+    return (dt, labels) if want_labels else (dt, None)
 
 
-def _cpu_worker(seed):
-    return cpu_keyframe(seed)
+def _cpu_worker(arg):
+    seed, want = arg
+    return cpu_keyframe(seed, want)
 
 
-def cpu_throughput(procs, rounds):
-    """`procs` independent single-thread pipelines side by side (keyframes are independent), `rounds` times."""
+def cpu_throughput(procs, rounds, warmup=1, first_seed=None):
+    """`procs` independent single-thread pipelines side by side (keyframes are independent), `rounds` times.  A round's
+    time is its slowest pipeline's compute time.  first_seed: worker 0 of the first timed round runs that frame and its
+    label maps are returned (parity check of the GPU arm against the very keyframes the CPU arm computed)."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, range(procs))  # warm-up: page in libraries, build LUTs
-        t0 = time.perf_counter()
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(ctx.Barrier(procs),)) as pool:
+        for w in range(max(1, warmup)):  # page in libraries, build LUTs
+            pool.map(_cpu_worker, [(50 + w * procs + i, False) for i in range(procs)], chunksize=1)
+        total, labels = 0.0, None
         for r in range(rounds):
-            pool.map(_cpu_worker, range(100 + r * procs, 100 + (r + 1) * procs))
-        dt = time.perf_counter() - t0
-    return procs * rounds / dt, dt
+            seeds = [(100 + r * procs + i, False) for i in range(procs)]
+            if r == 0 and first_seed is not None:
+                seeds[0] = (first_seed, True)
+            res = pool.map(_cpu_worker, seeds, chunksize=1)
+            total += max(dt for dt, _ in res)
+            if r == 0 and first_seed is not None:
+                labels = res[0][1]
+    return procs * rounds / total, total, labels
 
 
 def run_reference(args, rank, world):
@@ -147,18 +164,18 @@ def run_reference(args, rank, world):
     oracle.build(ref=False)
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
-    steps = max(1, min(args.steps, 3))
-    for _ in range(0):
-        pass
-    val, dt = cpu_throughput(procs, steps)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    val, dt, _ = cpu_throughput(procs, steps, warmup)
+    sample = ("one step = %d full 640x480 keyframes side by side, one single-thread oracle pipeline per host core "
+              "(oracle/oracle.c, pinned bit-exact / 1e-6 against the compiled reference); %d steps after %d warm-up steps; "
+              "a step's time is its slowest pipeline's compute time (frame synthesis and forest load excluded)"
+              % (procs, steps, warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "keyframes/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "CPU run"},
-        "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": procs, "kind": "port",
-                         "sample": "%d rounds of %d full 640x480 keyframes, one single-thread oracle pipeline per core "
-                                   "(oracle/oracle.c, validated bit-exact against the compiled reference)" % (steps, procs)},
+        "config": {"workload": WORKLOAD, "l2": "CPU run", "step": "%d keyframes (one per host core)" % procs},
+        "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -210,8 +227,48 @@ def algo_bytes(name, env):
         "tile_csr_build_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * N + 16 * (d + 1) * N),
         "splat_ones_runs_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * V),
         "slice_kernel": mean(lambda d, V: 8 * (d + 1) * N + 4 * V + 4 * N),
+        # two hash look-ups per (vertex, axis): the vertex key once, the int2 neighbour pair out, the two probed slots in
+        "neighbors_kernel<D>": mean(lambda d, V: 16 * V + (d + 1) * V * (8 + 2 * 16 + 2 * 4)),
+        "zero_rows_kernel": mean(lambda d, V: 16 * V), "norm_kernel": 8 * N,
+        "feat_bilateral_kernel": 3 * N + 20 * N, "feat_frame_xyz_kernel": 16 * N + 12 * N,
+        "lowres_fill_kernel": 4 * M * (N // 4),
     }
-    return table.get(name)
+    if name in table:
+        return table[name]
+    import re
+    return table.get(re.sub(r"<[0-9, ]+>", "<D>", name))
+
+
+def local_map_bench(ctx, synth, NM, wxyz, wrgb, peak, regime):
+    """BASELINE configs[3] side measurement: one local map of NM points, both label layers through one 6-D lattice
+    (src/segmenter.cpp:629-643), 10 mean-field iterations; device time from the library's events."""
+    xyz, col = synth.local_map(seed=5, n_points=NM)
+    rng = np.random.default_rng(0)
+    U = [rng.random((NM, m), dtype=np.float32) for m in (8, 9)]
+    builds = []
+    crf = None
+    for rep in range(2):  # the first build also pays for every device allocation of a map of this size
+        if crf is not None:
+            crf.close()
+        crf = ctx.crf(NM, [8, 9])
+        for l in range(2):
+            crf.set_unary(U[l], l)
+        t0 = time.perf_counter()
+        crf.add_pairwise_xyzrgb(xyz, col, wxyz, wrgb, 10.0)
+        builds.append(time.perf_counter() - t0)
+    crf.inference(10, unknown=[7, 8], want_Q=False, want_labels=True)
+    ms_iter = ctx.timings()["meanfield_ms"] / 10
+    V, M, d = crf.lattice_size(0), 17, 6
+    # one iteration, generic path: splat (Q rows + vertex-major CSR in, value rows out), d+1 blur axes (rows in/out +
+    # neighbour pairs), slice + soft-max (offsets + weights + norm + unique rows + unary in, Q out)
+    ab = (4 * M * NM + 8 * (d + 1) * NM + 4 * NM + 4 * M * V) + (d + 1) * (8 * M * V + 8 * V) + \
+         (8 * (d + 1) * NM + 4 * NM + 4 * M * V + 8 * M * NM)
+    out = {"points": NM, "labels": 17, "regime": regime, "vertices": V, "ms_per_meanfield_iter": ms_iter,
+           "lattice_build_ms_incl_h2d": 1000.0 * builds[-1], "first_build_ms_incl_allocation": 1000.0 * builds[0],
+           "algorithmic_bytes_per_iter": int(ab), "achieved_gbs": ab / (ms_iter / 1000.0) / 1e9,
+           "frac_of_hbm_peak": ab / (ms_iter / 1000.0) / 1e9 / peak}
+    crf.close()
+    return out
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -312,11 +369,12 @@ def run_gpu(args, rank, world, local_rank):
     # ---- (3) throughput: K steps shared by the NC contexts (keyframes are independent units; the reference runs one
     # worker per stage, here one worker per context).  Every step is preceded by a 160 MiB write on the worker's side
     # stream (L2 flush).  resident: the context's frame is already in HBM; e2e: pinned host rgb/depth in, labels out.
-    def throughput_pass(host_io, steps=None):
+    def throughput_pass(host_io, steps=None, nc=None):
         steps = args.steps if steps is None else steps
-        per = [steps // NC + (1 if i < steps % NC else 0) for i in range(NC)]
+        nc = NC if nc is None else nc
+        per = [steps // nc + (1 if i < steps % nc else 0) for i in range(nc)]
         if not host_io:
-            for i, c in enumerate(ctxs):
+            for i, c in enumerate(ctxs[:nc]):
                 c.upload_frame(*frames[i % N_FRAMES])
         errs = []
 
@@ -334,7 +392,7 @@ def run_gpu(args, rank, world, local_rank):
                 errs.append(e)
 
         l0 = sum(c.kernel_launches for c in ctxs)
-        ths = [th.Thread(target=worker, args=(i,)) for i in range(NC)]
+        ths = [th.Thread(target=worker, args=(i,)) for i in range(nc)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -350,19 +408,39 @@ def run_gpu(args, rank, world, local_rank):
         return e0.elapsed_time(e1), sum(c.kernel_launches for c in ctxs) - l0
 
     throughput_pass(False, steps=2 * NC)  # untimed: worker threads, side streams and flush buffers warm
-    res_ms, launches = throughput_pass(False)
-    e2e_ms, _ = throughput_pass(True)
+    # The timed region of K keyframes is short (tens of ms), so it is REPEATED `repeats` times back to back; every repeat
+    # times exactly K steps, the slowest rank decides per repeat, and the MEDIAN repeat is reported (min / max beside it).
+    R = max(1, args.repeats)
+    res_all, e2e_all, launches = [], [], 0
+    for _ in range(R):
+        ms, launches = throughput_pass(False)
+        res_all.append(ms)
+    for _ in range(R):
+        e2e_all.append(throughput_pass(True)[0])
+    # the same with ONE keyframe in flight (no overlap between keyframes: what a single synchronous caller gets)
+    res1_all = [throughput_pass(False, nc=1)[0] for _ in range(R)] if NC > 1 else list(res_all)
+    e2e1_all = [throughput_pass(True, nc=1)[0] for _ in range(R)] if NC > 1 else list(e2e_all)
+    # parity of the timed path: the label maps the e2e entry point writes for this rank's first frame (checked on rank 0
+    # against the CPU arm's label maps of the same keyframe, below)
+    call(ctx, frames[0][0], frames[0][1], outs[0])
+    gpu_labels0 = outs[0].copy()
     barrier()
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
-    # slowest rank decides
-    res_ms_max, e2e_ms_max, lat_ms_max = max_over_ranks([res_ms, e2e_ms, lat_ms], dist, dev)
+    # slowest rank decides (per repeat)
+    allv = max_over_ranks(res_all + e2e_all + res1_all + e2e1_all + [lat_ms], dist, dev)
+    res_all, e2e_all, res1_all, e2e1_all = (allv[k * R:(k + 1) * R] for k in range(4))
+    lat_ms_max = allv[4 * R]
+    med = lambda v: sorted(v)[len(v) // 2]
+    res_ms_max, e2e_ms_max = med(res_all), med(e2e_all)
 
     if rank == 0:
         value = job_throughput(args.steps, world, res_ms_max)
         e2e = job_throughput(args.steps, world, e2e_ms_max)
+        spread = lambda v: {"median": job_throughput(args.steps, world, med(v)), "min": job_throughput(args.steps, world, max(v)),
+                            "max": job_throughput(args.steps, world, min(v)), "repeats": len(v)}
         peak, peak_src = peaks()
         top = sorted(prof.items(), key=lambda kv: -kv[1][0])
         kernel_table = [{"kernel": n, "ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps,
@@ -380,13 +458,21 @@ def run_gpu(args, rank, world, local_rank):
         dom_name, (dom_ms, dom_cnt) = top[0]
         ab = algo_bytes(dom_name, env)
         ach = ab / (dom_ms / dom_cnt / 1000.0) / 1e9 if ab is not None else None
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full` captures
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            traffic = next((v.get("dram_bytes_per_launch") for k, v in tj.items() if k.split("<")[0] == dom_name.split("<")[0]), None)
+            # exact name first; otherwise the instantiation of that kernel that was captured most often, i.e. the variant
+            # that runs once per mean-field iteration (not the first / last pass variants)
+            cand = [(k, v) for k, v in tj.items() if k == dom_name] or \
+                   [(k, v) for k, v in tj.items() if k.split("<")[0] == dom_name.split("<")[0]]
+            if cand:
+                tk, tv = max(cand, key=lambda kv: kv[1].get("launches_profiled", 0))
+                traffic, traffic_src = tv.get("dram_bytes_per_launch"), tk
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak if ach is not None else None, "traffic": traffic, "peak_source": peak_src,
+                "frac": ach / peak if ach is not None else None, "traffic": traffic,
+                "traffic_kernel": traffic_src if traffic is not None else None,
+                "traffic_ratio": (traffic / ab) if (traffic is not None and ab) else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(ab) if ab is not None else None,
                 "us_per_launch": 1000.0 * dom_ms / dom_cnt,
                 "lattices": [{"d": d, "vertices": V} for d, V in lat_info]}
@@ -400,10 +486,14 @@ def run_gpu(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "every step is preceded by a %d MiB device write (L2 flush; L2 = 126 MB)" % FLUSH_MIB,
                        "frames": "%d distinct synthetic frames per rank" % N_FRAMES,
-                       "inflight": "%d keyframes in flight per GPU (one context + host thread each)" % NC},
+                       "inflight": "%d keyframes in flight per GPU (one context + host thread each)" % NC,
+                       "repeats": "the K-step timed region is repeated %d times; value / e2e are the median repeat" % R},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "keyframes/s", "h2d_bytes_per_step": W * H * 3 + W * H * 2,
                     "d2h_bytes_per_step": 2 * W * H, "ms_per_step": e2e_ms_max / args.steps},
+            "spread": {"value": spread(res_all), "e2e": spread(e2e_all)},
+            "inflight_1": {"value": spread(res1_all), "e2e": spread(e2e1_all),
+                           "note": "one keyframe in flight per GPU: a single synchronous caller, no overlap between keyframes"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "latency": {"ms_per_keyframe": lat_ms_max / args.steps,
@@ -415,39 +505,25 @@ def run_gpu(args, rank, world, local_rank):
                             "(%.3f ms/keyframe vs %.3f ms/keyframe without)" % (lat_ms_prof / args.steps, lat_ms / args.steps),
         }
         if world == 1 and not args.quick:
-            # configs[3] side measurement (not the headline): one local map of 2 M points, both label layers through one
-            # 6-D lattice at the node's kernel widths, 10 mean-field iterations, device time from the library's events
-            NM = 2_000_000
-            xyz, col = synth.local_map(seed=5, n_points=NM)
-            crf = ctx.crf(NM, [8, 9])
-            rng = np.random.default_rng(0)
-            for l, m in enumerate((8, 9)):
-                crf.set_unary(rng.random((NM, m), dtype=np.float32), l)
-            builds = []
-            for rep in range(2):  # the first build also pays for every device allocation of a map of this size
-                if rep:
-                    crf.close()
-                    crf = ctx.crf(NM, [8, 9])
-                    for l, m in enumerate((8, 9)):
-                        crf.set_unary(rng.random((NM, m), dtype=np.float32), l)
-                t0 = time.perf_counter()
-                crf.add_pairwise_xyzrgb(xyz, col, 0.5, 4.0, 10.0)
-                builds.append(time.perf_counter() - t0)
-            build_s = builds[-1]
-            crf.inference(10, unknown=[7, 8], want_Q=False, want_labels=True)
-            line["local_map"] = {"points": NM, "labels": 17, "vertices": crf.lattice_size(0),
-                                 "ms_per_meanfield_iter": ctx.timings()["meanfield_ms"] / 10,
-                                 "lattice_build_ms_incl_h2d": 1000.0 * build_s, "first_build_ms_incl_allocation": 1000.0 * builds[0],
-                                 "note": "generic (unordered point set) path: vertex-major CSR gather splat"}
-            crf.close()
+            line["local_map"] = local_map_bench(ctx, synth, 2_000_000, 0.5, 4.0, peak, "node scales (xyz*0.5, rgb*4)")
+        if world == 1 and not args.quick and not args.no_15m:
+            # BASELINE configs[3]: 50 keyframes fused into one ~15 M-point map, both lattice regimes
+            line["local_map_15m"] = [
+                local_map_bench(ctx, synth, 15_000_000, 0.5, 4.0, peak, "node scales (xyz*0.5, rgb*4): few vertices"),
+                local_map_bench(ctx, synth, 15_000_000, 20.0, 40.0, peak, "fine scales (xyz*20, rgb*40): millions of vertices")]
         if world == 1 and not args.no_cpu and not args.quick:
             import oracle
             oracle.build(ref=False)
             procs = max(1, min(os.cpu_count() or 1, 32))
-            cv, cdt = cpu_throughput(procs, 1)
+            cv, cdt, cpu_labels0 = cpu_throughput(procs, 1, 1, first_seed=frame_seeds(0)[0])
             line["cpu_baseline"] = {"value": cv, "unit": "keyframes/s", "cores": procs, "kind": "port",
                                     "sample": "%d full 640x480 keyframes, one single-thread oracle pipeline per core "
-                                              "(%.1f s)" % (procs, cdt)}
+                                              "(%.1f s compute)" % (procs, cdt)}
+            # the label maps the timed e2e entry point wrote for frame 0 vs the CPU arm's label maps of the same keyframe
+            agree = [float((gpu_labels0[l] == cpu_labels0[l]).mean()) for l in range(2)]
+            line["parity_check"] = {"label_agreement": min(agree), "per_layer": agree, "frame_seed": frame_seeds(0)[0],
+                                    "bar": 0.999, "ok": bool(min(agree) >= 0.999),
+                                    "what": "rss_segment_keyframe (host buffers, the e2e path) vs oracle.keyframe on the same 640x480 frame"}
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()
@@ -464,6 +540,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="skip the keyframes-in-flight sweep and the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-15m", dest="no_15m", action="store_true", help="skip the 15 M-point local-map side measurement")
+    ap.add_argument("--repeats", type=int, default=5, help="repeats of the K-step timed region (median reported)")
     ap.add_argument("--inflight", type=int, default=3,
                     help="keyframes in flight per GPU (one context + host thread each)")
     args = ap.parse_args()

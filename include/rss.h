@@ -75,6 +75,11 @@ rss_status rss_destroy(rss_ctx* ctx);
 rss_status rss_load_forest(rss_ctx* ctx, const char* forest_dat_path);
 rss_status rss_load_forest_memory(rss_ctx* ctx, const void* bytes, size_t size);
 rss_status rss_get_info(const rss_ctx* ctx, rss_info* out);
+/* Host-only parse of a config JSON (Utils::Config + the Segmenter / FeatureExtractor constructors, src/config.cpp,
+ * src/segmenter.cpp:70-127, include/feature_extractor.h:29-39): fills the config-derived fields of rss_info without
+ * touching a CUDA device, so a config can be validated before a context exists.  Same status codes and messages as
+ * rss_create (message via rss_last_error(NULL)). */
+rss_status rss_parse_config(const char* config_json_path, rss_info* out);
 /* message of the last failing call on this context ("" if none); ctx may be NULL for create failures */
 const char* rss_last_error(const rss_ctx* ctx);
 const char* rss_status_string(rss_status s);

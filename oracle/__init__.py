@@ -284,6 +284,29 @@ def features_xyzrgb(xyz, rgb, wxyz, wrgb):
     return f
 
 
+def keyframe(forest, rgb, depth, Kinv, R, t, sigma_xyz, w_gauss, sigma_px, sigma_rgb, w_bilateral, iters, fill=0.0,
+             layers=((8, 7), (9, 8)), stride=2, dmin=0.5, dmax=15.0, cfg=None):
+    """The whole keyframe path of rss_segment_keyframe on the CPU (src/segmenter.cpp:349-434 frame worker, then per layer
+    a DenseCRF with a Gaussian kernel on the back-projected points and a bilateral kernel, :629-657).
+    layers: (label count, "Unknown" label) per layer.  Returns (labels uint8 [L][N], [Q_l (N, M_l)], posteriors)."""
+    depth = np.ascontiguousarray(depth, np.uint16)
+    H, W = depth.shape
+    N = W * H
+    post = segment_frame(cfg or default_config(), forest, stride, rgb, depth, Kinv, R, t, dmin, dmax, fill)
+    xyz = cloud(depth, Kinv, R, t, dmin, dmax).reshape(-1, 3)
+    xyz[np.isnan(xyz[:, 0])] = np.asarray(t, np.float32)
+    f3 = (xyz * np.float32(1.0 / sigma_xyz)).astype(np.float32)
+    f5 = features_bilateral2d(W, H, sigma_px, sigma_px, sigma_rgb, sigma_rgb, sigma_rgb, rgb)
+    labels = np.empty((len(layers), N), np.uint8)
+    Qs, off = [], 0
+    for l, (M, unk) in enumerate(layers):
+        Q = crf_inference(-post[off:off + N * M].reshape(N, M), [(f3, w_gauss), (f5, w_bilateral)], iters)
+        labels[l] = gated_argmax(Q, unk)
+        Qs.append(Q)
+        off += N * M
+    return labels, Qs, post
+
+
 # ------------------------------------------------------------------ the unmodified reference (oracle/_ref)
 _ref = None
 

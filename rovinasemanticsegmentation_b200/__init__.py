@@ -76,6 +76,16 @@ def _calib(Kinv, R, t):
             np.ascontiguousarray(t, np.float32).reshape(3))
 
 
+def parse_config(path):
+    """rss_parse_config: the config-derived fields of Info, parsed on the host (no CUDA device needed)."""
+    lib = load_library()
+    info = Info()
+    st = lib.rss_parse_config(os.fsencode(path), C.byref(info))
+    if st != 0:
+        raise RssError(st, (lib.rss_last_error(None) or b"").decode())
+    return info
+
+
 class Context:
     """One GPU context = the reference Segmenter's constructor state (config + forest), see rss_create."""
 

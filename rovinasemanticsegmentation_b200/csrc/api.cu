@@ -4,6 +4,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <stdexcept>
 
 #include "json_min.hpp"
 #include "kernels.hpp"
@@ -132,7 +133,17 @@ static rss_status load_forest(rss_ctx* ctx, const char* path) {
     std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     return load_forest_bytes(ctx, bytes.data(), bytes.size());
 }
+static rss_status load_forest_bytes_impl(rss_ctx* ctx, const unsigned char* data, size_t size);
+// A truncated or corrupt model must come back as RSS_ERR_MODEL, never as an exception through the extern "C" boundary.
 static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, size_t size) {
+    try {
+        return load_forest_bytes_impl(ctx, data, size);
+    } catch (const std::exception& e) {
+        ctx->forest.loaded = false;
+        return ctx->fail(RSS_ERR_MODEL, std::string("forest: ") + e.what());
+    }
+}
+static rss_status load_forest_bytes_impl(rss_ctx* ctx, const unsigned char* data, size_t size) {
     Reader rd{data, data + size};
     ForestDev& F = ctx->forest;
     const int T = rd.i32();
@@ -144,12 +155,14 @@ static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, siz
     int C[RSS_MAX_LAYERS] = {0};
     for (int t = 0; t < T; t++) {
         const int n = rd.i32();
-        if (!rd.ok || n <= 0) return ctx->fail(RSS_ERR_MODEL, "forest: bad node count");
+        // every node costs at least 12 bytes of split data that must still be in the file: bound n BEFORE allocating
+        if (!rd.ok || n <= 0 || (size_t)n > (size_t)(rd.e - rd.p) / 12) return ctx->fail(RSS_ERR_MODEL, "forest: bad node count");
+        const size_t nb = (size_t)n * 4;
         std::vector<int32_t> feat(n), left(n);
         std::vector<float> thr(n);
-        if (!rd.raw(feat.data(), 4u * n)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated splitFeatures");
-        if (rd.i32() != n || !rd.raw(thr.data(), 4u * n)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated thresholds");
-        if (rd.i32() != n || !rd.raw(left.data(), 4u * n)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated leftChild");
+        if (!rd.raw(feat.data(), nb)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated splitFeatures");
+        if (rd.i32() != n || !rd.raw(thr.data(), nb)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated thresholds");
+        if (rd.i32() != n || !rd.raw(left.data(), nb)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated leftChild");
         const size_t base = nodes.size();
         tree_off[t] = (int)base;
         nodes.resize(base + n);
@@ -165,7 +178,7 @@ static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, siz
             const int c = rd.i32();
             if (!rd.ok || c < 0 || c > 4096) return ctx->fail(RSS_ERR_MODEL, "forest: bad histogram size");
             single[i].resize(c);
-            if (c && !rd.raw(single[i].data(), 4u * c)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated histogram");
+            if (c && !rd.raw(single[i].data(), (size_t)4 * c)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated histogram");
         }
         if (rd.i32() != n) return ctx->fail(RSS_ERR_MODEL, "forest: multi_histograms length mismatch");
         for (int i = 0; i < n; i++) {
@@ -179,7 +192,7 @@ static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, siz
                 lc[k] = c;
                 const size_t o = row.size();
                 row.resize(o + c);
-                if (c && !rd.raw(row.data() + o, 4u * c)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated multi histogram");
+                if (c && !rd.raw(row.data() + o, (size_t)4 * c)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated multi histogram");
             }
             int ll = l;
             if (l == 0 && !single[i].empty()) {  // single-label forest: one layer
@@ -188,10 +201,11 @@ static rss_status load_forest_bytes(rss_ctx* ctx, const unsigned char* data, siz
                 lc[0] = (int)row.size();
             }
             if (nodes[base + i].left == 0) {
-                if (ll == 0) return ctx->fail(RSS_ERR_MODEL, "forest: leaf without histogram");
+                if (ll == 0 || row.empty()) return ctx->fail(RSS_ERR_MODEL, "forest: leaf without histogram");
                 if (L < 0) {
                     L = ll;
                     for (int k = 0; k < ll; k++) { C[k] = lc[k]; sumC += lc[k]; }
+                    if (sumC <= 0) return ctx->fail(RSS_ERR_MODEL, "forest: leaf histograms without classes");
                 } else {
                     if (ll != L) return ctx->fail(RSS_ERR_MODEL, "forest: inconsistent layer count");
                     for (int k = 0; k < ll; k++)
@@ -390,6 +404,36 @@ extern "C" void rss_host_free(void* p) {
 extern "C" rss_status rss_destroy(rss_ctx* ctx) {
     if (!ctx) return RSS_ERR_INVALID;
     free_ctx(ctx);
+    return RSS_OK;
+}
+
+static void info_from_config(const HostConfig& c, rss_info* o) {
+    o->feature_color_patch = c.use_color; o->feature_depth = c.use_depth;
+    o->feature_height = c.use_height; o->feature_normal = c.use_normal;
+    o->patch_size = c.patch_size; o->patch_size_reduce = c.patch_size_reduce; o->feature_length = c.feature_length();
+    o->layer_count = c.layer_count;
+    for (int l = 0; l < c.layer_count; l++) { o->class_counts[l] = c.class_counts[l]; o->total_classes += c.class_counts[l]; }
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) o->unknown_label[l] = l < c.layer_count ? c.unknown_label[l] : 0;
+    o->use_dense_crf = c.use_dense_crf; o->dcrf_iterations = c.dcrf_iters; o->rf_prediction_stride = c.rf_stride;
+    o->dcrf_xyz_kernel = c.dcrf_xyz; o->dcrf_rgb_kernel = c.dcrf_rgb; o->dcrf_kernel_weight = c.dcrf_w;
+    o->depth_min = c.depth_min; o->depth_max = c.depth_max;
+    o->cuda_device = -1;
+}
+extern "C" rss_status rss_parse_config(const char* config_json_path, rss_info* out) {
+    g_create_error.clear();
+    if (!config_json_path || !out) { g_create_error = "null argument"; return RSS_ERR_INVALID; }
+    memset(out, 0, sizeof(*out));
+    HostConfig cfg;
+    std::string err;
+    rss_status st;
+    try {
+        st = load_config(config_json_path, cfg, err);
+    } catch (const std::exception& e) {
+        st = RSS_ERR_IO;
+        err = std::string("config: ") + e.what();
+    }
+    if (st != RSS_OK) { g_create_error = err; return st; }
+    info_from_config(cfg, out);
     return RSS_OK;
 }
 

@@ -9,6 +9,7 @@
 // point-parallel kernel: slice of every lattice + post-scale by norm + Potts + unary + per-layer soft-max
 // (+ the gated argmax on the last iteration).  Q never leaves the device between iterations.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 
@@ -536,21 +537,34 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
     L->potts_w = potts_w;
     L->norm_type = norm_type;
     crf->kernels.push_back(L);
+    // a failed build (allocation, capacity) must not leave a half-built lattice registered: later inference / filter calls
+    // would launch on null or uninitialised buffers.  The buffers go back to the pool.
+    auto fail_build = [&](rss_status rc) {
+        crf->kernels.pop_back();
+        L->tile_TP = 0; L->have_csr = false; L->ordered = false;
+        crf->pool.push_back(L);
+        return rc;
+    };
     const uint64_t maxv = (uint64_t)crf->N * (d + 1);
     uint32_t hcap = next_pow2(std::min<uint64_t>(2 * maxv, 1u << 17));
     if (L->hcap > hcap && L->d == d) hcap = L->hcap;
     if (L->want_hcap > hcap) hcap = L->want_hcap;
+    // test knob: start from a deliberately undersized table so that the overflow -> regrow -> re-run path executes
+    if (const char* dbg = getenv("RSS_DEBUG_HCAP")) {
+        const long v = atol(dbg);
+        if (v >= 64 && L->want_hcap == 0) hcap = next_pow2((uint64_t)v);
+    }
     for (;;) {
         // raster order: the tile kernel does the splat, the vertex-major CSR of the generic path is not needed
         const bool tile_ok = fused_group_supported(crf->Mp / 4);
         rss_status rc = lattice_build(ctx, st, *L, feat_dev, crf->N, d, hcap, crf->Mp, !(raster && tile_ok));
-        if (rc != RSS_OK) return rc;
+        if (rc != RSS_OK) return fail_build(rc);
         rc = lattice_normalization(ctx, st, *L);
-        if (rc != RSS_OK) return rc;
+        if (rc != RSS_OK) return fail_build(rc);
         L->ordered = raster;
         if (raster && tile_ok) {
             rc = lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, crf->grid_w, crf->grid_h);
-            if (rc != RSS_OK) return rc;
+            if (rc != RSS_OK) return fail_build(rc);
         }
         if (!sync) return RSS_OK;
         launch_run_count(ctx, st, *L);
@@ -566,7 +580,7 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
             return RSS_OK;
         }
         if ((uint64_t)hcap >= 2 * next_pow2(2 * maxv) || hcap >= (1u << 30))
-            return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
+            return fail_build(ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow"));
         hcap = (uint32_t)std::min<uint64_t>((uint64_t)hcap * 8, 1u << 30);
     }
 }
@@ -906,6 +920,14 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     const ForestDev& F = ctx->forest;
     if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
+    // the gated argmax takes its "Unknown" labels from the config's layers, the CRF its label counts from the forest:
+    // the two must describe the same layers (segmenter.cpp:81-87 builds both from one config)
+    if (ctx->cfg.layer_count > 0) {
+        if (ctx->cfg.layer_count != F.L) return ctx->fail(RSS_ERR_STATE, "config and forest disagree on the number of label layers");
+        for (int l = 0; l < F.L; l++)
+            if (ctx->cfg.class_counts[l] != F.C[l])
+                return ctx->fail(RSS_ERR_STATE, "config and forest disagree on the class count of a label layer");
+    }
     const int N = W * H;
     rss_crf* crf = ctx->keyframe_crf;
     rss_status st;

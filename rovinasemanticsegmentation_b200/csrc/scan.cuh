@@ -56,9 +56,10 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const uint
 }
 
 // phase 3 (and the whole job when one tile suffices): rescan a tile with its offset
-static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply(const uint32_t* __restrict__ in, size_t n,
+// `in` may alias `out` (in-place scans of rank / deg / nseg): no __restrict__ on the two, so the loads stay coherent
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply(const uint32_t* in, size_t n,
                                                                 const uint32_t* __restrict__ tile_off,
-                                                                uint32_t* __restrict__ out,
+                                                                uint32_t* out,
                                                                 uint32_t* __restrict__ total_out) {
     const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];

@@ -67,3 +67,36 @@ def test_cpp_host_side_builds_without_cuda_headers(lib, tmp_path):
     if not torch.cuda.is_available():
         r = subprocess.run([exe, "--config", CONFIG, "--forest", FOREST, "--frames", "2"], capture_output=True, text=True)
         assert r.returncode != 0 and "keyframe_worker:" in r.stderr
+
+
+def test_parse_config_host_only(lib, tmp_path):
+    """rss_parse_config needs no device: the repo's own config, a missing key (reference message, config.h:13-24), and -
+    where the reference tree is mounted - the reference's resources/config.json fed through UNCHANGED
+    (src/segmenter.cpp:70-127: two layers, 8 + 9 non-negative labels, "Unknown" = 7 / 8)."""
+    import json
+    info = rss.parse_config(CONFIG)
+    assert (info.patch_size, info.patch_size_reduce, info.feature_length) == (77, 11, 366)
+    assert info.layer_count == 2 and list(info.class_counts)[:2] == [8, 9] and list(info.unknown_label)[:2] == [7, 8]
+    cfg = json.load(open(CONFIG))
+    del cfg["feature_normal"]
+    bad = tmp_path / "bad.json"
+    bad.write_text(json.dumps(cfg))
+    with pytest.raises(rss.RssError) as e:
+        rss.parse_config(str(bad))
+    assert e.value.status == 3 and "The key: 'feature_normal' was not found in the config file." in str(e.value)
+    ref = "/root/reference/resources/config.json"
+    if os.path.exists(ref):
+        r = rss.parse_config(ref)
+        assert (r.feature_color_patch, r.feature_depth, r.feature_height, r.feature_normal) == (1, 1, 1, 1)
+        assert (r.patch_size, r.patch_size_reduce, r.feature_length) == (77, 11, 366)
+        assert r.layer_count == 2 and list(r.class_counts)[:2] == [8, 9] and r.total_classes == 17
+        assert list(r.unknown_label)[:2] == [7, 8]
+        assert (r.use_dense_crf, r.dcrf_iterations, r.rf_prediction_stride) == (0, 10, 2)
+        assert (r.dcrf_xyz_kernel, r.dcrf_rgb_kernel, r.dcrf_kernel_weight) == (0.5, 4.0, 10.0)
+        assert (r.depth_min, r.depth_max) == (0.5, 15.0)
+
+
+def test_corrupt_forest_is_an_error_not_a_crash(lib):
+    """node counts are bounded by the bytes left in the file BEFORE anything is allocated, and no exception
+    crosses the C boundary.  (Loading needs a context, hence a GPU; on the CPU box only the export is checked.)"""
+    assert hasattr(lib, "rss_load_forest_memory")

@@ -177,6 +177,33 @@ def test_keyframe_fused(ctx, orc):
         off += N * M
 
 
+@pytest.mark.parametrize("k", [0, 5])
+def test_keyframe_fused_640x480(ctx, orc, k):
+    """The EXACT workload bench.py times (BASELINE configs[1]+[2]: 640x480, bench.KF parameters, the bench's own frame seeds;
+    1080 tiles, two CTA waves, V ~ 40 k + 11 k) against the oracle: frame path + per-layer CRF, 10 iterations.
+    Reference: src/segmenter.cpp:349-434, :639-657."""
+    import bench
+    import rovinasemanticsegmentation_b200 as rss
+    from rovinasemanticsegmentation_b200 import synth
+    W, H = bench.W, bench.H
+    KF = bench.KF
+    rgb, depth = synth.frame(bench.frame_seeds(0)[k], W, H)
+    Kinv, R, t = synth.calibration(W, H)
+    prm = rss.KeyframeParams(KF["sigma_xyz"], KF["w_gauss"], KF["sigma_px"], KF["sigma_rgb"], KF["w_bilateral"], KF["iters"],
+                             KF["fill"])
+    labels, Q = ctx.segment_keyframe(rgb, depth, Kinv, R, t, prm, want_Q=True)
+    l0, Q0, _ = orc.keyframe(orc.Forest(FOREST), rgb, depth, Kinv, R, t, **KF)
+    off, N = 0, W * H
+    for l, M in enumerate((8, 9)):
+        Q1 = Q[off:off + N * M].reshape(N, M)
+        assert np.abs(Q0[l] - Q1).max() <= TOL
+        assert (l0[l] == labels[l]).mean() >= 0.999
+        off += N * M
+    # the resident-frame entry (rgb = depth = NULL), which is what the bench's `value` pass calls, gives the same labels
+    again = ctx.segment_keyframe(None, None, Kinv, R, t, prm, W=W, H=H)
+    assert (again == labels).mean() >= 0.9999  # float atomics in the splat: not bit-reproducible run to run
+
+
 def test_unary_accumulate_from_resident_posteriors(ctx, orc):
     """Frame worker -> map worker without a host round trip: rss_segment_frame leaves the posteriors on the device and
     rss_crf_unary_accumulate(posteriors = NULL) scatters them through the index image (segmenter.cpp:597-616)."""

@@ -295,3 +295,73 @@ def test_normalization_types(ctx, norm_type):
     e = np.exp(tmp - tmp.max(1, keepdims=True))
     assert np.abs(e / e.sum(1, keepdims=True) - Q1).max() <= 1e-4
     crf.close()
+
+
+def test_corrupt_forest_returns_model_error():
+    """ADVICE r1 (api.cu load_forest_bytes): truncated files, absurd node counts and class-less leaves come back as
+    RSS_ERR_MODEL (4) - no bad_alloc through the C boundary, no division by zero."""
+    import struct
+    import rovinasemanticsegmentation_b200 as rss
+    good = open(FOREST, "rb").read()
+    with rss.Context(CONFIG, None, 0) as c:
+        import ctypes
+        lib = c._lib
+        lib.rss_load_forest_memory.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+
+        def load(b):
+            return lib.rss_load_forest_memory(c.h, b, len(b))
+        assert load(good) == 0
+        for cut in (3, 4, 8, 100, len(good) // 2, len(good) - 1):
+            assert load(good[:cut]) == 4, cut
+        # tree count ok, node count 2^30 with no data behind it (used to wrap 4u * n to 0 and allocate 3 x 4 GiB)
+        assert load(struct.pack("<ii", 1, 1 << 30)) == 4
+        assert load(struct.pack("<ii", 1, 0x7fffffff) + b"\0" * 64) == 4
+        # one leaf node whose multi-histograms all have size 0 (sumC == 0 used to divide by zero)
+        one = struct.pack("<i", 1)                                    # T
+        one += struct.pack("<ii", 1, 0) + struct.pack("<if", 1, 0.0) + struct.pack("<ii", 1, 0)  # feat, thr, left (leaf)
+        one += struct.pack("<ii", 1, 0)                               # histograms: 1 node, 0 floats
+        one += struct.pack("<iiii", 1, 2, 0, 0)                       # multi: 1 node, 2 layers of 0 classes
+        assert load(one) == 4
+        assert load(good) == 0 and c.info.num_trees == 4               # the context is still usable
+
+
+def test_config_forest_mismatch_is_rejected():
+    """ADVICE r1 (crf.cu rss_segment_keyframe): a 2-layer config with the 3-layer forest is a state error, not a silent
+    gate label 0."""
+    import rovinasemanticsegmentation_b200 as rss
+    from conftest import GOLDEN
+    from rovinasemanticsegmentation_b200 import synth
+    W, H = 64, 48
+    rgb, depth = synth.frame(3, W, H)
+    Kinv, R, t = synth.calibration(W, H)
+    with rss.Context(CONFIG, os.path.join(GOLDEN, "forest_3layer.dat"), 0) as c:
+        with pytest.raises(rss.RssError) as e:
+            c.segment_keyframe(rgb, depth, Kinv, R, t, rss.KeyframeParams(0.05, 3.0, 80.0, 13.0, 10.0, 2, 0.0))
+        assert e.value.status == 7 and "disagree" in str(e.value)
+
+
+def test_hash_overflow_retry_path(orc, monkeypatch):
+    """The keyframe path builds its lattices without a host sync; an undersized hash table raises a device flag, the host
+    regrows the table (x4) and re-runs the CRF (crf.cu, rss_segment_keyframe retry loop).  RSS_DEBUG_HCAP forces the
+    first table to be far too small so that the path actually runs; the result must still match the oracle."""
+    import rovinasemanticsegmentation_b200 as rss
+    from rovinasemanticsegmentation_b200 import synth
+    W, H = 320, 240
+    rgb, depth = synth.frame(77, W, H)
+    Kinv, R, t = synth.calibration(W, H)
+    KF = dict(sigma_xyz=0.05, w_gauss=3.0, sigma_px=80.0, sigma_rgb=13.0, w_bilateral=10.0, iters=5, fill=0.0)
+    prm = rss.KeyframeParams(*[KF[k] for k in ("sigma_xyz", "w_gauss", "sigma_px", "sigma_rgb", "w_bilateral", "iters", "fill")])
+    monkeypatch.setenv("RSS_DEBUG_HCAP", "2048")
+    with rss.Context(CONFIG, FOREST, 0) as c:
+        labels, Q = c.segment_keyframe(rgb, depth, Kinv, R, t, prm, want_Q=True)
+        V = [c.keyframe_lattice_info(k)[1] for k in range(2)]
+        assert max(V) > 1024  # the 2048-slot table (capacity 1024 vertices) cannot have been enough
+        # second keyframe on the same context: the regrown capacity is reused, same answer
+        labels2 = c.segment_keyframe(rgb, depth, Kinv, R, t, prm)
+    monkeypatch.delenv("RSS_DEBUG_HCAP")
+    l0, Q0, _ = orc.keyframe(orc.Forest(FOREST), rgb, depth, Kinv, R, t, **KF)
+    off, N = 0, W * H
+    for l, M in enumerate((8, 9)):
+        assert np.abs(Q0[l] - Q[off:off + N * M].reshape(N, M)).max() <= 1e-4
+        assert (l0[l] == labels[l]).mean() >= 0.999 and (l0[l] == labels2[l]).mean() >= 0.999
+        off += N * M
