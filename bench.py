@@ -222,9 +222,13 @@ def algo_bytes(name, env):
         "slice_softmax_kernel<MP>": sum(8 * (d + 1) * N + 4 * N + 4 * M * V for d, V in lat) + 8 * M * N,
         # fused path (meanfield.cu): one point kernel per iteration = slice (vertex ids + weights, norms, unique rows) +
         # unary + tile-local splat (pair list, unique rows out); one cooperative blur for all lattices
-        "meanfield_tile_kernel": 4 * M * N + sum(16 * (d + 1) * N + 4 * N + 8 * M * V for d, V in lat),
+        # one point kernel per iteration: unary rows + per (point, corner) slice weight (4 B) and row slot (2 B) + the
+        # distinct value rows in; splat pairs (8 B per (point, corner)) in, the distinct value rows out
+        "meanfield_point_kernel": 4 * M * N + sum(14 * (d + 1) * N + 8 * M * V for d, V in lat),
+        "meanfield_point_kernel<first>": 4 * M * N + sum(8 * (d + 1) * N + 4 * M * V for d, V in lat),
+        "meanfield_point_kernel<last>": 8 * M * N + 2 * N + sum(6 * (d + 1) * N + 4 * M * V for d, V in lat),
         "blur_multi_coop_kernel": sum((d + 1) * (8 * M * V + 8 * V) + 4 * M * V for d, V in lat),
-        "tile_csr_build_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * N + 16 * (d + 1) * N),
+        "tile_csr_build_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * N + (8 + 6) * (d + 1) * N + 12 * V),
         "splat_ones_runs_kernel<D>": mean(lambda d, V: 8 * (d + 1) * N + 4 * V),
         "slice_kernel": mean(lambda d, V: 8 * (d + 1) * N + 4 * V + 4 * N),
         # two hash look-ups per (vertex, axis): the vertex key once, the int2 neighbour pair out, the two probed slots in

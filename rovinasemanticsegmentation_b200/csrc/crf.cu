@@ -34,7 +34,8 @@ constexpr int CRF_MAX_CH = 32;
 
 struct LayerSpec {
     int n_layers;
-    int off[RSS_MAX_LAYERS + 1];
+    int off[RSS_MAX_LAYERS + 1];  // first channel of the layer in the device row (a multiple of 4)
+    int end[RSS_MAX_LAYERS];      // one past its last label (channels between end[l] and off[l + 1] are padding)
     int unknown[RSS_MAX_LAYERS];  // < 0: plain argmax
 };
 struct SliceArgs {
@@ -69,7 +70,7 @@ __device__ __forceinline__ float group_sum(float v) {
 __device__ __forceinline__ void softmax_layers(float (&t)[4], int c0, const LayerSpec& ls) {
     float out[4] = {0.f, 0.f, 0.f, 0.f};
     for (int l = 0; l < ls.n_layers; l++) {
-        const int a = ls.off[l], b = ls.off[l + 1];
+        const int a = ls.off[l], b = ls.end[l];
         float mx = -INFINITY;
 #pragma unroll
         for (int q = 0; q < 4; q++)
@@ -97,7 +98,7 @@ __device__ __forceinline__ void softmax_layers(float (&t)[4], int c0, const Laye
 __device__ __forceinline__ void write_labels(const float (&q)[4], int c0, int g, const LayerSpec& ls, int i, int N,
                                              uint8_t* __restrict__ labels) {
     for (int l = 0; l < ls.n_layers; l++) {
-        const int a = ls.off[l], b = ls.off[l + 1];
+        const int a = ls.off[l], b = ls.end[l];
         const bool gated = ls.unknown[l] >= 0;
         float bv = gated ? (float)(2.0 / (double)(b - a)) : -INFINITY;
         int best = 1 << 20;  // "no label passed the gate"
@@ -142,8 +143,13 @@ __global__ void __launch_bounds__(256) softmax_init_kernel(const float* __restri
 // (MP = padded channel count, compile time), rows are read as float4.
 template <int MP>
 __device__ __forceinline__ void softmax_regs(float (&t)[MP], const LayerSpec& ls) {
+    unsigned live = 0;  // channels that belong to a layer; the others (padding) come out as 0
+    for (int l = 0; l < ls.n_layers; l++) live |= (ls.end[l] >= 32 ? 0xffffffffu : ((1u << ls.end[l]) - 1u)) & ~((1u << ls.off[l]) - 1u);
+#pragma unroll
+    for (int c = 0; c < MP; c++)
+        if (!((live >> c) & 1u)) t[c] = 0.f;
     for (int l = 0; l < ls.n_layers; l++) {
-        const int a = ls.off[l], b = ls.off[l + 1];
+        const int a = ls.off[l], b = ls.end[l];
         float mx = -INFINITY;
 #pragma unroll
         for (int c = 0; c < MP; c++)
@@ -224,11 +230,10 @@ __global__ void __launch_bounds__(128) slice_softmax_kernel(SliceArgs sa, const 
     float4* qp = reinterpret_cast<float4*>(Q + (size_t)i * MP);
 #pragma unroll
     for (int g = 0; g < MP / 4; g++)
-        qp[g] = make_float4(4 * g < M ? t[4 * g] : 0.f, 4 * g + 1 < M ? t[4 * g + 1] : 0.f, 4 * g + 2 < M ? t[4 * g + 2] : 0.f,
-                            4 * g + 3 < M ? t[4 * g + 3] : 0.f);
+        qp[g] = make_float4(t[4 * g], t[4 * g + 1], t[4 * g + 2], t[4 * g + 3]);
     if (labels) {
         for (int l = 0; l < ls.n_layers; l++) {
-            const int a = ls.off[l], b = ls.off[l + 1];
+            const int a = ls.off[l], b = ls.end[l];
             const bool gated = ls.unknown[l] >= 0;
             float bv = gated ? (float)(2.0 / (double)(b - a)) : -INFINITY;  // segmenter.cpp:647
             int best = gated ? ls.unknown[l] : 0;
@@ -261,19 +266,26 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float* __restrict__ Q
 }
 
 // layout helpers between the reference's per-layer matrices ([N][M_l]) and the padded interleaved device layout
-__global__ void __launch_bounds__(256) interleave_kernel(const float* __restrict__ src, int N, int Ml, int Mp, int off,
-                                                         float scale, float* __restrict__ dst) {
+// host: rows of hstride floats, the layer's Ml labels at column hoff; device: rows of Mp floats, the layer at column off
+__global__ void __launch_bounds__(256) interleave_kernel(const float* __restrict__ src, int N, int Ml, int hstride, int hoff,
+                                                         int Mp, int off, float scale, float* __restrict__ dst) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)N * Ml) return;
     const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
-    dst[(size_t)i * Mp + off + c] = scale * src[gid];
+    dst[(size_t)i * Mp + off + c] = scale * src[(size_t)i * hstride + hoff + c];
 }
 __global__ void __launch_bounds__(256) deinterleave_kernel(const float* __restrict__ src, int N, int Ml, int Mp, int off,
-                                                           float* __restrict__ dst) {
+                                                           int hstride, int hoff, float* __restrict__ dst) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)N * Ml) return;
     const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
-    dst[gid] = src[(size_t)i * Mp + off + c];
+    dst[(size_t)i * hstride + hoff + c] = src[(size_t)i * Mp + off + c];
+}
+// unary rows start as energy 0 on the label channels and +inf on the padding channels of every layer (bit c of live:
+// channel c is a label), so that exp(-unary - max) of a padding channel is 0 in every soft-max
+__global__ void __launch_bounds__(256) unary_init_kernel(float* __restrict__ unary, size_t n, int Mp, unsigned live) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) unary[i] = ((live >> (unsigned)(i % Mp)) & 1u) ? 0.f : INFINITY;
 }
 // segmenter.cpp:597-616: unaries(c, idx) += posterior[pixel*C + c] for idx >= 0.  The CRF stores ENERGIES
 // (= -unaries, segmenter.cpp:642), so the log-posterior is subtracted.
@@ -331,7 +343,8 @@ __global__ void __launch_bounds__(256) feat_frame_xyz_kernel(int N, const float4
 static LayerSpec make_layers(const rss_crf* crf, const int* unknown) {
     LayerSpec ls;
     ls.n_layers = crf->n_layers;
-    for (int l = 0; l <= RSS_MAX_LAYERS; l++) ls.off[l] = l <= crf->n_layers ? crf->moff[l] : crf->Mtot;
+    for (int l = 0; l <= RSS_MAX_LAYERS; l++) ls.off[l] = l <= crf->n_layers ? crf->moff[l] : crf->Mp;
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) ls.end[l] = l < crf->n_layers ? crf->moff[l] + crf->M[l] : crf->Mp;
     for (int l = 0; l < RSS_MAX_LAYERS; l++) ls.unknown[l] = (unknown && l < crf->n_layers) ? unknown[l] : -1;
     return ls;
 }
@@ -344,7 +357,7 @@ static bool crf_fused_order(const rss_crf* crf, int* first, int* second) {
     const int K = (int)crf->kernels.size();
     if (K < 1 || K > FUSED_MAX_LAT) return false;
     const int G = crf->Mp / 4;
-    const TileMap tm = fused_tile_map(G, crf->N, crf->grid_w, crf->grid_h, crf->ctx->sm_count);
+    const TileMap tm = fused_tile_map(crf->N, crf->grid_w, crf->grid_h);
     for (const Lattice* L : crf->kernels)
         if (!L->ordered || L->tile_TP != tm.TP || L->tile_W != tm.W) return false;
     if (K == 1) {
@@ -365,23 +378,14 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     const LayerSpec ls0 = make_layers(crf, unknown);
     FusedLayers ls;
     ls.n_layers = ls0.n_layers;
-    for (int l = 0; l <= RSS_MAX_LAYERS; l++) ls.off[l] = ls0.off[l];
     for (int l = 0; l < RSS_MAX_LAYERS; l++) {
+        const int Ml = l < crf->n_layers ? crf->M[l] : 0;
+        ls.off[l] = ls0.off[l];
+        ls.count[l] = Ml;
+        ls.gmask[l] = 0;
+        for (int g = ls0.off[l] / 4; l < crf->n_layers && g < (ls0.off[l] + Ml + 3) / 4; g++) ls.gmask[l] |= 1u << g;
         ls.unknown[l] = ls0.unknown[l];
-        const int Ml = ls0.off[l + 1] - ls0.off[l];
         ls.gate[l] = (ls0.unknown[l] >= 0 && Ml > 0) ? (float)(2.0 / (double)Ml) : -INFINITY;  // segmenter.cpp:647
-    }
-    ls.aligned = 1;
-    for (int l = 0; l < ls.n_layers; l++)
-        if (ls.off[l] % 4) ls.aligned = 0;
-    for (int gq = 0; gq < 8; gq++) {
-        ls.group_lmask[gq] = 0; ls.group_valid[gq] = 0; ls.group_layer[gq] = -1;
-        for (int l = 0; l < ls.n_layers; l++) {
-            for (int k = 0; k < 4; k++)
-                if (4 * gq + k >= ls.off[l] && 4 * gq + k < ls.off[l + 1]) ls.group_lmask[gq] |= 1u << (4 * l + k);
-            if (4 * gq >= ls.off[l] && 4 * gq < ls.off[l + 1]) ls.group_layer[gq] = l;
-        }
-        if (ls.group_layer[gq] >= 0) ls.group_valid[gq] = (ls.group_lmask[gq] >> (4 * ls.group_layer[gq])) & 15u;
     }
     DevBuf* tgt[FUSED_MAX_LAT];
     DevBuf* spare[FUSED_MAX_LAT];
@@ -391,8 +395,7 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     ba.K = K;
     for (int k = 0; k < FUSED_MAX_LAT; k++) {
         if (k >= K) {
-            fa.lat[k] = FusedLat{}; fa.counts[k] = nullptr; fa.pairs[k] = nullptr; fa.ent_meta[k] = nullptr;
-            fa.tile_nent[k] = nullptr;
+            fa.lat[k] = FusedLat{};
             continue;
         }
         Lattice& L = *Ls[k];
@@ -400,13 +403,10 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
         spare[k] = L.splat_target ? &L.val_a : &L.val_b;
         res[k] = &L.val_c;
         FusedLat& f = fa.lat[k];
-        f.offsets = L.offsets.as<int>(); f.bary = L.bary.as<float>(); f.norm = L.norm.as<float>();
-        f.potts = L.potts_w; f.alpha = lattice_alpha(L.d);
-        f.pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
-        f.post = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_AFTER;
-        fa.counts[k] = L.counts.as<uint32_t>();
-        fa.pairs[k] = L.tile_pairs.as<uint2>(); fa.ent_meta[k] = L.tile_ent_meta.as<int2>();
-        fa.tile_nent[k] = L.tile_nent.as<int>();
+        f.pt_w = L.tile_pt_w.as<float>(); f.pt_slot = L.tile_pt_slot.as<uint16_t>();
+        f.pairs = L.tile_pairs.as<uint2>(); f.ent_meta = L.tile_ent_meta.as<int2>();
+        f.tile_vert = L.tile_vert.as<int>(); f.tile_info = L.tile_info.as<int2>();
+        f.counts = L.counts.as<uint32_t>();
         ba.nbr[k] = L.nbr.as<int2>(); ba.counts[k] = L.counts.as<uint32_t>(); ba.d1[k] = L.d + 1; ba.vcap[k] = L.vcap;
     }
     const int d1a = Ls[0]->d + 1, d1b = K > 1 ? Ls[1]->d + 1 : 0;
@@ -414,15 +414,15 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     const float* U = crf->unary.as<float>();
     float* Q = crf->Q.as<float>();
     Lattice& L0 = *Ls[0];
-    const TileMap tm = fused_tile_map(G, N, crf->grid_w, crf->grid_h, ctx->sm_count);
+    const TileMap tm = fused_tile_map(N, crf->grid_w, crf->grid_h);
     // pass 0: Q0 = expAndNormalize(-unary) and its splat
     for (int k = 0; k < K; k++) { fa.lat[k].vin = nullptr; fa.lat[k].vout = tgt[k]->as<float>(); }
-    launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, nullptr, tm, G, ls, 2);
+    RSS_CU(ctx, launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, nullptr, tm, G, ls, 2));
     for (int it = 0; it < iters; it++) {
         for (int k = 0; k < K; k++) {
             ba.ping[k] = tgt[k]->as<float4>(); ba.pong[k] = spare[k]->as<float4>(); ba.zero[k] = res[k]->as<float4>();
         }
-        launch_blur_multi(ctx, s0, ba, G, L0.counts.as<unsigned int>() + 8, L0.barrier_base);
+        RSS_CU(ctx, launch_blur_multi(ctx, s0, ba, G, L0.counts.as<unsigned int>() + 8, L0.barrier_base));
         L0.barrier_base += (unsigned int)(maxd1 - 1) * (unsigned int)blur_multi_grid(ctx);
         for (int k = 0; k < K; k++) {
             DevBuf* X = (ba.d1[k] % 2 == 0) ? tgt[k] : spare[k];  // blurred result
@@ -433,7 +433,7 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
             fa.lat[k].vout = tgt[k]->as<float>();
         }
         const bool last = it == iters - 1;
-        launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, last ? labels_dev : nullptr, tm, G, ls, last ? (1 | 4) : (1 | 2));
+        RSS_CU(ctx, launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, last ? labels_dev : nullptr, tm, G, ls, last ? (1 | 4) : (1 | 2)));
     }
     // restore the two-table convention of the generic path: val_a = the all-zero table, splat_target = 0
     for (int k = 0; k < K; k++) {
@@ -622,27 +622,44 @@ void crf_release_cached(rss_ctx* ctx) {
     ctx->keyframe_crf = nullptr;
 }
 
+static void unary_clear(rss_crf* crf) {
+    unsigned live = 0;
+    for (int l = 0; l < crf->n_layers; l++)
+        for (int c = crf->moff[l]; c < crf->moff[l] + crf->M[l]; c++) live |= 1u << c;
+    const size_t n = (size_t)crf->N * crf->Mp;
+    rss_ctx* ctx = crf->ctx;
+    RSS_LAUNCH(ctx, unary_init_kernel, (int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, ctx->s0, crf->unary.as<float>(), n,
+               crf->Mp, live);
+}
 rss_status crf_new(rss_ctx* ctx, int N, int n_layers, const int* M, rss_crf** out) {
     if (!ctx || !out) return RSS_ERR_INVALID;
     if (N < 1 || n_layers < 1 || n_layers > RSS_MAX_LAYERS || !M) return ctx->fail(RSS_ERR_INVALID, "bad CRF dimensions");
     rss_crf* crf = new rss_crf();
     crf->ctx = ctx; crf->N = N; crf->n_layers = n_layers;
-    int off = 0;
+    int off = 0, hoff = 0;
     for (int l = 0; l < n_layers; l++) {
         if (M[l] < 1) { delete crf; return ctx->fail(RSS_ERR_INVALID, "layer with no labels"); }
         crf->M[l] = M[l];
         crf->moff[l] = off;
-        off += M[l];
+        crf->hoff[l] = hoff;
+        off += (M[l] + 3) / 4 * 4;  // every layer starts on a float4 group
+        hoff += M[l];
     }
-    for (int l = n_layers; l <= RSS_MAX_LAYERS; l++) crf->moff[l] = off;
-    crf->Mtot = off;
-    crf->Mp = (off + 3) / 4 * 4;
-    if (crf->Mp > CRF_MAX_CH) { delete crf; return ctx->fail(RSS_ERR_INVALID, "more than 32 labels in total are not supported"); }
+    for (int l = n_layers; l <= RSS_MAX_LAYERS; l++) { crf->moff[l] = off; crf->hoff[l] = hoff; }
+    crf->Mtot = hoff;
+    crf->Mp = off;
+    if (crf->Mp > CRF_MAX_CH) {
+        delete crf;
+        return ctx->fail(RSS_ERR_INVALID, "more than 32 label channels (every layer rounded up to 4) are not supported");
+    }
     cudaError_t e = crf->unary.reserve((size_t)N * crf->Mp * 4);
     if (e == cudaSuccess) e = crf->Q.reserve((size_t)N * crf->Mp * 4);
     if (e == cudaSuccess) e = crf->labels.reserve((size_t)N * n_layers);
     if (e == cudaSuccess) e = crf->scratch.reserve((size_t)N * (crf->Mp + 4) * 4);
-    if (e == cudaSuccess) e = cudaMemsetAsync(crf->unary.ptr, 0, (size_t)N * crf->Mp * 4, ctx->s0);
+    if (e == cudaSuccess) {
+        unary_clear(crf);
+        e = cudaGetLastError();
+    }
     for (int k = 0; k < 4 && e == cudaSuccess; k++) {
         // lattice construction runs beside the frame path and is on the keyframe's critical path: high priority
         int prio_lo = 0, prio_hi = 0;
@@ -686,7 +703,7 @@ extern "C" rss_status rss_crf_set_unary(rss_crf* crf, int layer, const float* U)
     const int Ml = crf->M[layer];
     RSS_CU(ctx, cudaMemcpyAsync(crf->scratch.ptr, U, (size_t)crf->N * Ml * 4, cudaMemcpyHostToDevice, ctx->s0));
     RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)crf->N * Ml, 256), 256, 0, ctx->s0, crf->scratch.as<float>(),
-               crf->N, Ml, crf->Mp, crf->moff[layer], 1.0f, crf->unary.as<float>());
+               crf->N, Ml, Ml, 0, crf->Mp, crf->moff[layer], 1.0f, crf->unary.as<float>());
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     crf->unary_set = true;
     return RSS_OK;
@@ -758,15 +775,22 @@ extern "C" rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     Lattice& L = *crf->kernels[k];
     const int N = crf->N, M = crf->Mtot, Mp = crf->Mp;
-    // scratch: [N][Mp] padded input, followed by the [N][M] host-layout staging area
+    // scratch: [N][Mp] input in the device channel layout; feat_stage: the [N][M] host-layout matrix, then the [N][Mp]
+    // filtered rows
     float* padded = crf->scratch.as<float>();
-    RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * M * 4));
+    RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * (M + Mp) * 4));
     float* stage = crf->feat_stage.as<float>();
+    float* sliced = stage + (size_t)N * M;
     RSS_CU(ctx, cudaMemsetAsync(padded, 0, (size_t)N * Mp * 4, ctx->s0));
     RSS_CU(ctx, cudaMemcpyAsync(stage, in, (size_t)N * M * 4, cudaMemcpyHostToDevice, ctx->s0));
-    RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)N * M, 256), 256, 0, ctx->s0, stage, N, M, Mp, 0, 1.0f, padded);
+    for (int l = 0; l < crf->n_layers; l++)
+        RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, stage, N, crf->M[l], M,
+                   crf->hoff[l], Mp, crf->moff[l], 1.0f, padded);
     float* vals = lattice_splat_blur(ctx, ctx->s0, L, padded, Mp, nullptr, Mp);
-    lattice_slice(ctx, ctx->s0, L, vals, M, Mp, M <= 2 ? 1 : 0, stage, M);
+    lattice_slice(ctx, ctx->s0, L, vals, Mp, Mp, M <= 2 ? 1 : 0, sliced, Mp);
+    for (int l = 0; l < crf->n_layers; l++)
+        RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, sliced, N, crf->M[l], Mp,
+                   crf->moff[l], M, crf->hoff[l], stage);
     RSS_CU(ctx, cudaMemcpyAsync(out, stage, (size_t)N * M * 4, cudaMemcpyDeviceToHost, ctx->s0));
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     return RSS_OK;
@@ -782,14 +806,14 @@ static rss_status crf_fetch(rss_crf* crf, int layer, float* Q, uint8_t* labels) 
             float* dstQ = Q;
             for (int l = 0; l < crf->n_layers; l++) {
                 RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0,
-                           crf->Q.as<float>(), N, crf->M[l], crf->Mp, crf->moff[l], crf->scratch.as<float>());
+                           crf->Q.as<float>(), N, crf->M[l], crf->Mp, crf->moff[l], crf->M[l], 0, crf->scratch.as<float>());
                 RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
                 RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
                 dstQ += (size_t)N * crf->M[l];
             }
         } else {
             RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[layer], 256), 256, 0, ctx->s0,
-                       crf->Q.as<float>(), N, crf->M[layer], crf->Mp, crf->moff[layer], crf->scratch.as<float>());
+                       crf->Q.as<float>(), N, crf->M[layer], crf->Mp, crf->moff[layer], crf->M[layer], 0, crf->scratch.as<float>());
             RSS_CU(ctx, cudaMemcpyAsync(Q, crf->scratch.ptr, (size_t)N * crf->M[layer] * 4, cudaMemcpyDeviceToHost, ctx->s0));
         }
     }
@@ -865,7 +889,7 @@ extern "C" rss_status rss_crf_unary_reset(rss_crf* crf) {
     if (!crf) return RSS_ERR_INVALID;
     rss_ctx* ctx = crf->ctx;
     RSS_CU(ctx, cudaSetDevice(ctx->device));
-    RSS_CU(ctx, cudaMemsetAsync(crf->unary.ptr, 0, (size_t)crf->N * crf->Mp * 4, ctx->s0));
+    unary_clear(crf);
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     return RSS_OK;
 }
@@ -892,7 +916,7 @@ extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx,
     }
     for (int l = 0; l < crf->n_layers; l++) {
         RSS_LAUNCH(ctx, unary_accumulate_kernel, rss_div_up((long long)npix * crf->M[l], 256), 256, 0, ctx->s0, idx_dev, npix,
-                   post_dev + (size_t)npix * crf->moff[l], crf->M[l], crf->Mp, crf->moff[l], crf->N, crf->unary.as<float>());
+                   post_dev + (size_t)npix * crf->hoff[l], crf->M[l], crf->Mp, crf->moff[l], crf->N, crf->unary.as<float>());
     }
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     crf->unary_set = true;
@@ -997,7 +1021,7 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
             float* dstQ = Qout;
             for (int l = 0; l < crf->n_layers; l++) {
                 RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0,
-                           crf->Q.as<float>(), N, crf->M[l], crf->Mp, crf->moff[l], crf->scratch.as<float>());
+                           crf->Q.as<float>(), N, crf->M[l], crf->Mp, crf->moff[l], crf->M[l], 0, crf->scratch.as<float>());
                 RSS_CU(ctx, cudaMemcpyAsync(dstQ, crf->scratch.ptr, (size_t)N * crf->M[l] * 4, cudaMemcpyDeviceToHost, ctx->s0));
                 RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
                 dstQ += (size_t)N * crf->M[l];

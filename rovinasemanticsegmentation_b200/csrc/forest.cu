@@ -88,6 +88,7 @@ struct LayerDims {
     int L;
     int C[RSS_MAX_LAYERS];
     int coff[RSS_MAX_LAYERS];  // class offset of the layer inside a sumC row
+    int uoff[RSS_MAX_LAYERS];  // channel offset of the layer inside a CRF unary row (layers padded to 4 channels)
 };
 __global__ void __launch_bounds__(256) lowres_scatter_kernel(const float* __restrict__ post, int sumC,
                                                              const int* __restrict__ xs, const int* __restrict__ ys,
@@ -106,11 +107,13 @@ __global__ void __launch_bounds__(256) lowres_scatter_kernel(const float* __rest
 static LayerDims make_dims(int L, const int* C) {
     LayerDims d;
     d.L = L;
-    int off = 0;
+    int off = 0, uoff = 0;
     for (int l = 0; l < RSS_MAX_LAYERS; l++) {
         d.C[l] = l < L ? C[l] : 0;
         d.coff[l] = off;
+        d.uoff[l] = uoff;
         off += d.C[l];
+        uoff += (d.C[l] + 3) / 4 * 4;  // the CRF's device rows start every layer on a float4 group (lattice.cuh, rss_crf)
     }
     return d;
 }
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__
         const float* r01 = src + ((size_t)y0 * gw + sx1) * C;
         const float* r10 = src + ((size_t)y1 * gw + sx) * C;
         const float* r11 = src + ((size_t)y1 * gw + sx1) * C;
-        float* o = UNARY ? out + (size_t)p * Mp + ld.coff[l] : out + (size_t)W * H * ld.coff[l] + (size_t)p * C;
+        float* o = UNARY ? out + (size_t)p * Mp + ld.uoff[l] : out + (size_t)W * H * ld.coff[l] + (size_t)p * C;
         for (int cl = 0; cl < C; cl++) {
             const float h0 = __fadd_rn(__fmul_rn(__ldg(r00 + cl), a0), __fmul_rn(__ldg(r01 + cl), a1));
             const float h1 = __fadd_rn(__fmul_rn(__ldg(r10 + cl), a0), __fmul_rn(__ldg(r11 + cl), a1));

@@ -364,14 +364,17 @@ __global__ void __launch_bounds__(512) splat_kernel(const int* __restrict__ seg_
 // one launch per axis: the large-lattice path (value tables beyond L2 reach of one cluster)
 __global__ void __launch_bounds__(256) blur_kernel(const float4* __restrict__ src, float4* __restrict__ dst,
                                                    const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
-                                                   int G) {
+                                                   int G, int vcap) {
     const uint32_t V = counts[0];
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (counts[1] || gid >= (long long)V * G) return;
     const uint32_t v = (uint32_t)(gid / G);
     const int g = (int)(gid - (long long)v * G);
     const int2 nb = __ldg(nbr + v);
-    dst[(size_t)v * G + g] = blur_item(src[(size_t)v * G + g], src[(size_t)nb.x * G + g], src[(size_t)nb.y * G + g]);
+    // a missing neighbour is the zero row (index vcap): skip the load, the row is hot enough to serialise on one L2 slice
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    dst[(size_t)v * G + g] = blur_item(src[(size_t)v * G + g], nb.x != vcap ? src[(size_t)nb.x * G + g] : z,
+                                       nb.y != vcap ? src[(size_t)nb.y * G + g] : z);
 }
 __global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p, const uint32_t* __restrict__ counts, int G) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,7 +401,9 @@ __global__ void __launch_bounds__(512) blur_coop_kernel(float4* __restrict__ a, 
         for (uint32_t it = tid; it < items; it += nthr) {
             const uint32_t v = it / (uint32_t)G, g = it - v * (uint32_t)G;
             const int2 nb = __ldg(nb_j + v);
-            const float4 o = __ldcg(src + it), x = __ldcg(src + (size_t)nb.x * G + g), y = __ldcg(src + (size_t)nb.y * G + g);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 o = __ldcg(src + it), x = nb.x != (int)vcap ? __ldcg(src + (size_t)nb.x * G + g) : z,
+                         y = nb.y != (int)vcap ? __ldcg(src + (size_t)nb.y * G + g) : z;
             __stcg(dst + it, blur_item(o, x, y));
         }
         grid_barrier(barrier, barrier_base + (unsigned int)(j + 1) * gridDim.x);
@@ -606,7 +611,7 @@ float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float
         for (int j = 0; j < d1; j++) {
             RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st,
                        reinterpret_cast<const float4*>(s), reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap,
-                       L.counts.as<uint32_t>(), G);
+                       L.counts.as<uint32_t>(), G, (int)L.vcap);
             float* t = s; s = d; d = t;
         }
         RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st, reinterpret_cast<float4*>(d),
@@ -657,7 +662,7 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
     float* d = b;
     for (int j = 0; j < d1; j++) {
         RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<const float4*>(s),
-                   reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), 1);
+                   reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), 1, (int)L.vcap);
         float* t = s; s = d; d = t;
     }
     lattice_slice(ctx, st, L, s, 1, 4, 1, norm, 1);
@@ -671,18 +676,26 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
     return RSS_OK;
 }
 
-// tile-local CSR for the fused mean-field kernel (after the normalisation: the pre-scale is folded into the weights)
+// per-tile data of the fused mean-field kernel (after the normalisation: pre- / post-scale, Potts weight and slice scale
+// are folded into the weights)
 rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h) {
-    const TileMap tm = fused_tile_map(G, L.N, grid_w, grid_h, ctx->sm_count);
+    const TileMap tm = fused_tile_map(L.N, grid_w, grid_h);
     const int d1 = L.d + 1;
     const size_t ntiles = (size_t)tm.ntiles, cap = ntiles * tm.TP * d1;
     RSS_CU(ctx, L.tile_pairs.reserve(cap * sizeof(uint2)));
     RSS_CU(ctx, L.tile_ent_meta.reserve(cap * sizeof(int2)));
-    RSS_CU(ctx, L.tile_nent.reserve(ntiles * 4));
+    RSS_CU(ctx, L.tile_vert.reserve(cap * sizeof(int)));
+    RSS_CU(ctx, L.tile_pt_w.reserve(cap * sizeof(float)));
+    RSS_CU(ctx, L.tile_pt_slot.reserve(cap * sizeof(uint16_t)));
+    RSS_CU(ctx, L.tile_info.reserve(ntiles * sizeof(int2)));
     const bool pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
-    launch_tile_csr_build(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), pre ? L.norm.as<float>() : nullptr, tm, d1, G * 16,
-                          L.counts.as<uint32_t>(), L.tile_pairs.as<uint2>(), L.tile_ent_meta.as<int2>(),
-                          L.tile_nent.as<int>());
+    const bool post = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_AFTER;
+    TileCsrOut out;
+    out.pairs = L.tile_pairs.as<uint2>(); out.ent_meta = L.tile_ent_meta.as<int2>(); out.tile_vert = L.tile_vert.as<int>();
+    out.tile_info = L.tile_info.as<int2>(); out.pt_w = L.tile_pt_w.as<float>(); out.pt_slot = L.tile_pt_slot.as<uint16_t>();
+    // tmp -= -w * (alpha * filtered) * norm  (densecrf.cpp:126, labelcompatibility.cpp:46-48, permutohedral.cpp:571)
+    launch_tile_csr_build(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), L.norm.as<float>(), pre, post,
+                          L.potts_w * lattice_alpha(L.d), tm, d1, G * 16, L.counts.as<uint32_t>(), out);
     L.tile_TP = tm.TP;
     L.tile_W = tm.W;
     RSS_CU(ctx, cudaGetLastError());

@@ -42,7 +42,7 @@ struct Lattice {
     DevBuf seg_end;      // uint32[maxseg]
     DevBuf val_a, val_b; // float[(vcap+1)][Mp] ping-pong value tables (row vcap stays zero)
     DevBuf val_c;        // third table of the fused mean-field path (meanfield.cu)
-    DevBuf tile_pairs, tile_ent_meta, tile_nent;  // tile-local CSR of the splat matrix (meanfield.cu)
+    DevBuf tile_pairs, tile_ent_meta, tile_vert, tile_info, tile_pt_w, tile_pt_slot;  // per-tile data of the fused point kernel (meanfield.cuh, FusedLat)
     int tile_TP = 0;     // points per tile the tile CSR was built for (0 = not built)
     int tile_W = 0;      // image width of the 2-D tiling the tile CSR was built for (0 = 1-D tiles)
     bool have_csr = false;  // vertex-major CSR + segments (generic splat path) built
@@ -54,7 +54,7 @@ struct Lattice {
     unsigned int barrier_base = 0;  // grid-barrier arrivals issued so far (counts[8] is the barrier word)
     void release() {
         DevBuf* b[] = {&table, &slot_id, &first_ref, &rank, &vkeys, &offsets, &bary, &nbr, &norm, &counts, &deg, &cursor, &nseg,
-                       &csr_pt, &csr_w, &seg_v, &seg_begin, &seg_end, &val_a, &val_b, &val_c, &scan_tmp, &tile_pairs, &tile_ent_meta, &tile_nent};
+                       &csr_pt, &csr_w, &seg_v, &seg_begin, &seg_end, &val_a, &val_b, &val_c, &scan_tmp, &tile_pairs, &tile_ent_meta, &tile_vert, &tile_info, &tile_pt_w, &tile_pt_slot};
         for (DevBuf* p : b) p->release();
     }
 };
@@ -91,10 +91,14 @@ struct rss_crf {
     rss_ctx* ctx = nullptr;
     int N = 0, n_layers = 0;
     int M[RSS_MAX_LAYERS] = {0};
+    // Device channel layout: layer l owns channels [moff[l], moff[l] + M[l]) of a point's row; every layer starts at a
+    // multiple of 4 channels (float4 group) and its padding channels hold unary = +inf / Q = 0.  hoff[l] = sum of the
+    // label counts of the layers before l: the layer's offset in host-side concatenations.
     int moff[RSS_MAX_LAYERS + 1] = {0};
-    int Mtot = 0, Mp = 0;          // total labels, padded to a multiple of 4
-    rss::DevBuf unary;             // float[N][Mtot]  energies (layers concatenated per point)
-    rss::DevBuf Q;                 // float[N][Mtot]
+    int hoff[RSS_MAX_LAYERS + 1] = {0};
+    int Mtot = 0, Mp = 0;          // total labels; channels per row = sum over layers of M_l rounded up to 4
+    rss::DevBuf unary;             // float[N][Mp]  energies
+    rss::DevBuf Q;                 // float[N][Mp]
     rss::DevBuf scratch;           // float[N][Mp] staging for host-layout conversions / filter tests
     rss::DevBuf labels;            // uint8[n_layers][N]
     rss::DevBuf feat_stage;        // float[N][d] staging for feature upload

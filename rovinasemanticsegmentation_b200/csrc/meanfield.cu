@@ -1,17 +1,26 @@
 // Fused mean-field iteration for point sets whose order is spatially coherent (image raster order: the keyframe path,
 // DenseCRF2D; any point set whose consecutive points share lattice vertices).  Per iteration there are two launches:
-//   meanfield_tile_kernel   slice of the previous iteration's blurred value tables + Potts + unary + per-layer soft-max
+//   meanfield_point_kernel  slice of the previous iteration's blurred value tables + Potts + unary + per-layer soft-max
 //                           (+ gated argmax / Q store on the last pass) AND the splat of the new marginals;
 //   blur_multi_coop_kernel  every axis of every lattice of the CRF, one cooperative launch with grid barriers.
 // Reference: third-party/densecrf/src/densecrf.cpp:98-131 (expAndNormalize, inference), pairwise.cpp:63-80
 // (DenseKernel::filter), labelcompatibility.cpp:46-48 (Potts), permutohedral.cpp:529-589 (sseCompute).
 //
-// A tile (one CTA of the point kernel) is a block of ~512 points: a 32 x TH pixel block for image CRFs, else a run of
-// consecutive points.  Phase 1 keeps the tile's marginals in shared memory; phase 2 gathers them per (lattice vertex
-// touched by the tile) through a tile-local CSR built once per lattice (tile_csr_build_kernel) and issues one
-// red.global.add.v4.f32 per (segment of <= 32 pairs, channel group).  So Q is never re-read from L2, there is no
-// separate splat launch, and the number of global atomics is (distinct vertices per tile), not (nonzeros) - which is
-// what makes noisy images cheap: +-8 colour noise sends 64 % of consecutive pixels to a different bilateral vertex.
+// A tile (one CTA of the point kernel) is a block of 256 points - a 32 x 8 pixel block for image CRFs, else a run of
+// consecutive points - and ONE THREAD OWNS ONE POINT with all its label channels in registers.
+//   staging  asynchronous copies bring in, without touching a register: the tile's unary rows (TMA bulk copies,
+//            cp.async.bulk + mbarrier, into the shared Q tile: a thread reads its unary row, later overwrites it with its
+//            marginals), the tile's splat lists (segment metadata + pairs, TMA), and the DISTINCT value rows of each
+//            lattice that the tile's points reference (cp.async 16 B each, a few KB to ~13 KB per lattice, completion
+//            counted on the same mbarrier with cp.async.mbarrier.arrive).
+//   phase 1  t = -unary + sum over lattices and simplex corners of w * row[slot]: the weight already contains the
+//            barycentric coordinate, the post-normalisation, the Potts weight and the slice scale, and the row comes out
+//            of SHARED MEMORY by its tile-local slot - d+1 LDS.128 x G per lattice instead of L1/L2 gathers.  Soft-max
+//            per label layer in registers (no shuffles), marginals to the shared Q tile.
+//   phase 2  thread = one segment of <= TILE_SEG (point, weight) pairs of one vertex: sums w * Q[point] for all channels
+//            out of shared memory and issues G red.global.add.v4.f32.  Global atomics per iteration = (distinct vertices
+//            per tile) * G instead of (nonzeros) * G, Q is never re-read from L2, and nothing depends on how noisy the
+//            pixel order is (+-8 colour noise sends 64 % of consecutive pixels to a different bilateral vertex).
 // Value tables rotate through three buffers per lattice: `res` (blurred result being sliced), `tgt` (all zero, receives
 // the splat) and `spare`; the blur ping-pongs between tgt and spare and clears the old `res`, the next tgt.
 //
@@ -23,28 +32,17 @@
 #include "meanfield.cuh"
 
 #ifndef RSS_TILE_MINB
-#define RSS_TILE_MINB 4  // resident CTAs per SM the point kernel is compiled for (register budget)
-#endif
-#ifndef RSS_TILE_REGS  // explicit register cap instead of the occupancy-derived one
-#define RSS_TILE_BOUNDS __launch_bounds__(256, RSS_TILE_MINB)
-#else
-#define RSS_TILE_BOUNDS __maxnreg__(RSS_TILE_REGS)
+#define RSS_TILE_MINB 3  // resident CTAs per SM the point kernel is compiled for (register budget)
 #endif
 #ifndef RSS_BLUR_U
 #define RSS_BLUR_U 2      // independent (vertex, channel group) items a blur thread keeps in flight
 #endif
 #ifndef RSS_BLUR_MAXT
-#define RSS_BLUR_MAXT 128  // CTA size of the cooperative blur: small register / thread footprint on purpose, so that
-                           // kernels of OTHER keyframes in flight run on the SMs while its CTAs wait at the grid barriers
+#define RSS_BLUR_MAXT 512  // CTA size of the cooperative blur: the phases are L2-throughput-bound once >= 512 threads per
+                           // SM keep loads in flight (tools/micro/blur_bench.cu: 35 us at 128, 25 us at 512 and 1024)
 #endif
-#ifndef RSS_TILE_SINGLE_WAVE
-#define RSS_TILE_SINGLE_WAVE 0  // grow the tiles until all CTAs of the point kernel are resident at once
-#endif
-#ifndef RSS_TILE_IU
-#define RSS_TILE_IU 1  // splat segments a thread walks at once
-#endif
-#ifndef RSS_TILE_POINTS
-#define RSS_TILE_POINTS 288  // target points per tile (<= 512: the tile CSR build kernel's hash capacity)
+#ifndef RSS_TILE_SEG
+#define RSS_TILE_SEG 32
 #endif
 
 namespace rss {
@@ -92,38 +90,35 @@ __device__ __forceinline__ void red_add_v4(float* dst, const float4 v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Tile-local CSR of the splat matrix.  A tile is TP consecutive points (the points one CTA of the mean-field kernel
-// owns).  For every tile: the distinct lattice vertices its points touch ("entries") and, per entry, the list of
-// (local point, weight) pairs.  Built once per lattice by one CTA per tile with a shared-memory hash table (native
-// 32-bit CAS / integer adds only): insert keys -> count -> compact + scan -> fill.  weight = bary * norm_i when the
-// kernel is pre-normalised (DenseKernel::filter, pairwise.cpp:65-66), so the gather needs no norm lookup.
-// Entry meta: x = (start of the segment in the tile's pair array) | (length << 16), y = vertex id.
+// Tile data of one lattice (see FusedLat in meanfield.cuh).  Built once per lattice by one CTA per tile with a
+// shared-memory hash table (native 32-bit CAS / integer adds only): insert keys -> count -> compact + scan -> fill.
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef RSS_TILE_SEG
-#define RSS_TILE_SEG 32
-#endif
 constexpr int TILE_SEG = RSS_TILE_SEG;  // pairs per splat segment (one thread walks one segment serially)
-constexpr int TILE_CHUNK = 8;           // pairs requested at once by the gather
 
-__device__ __forceinline__ int2 block_excl_scan2(int a, int b, int2* total) {  // 256 threads
-    __shared__ int2 wsum[8];
-    __shared__ int2 btot;
+__device__ __forceinline__ int3 block_excl_scan3(int a, int b, int c, int3* total) {  // 256 threads
+    __shared__ int3 wsum[8];
+    __shared__ int3 btot;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int ia = a, ib = b;
+    int ia = a, ib = b, ic = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ia += ta; ib += tb; }
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o),
+                  tc = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += ta; ib += tb; ic += tc; }
     }
-    if (lane == 31) wsum[w] = make_int2(ia, ib);
+    if (lane == 31) wsum[w] = make_int3(ia, ib, ic);
     __syncthreads();
     if (threadIdx.x == 0) {
-        int sa = 0, sb = 0;
-        for (int k = 0; k < 8; k++) { const int2 v = wsum[k]; wsum[k] = make_int2(sa, sb); sa += v.x; sb += v.y; }
-        btot = make_int2(sa, sb);
+        int sa = 0, sb = 0, sc = 0;
+        for (int k = 0; k < 8; k++) {
+            const int3 v = wsum[k];
+            wsum[k] = make_int3(sa, sb, sc);
+            sa += v.x; sb += v.y; sc += v.z;
+        }
+        btot = make_int3(sa, sb, sc);
     }
     __syncthreads();
-    const int2 r = make_int2(ia - a + wsum[w].x, ib - b + wsum[w].y);
+    const int3 r = make_int3(ia - a + wsum[w].x, ib - b + wsum[w].y, ic - c + wsum[w].z);
     *total = btot;
     __syncthreads();
     return r;
@@ -131,32 +126,36 @@ __device__ __forceinline__ int2 block_excl_scan2(int a, int b, int2* total) {  /
 
 template <int D1>
 __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restrict__ offsets, const float* __restrict__ bary,
-                                                             const float* __restrict__ norm, const TileMap tm, int row_bytes,
-                                                             int HC, const uint32_t* __restrict__ counts,
-                                                             uint2* __restrict__ pairs, int2* __restrict__ ent_meta,
-                                                             int* __restrict__ tile_nent) {
+                                                             const float* __restrict__ norm, int pre, int post,
+                                                             float slice_scale, const TileMap tm, int row_bytes, int HC,
+                                                             const uint32_t* __restrict__ counts, const TileCsrOut out) {
     __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1];
-    extern __shared__ int tile_smem[];  // TILE_SMEM_BYTES, above the 48 KB static limit
+    extern __shared__ int tile_smem[];  // above the 48 KB static limit for large d
     int* hkeys = tile_smem;  // HC slots (power of two, > pairs per tile)
     int* hcnt = tile_smem + HC;
-    unsigned short* pslot = reinterpret_cast<unsigned short*>(tile_smem + 2 * HC);
+    int* hrow = tile_smem + 2 * HC;
+    int* hcur = tile_smem + 3 * HC;
+    unsigned short* pslot = reinterpret_cast<unsigned short*>(tile_smem + 4 * HC);
+    uint2* spairs = reinterpret_cast<uint2*>(pslot + TILE_POINTS * D1);  // the tile's pair lists, ordered here, written out at the end
+    int* segs = reinterpret_cast<int*>(spairs + TILE_POINTS * D1);      // start | length << 16 of every segment
     const int hshift = 32 - (31 - __clz(HC));
     const int tile = blockIdx.x;
-    const int TP = tm.TP;
+    constexpr int TP = TILE_POINTS;
     const TileOrigin org = tile_origin(tm, tile);
     const int npairs = TP * D1;  // slots; points outside the image / beyond N are skipped
     const size_t tb = (size_t)tile * TP * D1;
     if (counts[1]) {
-        if (threadIdx.x == 0) tile_nent[tile] = 0;
+        if (threadIdx.x == 0) out.tile_info[tile] = make_int2(0, 0);
         return;
     }
     for (int i = threadIdx.x; i < HC; i += 256) { hkeys[i] = -1; hcnt[i] = 0; }
     if (threadIdx.x <= TILE_SEG) hist[threadIdx.x] = 0;
     __syncthreads();
+    // pair i = (corner j, local point lp), lp fastest: the point-major outputs are written coalesced
     for (int i = threadIdx.x; i < npairs; i += 256) {
-        const int lp = i / D1, p = tile_point(tm, org, lp);
+        const int j = i / TP, lp = i - j * TP, p = tile_point(tm, org, lp);
         if (p < 0) continue;
-        const int key = offsets[(size_t)p * D1 + (i - lp * D1)];
+        const int key = offsets[(size_t)p * D1 + j];
         unsigned h = ((unsigned)key * 2654435761u) >> hshift;
         for (;;) {
             const int cur = hkeys[h];
@@ -172,8 +171,8 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     }
     __syncthreads();
     // Lists are cut into segments of at most TILE_SEG pairs and the segments are ordered by length (longest first), so
-    // that the lanes of a warp of the gather walk lists of (nearly) equal length.  Thread t owns slots [32t, 32t+32).
-    int nseg = 0, ncnt = 0;
+    // that the lanes of a warp of the gather walk lists of (nearly) equal length.  Thread t owns HC / 256 hash slots.
+    int nseg = 0, ncnt = 0, nvert = 0;
     const int spt = HC / 256, s0 = threadIdx.x * spt;  // slots per thread
 #pragma unroll 4
     for (int k = 0; k < spt; k++) {
@@ -184,81 +183,99 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
             if (rem) atomicAdd(&hist[rem], 1);
             nseg += full + (rem ? 1 : 0);
             ncnt += c;
+            nvert++;
         }
     }
-    int2 tot;
-    int2 pre = block_excl_scan2(nseg, ncnt, &tot);  // ends with a barrier: hist is complete
+    int3 tot;
+    int3 pre3 = block_excl_scan3(nseg, ncnt, nvert, &tot);  // ends with a barrier: hist is complete
     if (threadIdx.x == 0) {
         int pos = 0;
         for (int len = TILE_SEG; len >= 1; len--) { binstart[len] = pos; pos += hist[len]; hist[len] = 0; }
-        tile_nent[tile] = tot.x;
+        out.tile_info[tile] = make_int2(tot.x, tot.z);
     }
     __syncthreads();
     for (int k = 0; k < spt; k++) {
         const int c = hcnt[s0 + k];
         if (c > 0) {
-            const int key = hkeys[s0 + k];
-            for (int o = 0; o < c; o += TILE_SEG) {
-                const int len = min(TILE_SEG, c - o);
-                const int idx = binstart[len] + atomicAdd(&hist[len], 1);
-                ent_meta[tb + idx] = make_int2((pre.y + o) | (len << 16), key);
-            }
-            hcnt[s0 + k] = pre.y;  // becomes the fill cursor of the slot's pair list
-            pre.y += c;
+            hrow[s0 + k] = pre3.z;             // the vertex's row slot in the tile
+            out.tile_vert[tb + pre3.z] = hkeys[s0 + k];
+            pre3.z++;
+            hcur[s0 + k] = pre3.y;             // fill cursor of the slot's pair list
+            pre3.y += c;
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npairs; i += 256) {
-        const int lp = i / D1, p = tile_point(tm, org, lp);
-        if (p < 0) continue;
-        const int pos = atomicAdd(&hcnt[pslot[i]], 1);
-        float w = bary[(size_t)p * D1 + (i - lp * D1)];
-        if (norm) w = __fmul_rn(w, norm[p]);
-        pairs[tb + pos] = make_uint2((unsigned)lp * (unsigned)row_bytes, __float_as_uint(w));
+        const int j = i / TP, lp = i - j * TP, p = tile_point(tm, org, lp);
+        float ws = 0.f;
+        int slot = 0;
+        if (p >= 0) {
+            const int h = pslot[i];
+            const int pos = atomicAdd(&hcur[h], 1);
+            const float b = bary[(size_t)p * D1 + j];
+            const float nv = (pre | post) ? norm[p] : 1.f;
+            spairs[pos] = make_uint2((unsigned)lp, __float_as_uint(pre ? __fmul_rn(b, nv) : b));
+            ws = __fmul_rn(post ? __fmul_rn(b, nv) : b, slice_scale);
+            slot = hrow[h];
+        }
+        out.pt_w[tb + pt_index(D1, j, lp)] = ws;
+        out.pt_slot[tb + pt_index(D1, j, lp)] = (uint16_t)slot;
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// The point kernel.  One CTA = one tile of TP consecutive points.
-//  phase 1 (lane = (point, channel group), G lanes per point, 32/G points per warp-step):
-//     t = -unary + sum over lattices of w * norm_i * sum_j (bary_ij * alpha) * blurred[vertex_ij]; soft-max per label
-//     layer across the G lanes; marginals go to the shared-memory tile (and to global Q / label maps on request).
-//     A value-table row (Mp floats) is read by G adjacent lanes as one contiguous 16*G-byte access.
-//  phase 2 (item = (tile entry, channel group)): sum w * Q[point] over the entry's pair list out of shared memory and
-//     issue ONE red.global.add.v4.f32 per item.  Global atomics per iteration = (distinct vertices per tile) * G
-//     instead of (nonzeros) * G, Q is never re-read from L2, and nothing depends on how noisy the point order is.
-// `mode` bit 0: slice (not the first pass), bit 1: splat (not the last pass), bit 2: store Q.
-// ---------------------------------------------------------------------------------------------------------------
-// streaming inputs of one point for one lattice, loaded one step ahead of their use
-template <int D1>
-struct PointIn {
-    int key[D1 > 0 ? D1 : 1];
-    float w[D1 > 0 ? D1 : 1];
-    float nrm;
-    __device__ __forceinline__ void load(const FusedLat& L, int p) {
-        if constexpr (D1 > 0) {
-            load_row_i<D1>(L.offsets + (size_t)p * D1, key);
-            load_row_f<D1>(L.bary + (size_t)p * D1, w);
-            nrm = __ldg(L.norm + p);
+    __syncthreads();
+    // Segments, and the ORDER of the pairs inside a segment.  In the gather, thread e walks segment e; at step k the eight
+    // lanes of a quarter-warp read one 16-byte unit of eight different Q rows (an LDS.128 is served per quarter-warp).
+    // Row lp, unit g lies in bank group (G * lp + g) mod 8, so the eight reads are conflict-free when the eight lp differ
+    // mod 8 (G odd).  Every list is therefore arranged so that position k of segment e holds a point of class
+    // (e + k) mod 8 whenever the list still has one - a vertex covers a blob of pixels, so all classes occur about equally.
+    const int G = row_bytes / 16;
+    for (int k = 0; k < spt; k++) {
+        const int c = hcnt[s0 + k];
+        if (c > 0) {
+            const int key = hkeys[s0 + k], start = hcur[s0 + k] - c;
+            for (int o = 0; o < c; o += TILE_SEG) {
+                const int len = min(TILE_SEG, c - o);
+                const int idx = binstart[len] + atomicAdd(&hist[len], 1);
+                const int m = (start + o) | (len << 16);
+                out.ent_meta[tb + idx] = make_int2(m, key);
+                segs[idx] = m;
+            }
         }
     }
-};
-template <int D1>
-__device__ __forceinline__ void slice_lattice(const FusedLat& L, const PointIn<D1>& in, int Mp, int g, float4& t) {
-    float4 row[D1];
+    __syncthreads();
+    // one segment per thread: the classes of its <= 32 pairs packed as nibbles in two 64-bit registers (a used pair
+    // becomes 0xF, which matches no class), so "the first unused pair of class c" is a zero-nibble search, not a scan
+    static_assert(TILE_SEG <= 32, "the segment ordering packs 32 classes into 128 bits");
+    for (int idx = threadIdx.x; idx < tot.x; idx += 256) {
+        const int m = segs[idx], len = m >> 16, start = m & 0xffff;
+        const uint2* lst = spairs + start;
+        unsigned long long cls[2] = {~0ull, ~0ull};
+        for (int f = 0; f < len; f++) {
+            const unsigned long long c = (unsigned long long)((G * lst[f].x) & 7u);
+            cls[f >> 4] = (cls[f >> 4] & ~(0xFull << (4 * (f & 15)))) | (c << (4 * (f & 15)));
+        }
+        for (int q = 0; q < len; q++) {
+            const unsigned long long want = (unsigned long long)((unsigned)(G * (idx + q)) & 7u) * 0x1111111111111111ull;
+            int f = -1;
 #pragma unroll
-    for (int j = 0; j < D1; j++) row[j] = __ldg(reinterpret_cast<const float4*>(L.vin + (size_t)in.key[j] * Mp) + g);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < D1; j++) {
-        acc.x = fmaf(in.w[j], row[j].x, acc.x); acc.y = fmaf(in.w[j], row[j].y, acc.y);
-        acc.z = fmaf(in.w[j], row[j].z, acc.z); acc.w = fmaf(in.w[j], row[j].w, acc.w);
+            for (int h = 0; h < 2; h++) {
+                const unsigned long long x = cls[h] ^ want;  // zero nibble <=> unused pair of the wanted class
+                const unsigned long long z = (x - 0x1111111111111111ull) & ~x & 0x8888888888888888ull;
+                if (f < 0 && z) f = 16 * h + ((__ffsll((long long)z) - 1) >> 2);
+            }
+            if (f < 0) {  // the class is exhausted: any unused pair (bit 3 of its nibble is clear)
+                const unsigned long long u0 = ~cls[0] & 0x8888888888888888ull, u1 = ~cls[1] & 0x8888888888888888ull;
+                f = u0 ? ((__ffsll((long long)u0) - 1) >> 2) : 16 + ((__ffsll((long long)u1) - 1) >> 2);
+            }
+            cls[f >> 4] |= 0xFull << (4 * (f & 15));
+            const uint2 v = lst[f];
+            out.pairs[tb + start + q] = make_uint2(v.x * (unsigned)row_bytes, v.y);
+        }
     }
-    // tmp = -unary - (-w * (alpha * filtered) * norm)   (densecrf.cpp:126, pairwise.cpp:78-79, permutohedral.cpp:571)
-    const float c = L.potts * L.alpha * (L.post ? in.nrm : 1.f);
-    t.x = fmaf(c, acc.x, t.x); t.y = fmaf(c, acc.y, t.y); t.z = fmaf(c, acc.z, t.z); t.w = fmaf(c, acc.w, t.w);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The point kernel.  `MODE` bit 0: slice (not the first pass), bit 1: splat (not the last pass), bit 2: store Q.
+// ---------------------------------------------------------------------------------------------------------------
 // exp(x) for x <= 0 as one multiply and one ex2.approx.ftz (|rel err| < 2e-6; the CRF tolerance is 1e-4 abs; results
 // below 2^-126 flush to zero, which the normalisation cannot tell from the true value)
 __device__ __forceinline__ float fast_exp(float x) {
@@ -266,296 +283,319 @@ __device__ __forceinline__ float fast_exp(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
     return y;
 }
-template <int G>
-__device__ __forceinline__ float group_gather_max(float v, int gbase) {
-    float m = v;
-#pragma unroll
-    for (int i = 0; i < G; i++) m = fmaxf(m, __shfl_sync(0xffffffffu, v, (gbase + i) & 31));
-    return m;
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-template <int G>
-__device__ __forceinline__ float group_gather_sum(float v, int gbase) {  // same order on every lane of the group
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < G; i++) s += __shfl_sync(0xffffffffu, v, (gbase + i) & 31);
-    return s;
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
-// pairs[].x holds the BYTE offset of the local point's row inside the shared tile (lp * G * 16).
-// Entry meta of the tile was staged into shared memory at kernel start (`cap` entries; the rest comes from global).
-// Every thread walks IU segments at once (independent load streams); segments are sorted by length, so the lanes of
-// a warp finish together.
-template <int G, int IU>
-__device__ __forceinline__ void gather_entries(const uint2* pr, const int2* meta, int cap,
-                                               const int2* __restrict__ meta_g, int ne, float* __restrict__ vout,
-                                               const float4* qtile) {
-    constexpr int Mp = 4 * G;
-    const char* qbytes = reinterpret_cast<const char*>(qtile);
-    const int items = ne * G;
-    for (int it0 = threadIdx.x; it0 < items; it0 += 256 * IU) {
-        const uint2* pp[IU];
-        int len[IU], vertex[IU];
-        const char* qb[IU];
-        float4 acc[IU];
-        int longest = 0;
+// a point's D1 slice weights and row slots, fetched with vector loads (pt_index order) BEFORE the staging barrier is
+// waited on, so that their latency overlaps the TMA / cp.async traffic
+template <int D1>
+struct PointIn {
+    float w[D1 > 0 ? D1 : 1];
+    int s[D1 > 0 ? D1 : 1];
+    __device__ __forceinline__ void load(const FusedLat& L, size_t tb, int lp) {
+        if constexpr (D1 > 0) {
+            constexpr int TP = TILE_POINTS, n4 = D1 / 4, n2 = (D1 % 4) / 2, n1 = D1 % 2;
+            const float* wp = L.pt_w + tb;
+            const uint16_t* sp = L.pt_slot + tb;
 #pragma unroll
-        for (int u = 0; u < IU; u++) {
-            const int it = it0 + u * 256;
-            len[u] = 0; vertex[u] = -1; pp[u] = pr; qb[u] = qbytes;
-            acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (it < items) {
-                const int e = it / G;
-                const int2 m = e < cap ? meta[e] : __ldg(meta_g + e);
-                pp[u] = pr + (m.x & 0xffff);
-                len[u] = m.x >> 16;
-                vertex[u] = m.y;
-                qb[u] = qbytes + 16 * (it - e * G);
-                longest = max(longest, len[u]);
+            for (int k = 0; k < n4; k++) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(wp) + k * TP + lp);
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(sp) + k * TP + lp);
+                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                s[4 * k] = u.x & 0xffff; s[4 * k + 1] = u.x >> 16; s[4 * k + 2] = u.y & 0xffff; s[4 * k + 3] = u.y >> 16;
+            }
+            if constexpr (n2 > 0) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(wp + 4 * n4 * TP) + lp);
+                const unsigned u = __ldg(reinterpret_cast<const unsigned*>(sp + 4 * n4 * TP) + lp);
+                w[4 * n4] = v.x; w[4 * n4 + 1] = v.y;
+                s[4 * n4] = u & 0xffff; s[4 * n4 + 1] = u >> 16;
+            }
+            if constexpr (n1 > 0) {
+                w[D1 - 1] = __ldg(wp + (4 * n4 + 2 * n2) * TP + lp);
+                s[D1 - 1] = __ldg(sp + (4 * n4 + 2 * n2) * TP + lp);
             }
         }
-        // pairs are requested TILE_CHUNK at a time (independent loads, one L2 round trip per chunk), then the
-        // multiply-adds run out of shared memory
-        for (int c0 = 0; c0 < longest; c0 += TILE_CHUNK) {
-            uint2 pw[IU][TILE_CHUNK];
+    }
+};
+// t[c] += w * row[c] for the D1 corners of one lattice; rows of slots < TILE_ROW_CAP are in shared memory
+template <int G, int D1>
+__device__ __forceinline__ void slice_lattice(const FusedLat& L, size_t tb, const PointIn<D1>& in, const float4* rows,
+                                              float (&t)[4 * G]) {
+    constexpr int MP = 4 * G;
 #pragma unroll
-            for (int u = 0; u < IU; u++)
+    for (int j = 0; j < D1; j++) {
+        const float w = in.w[j];
+        if (in.s[j] < TILE_ROW_CAP) {
+            const float4* row = rows + in.s[j] * G;
 #pragma unroll
-                for (int i = 0; i < TILE_CHUNK; i++)
-                    if (c0 + i < len[u]) pw[u][i] = pp[u][c0 + i];
+            for (int g = 0; g < G; g++) {
+                const float4 v = row[g];
+                t[4 * g] = fmaf(w, v.x, t[4 * g]); t[4 * g + 1] = fmaf(w, v.y, t[4 * g + 1]);
+                t[4 * g + 2] = fmaf(w, v.z, t[4 * g + 2]); t[4 * g + 3] = fmaf(w, v.w, t[4 * g + 3]);
+            }
+        } else {  // more distinct vertices in this tile than staged rows (rare): straight from the value table
+            const float4* row = reinterpret_cast<const float4*>(L.vin + (size_t)__ldg(L.tile_vert + tb + in.s[j]) * MP);
 #pragma unroll
-            for (int i = 0; i < TILE_CHUNK; i++) {
-#pragma unroll
-                for (int u = 0; u < IU; u++) {
-                    if (c0 + i < len[u]) {
-                        const float w = __uint_as_float(pw[u][i].y);
-                        const float4 q = *reinterpret_cast<const float4*>(qb[u] + pw[u][i].x);
-                        acc[u].x = fmaf(w, q.x, acc[u].x); acc[u].y = fmaf(w, q.y, acc[u].y);
-                        acc[u].z = fmaf(w, q.z, acc[u].z); acc[u].w = fmaf(w, q.w, acc[u].w);
-                    }
-                }
+            for (int g = 0; g < G; g++) {
+                const float4 v = __ldg(row + g);
+                t[4 * g] = fmaf(w, v.x, t[4 * g]); t[4 * g + 1] = fmaf(w, v.y, t[4 * g + 1]);
+                t[4 * g + 2] = fmaf(w, v.z, t[4 * g + 2]); t[4 * g + 3] = fmaf(w, v.w, t[4 * g + 3]);
             }
         }
-#pragma unroll
-        for (int u = 0; u < IU; u++)
-            if (vertex[u] >= 0) red_add_v4(vout + (size_t)vertex[u] * Mp + (qb[u] - qbytes) / 4, acc[u]);
+    }
+}
+// the tile's distinct value rows -> shared memory, 16 bytes per cp.async, all threads
+template <int G>
+__device__ __forceinline__ void stage_rows(const FusedLat& L, size_t tb, int nrows, float4* rows) {
+    constexpr int MP = 4 * G;
+    for (int i = threadIdx.x; i < nrows * G; i += TILE_POINTS) {
+        const int r = i / G, g = i - r * G;
+        const float* src = L.vin + (size_t)__ldg(L.tile_vert + tb + r) * MP + 4 * g;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(rows + i)), "l"(src)
+                     : "memory");
     }
 }
 
-// MODE is a compile-time constant (2 = first pass, 3 = middle passes, 5 = last pass): the slice / splat / store branches
-// disappear from the instruction stream of each variant.
+// one thread = one splat segment, all channels in registers; pairs[].x = byte offset of the point's row in the Q tile
+template <int G>
+__device__ __forceinline__ void gather_entries(const uint2* pr, const int2* meta, int cap, const int2* __restrict__ meta_g,
+                                               int ne, float* __restrict__ vout, const float4* qtile) {
+    constexpr int MP = 4 * G;
+    const char* qbytes = reinterpret_cast<const char*>(qtile);
+    for (int e = threadIdx.x; e < ne; e += TILE_POINTS) {
+        const int2 m = e < cap ? meta[e] : __ldg(meta_g + e);
+        const uint2* pp = pr + (m.x & 0xffff);
+        const int len = m.x >> 16;
+        float4 acc[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = 0;
+        for (; k + 2 <= len; k += 2) {  // two pairs per trip: the second pair's loads overlap the first pair's multiply-adds
+            const uint2 p0 = pp[k], p1 = pp[k + 1];
+            const float w0 = __uint_as_float(p0.y), w1 = __uint_as_float(p1.y);
+            const float4* q0 = reinterpret_cast<const float4*>(qbytes + p0.x);
+            const float4* q1 = reinterpret_cast<const float4*>(qbytes + p1.x);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const float4 a = q0[g], b = q1[g];
+                acc[g].x = fmaf(w0, a.x, acc[g].x); acc[g].y = fmaf(w0, a.y, acc[g].y);
+                acc[g].z = fmaf(w0, a.z, acc[g].z); acc[g].w = fmaf(w0, a.w, acc[g].w);
+                acc[g].x = fmaf(w1, b.x, acc[g].x); acc[g].y = fmaf(w1, b.y, acc[g].y);
+                acc[g].z = fmaf(w1, b.z, acc[g].z); acc[g].w = fmaf(w1, b.w, acc[g].w);
+            }
+        }
+        if (k < len) {
+            const uint2 p0 = pp[k];
+            const float w0 = __uint_as_float(p0.y);
+            const float4* q0 = reinterpret_cast<const float4*>(qbytes + p0.x);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const float4 a = q0[g];
+                acc[g].x = fmaf(w0, a.x, acc[g].x); acc[g].y = fmaf(w0, a.y, acc[g].y);
+                acc[g].z = fmaf(w0, a.z, acc[g].z); acc[g].w = fmaf(w0, a.w, acc[g].w);
+            }
+        }
+        float* dst = vout + (size_t)m.y * MP;
+#pragma unroll
+        for (int g = 0; g < G; g++) red_add_v4(dst + 4 * g, acc[g]);
+    }
+}
+
 template <int G, int D1A, int D1B, int MODE>
-__global__ void RSS_TILE_BOUNDS meanfield_tile_kernel(const __grid_constant__ FusedArgs a,
-                                                             const float* __restrict__ unary, float* __restrict__ Q,
-                                                             uint8_t* __restrict__ labels,
-                                                             const __grid_constant__ TileMap tm, int steps,
-                                                             const __grid_constant__ FusedLayers ls) {
-    extern __shared__ float4 qtile[];  // [TP][G]
-    if (a.counts[0][1]) return;  // lattice overflow: the host rebuilds with a larger table and runs again
-    if constexpr (D1B > 0) { if (a.counts[1][1]) return; }
-    constexpr int Mp = 4 * G, cpw = 32 / G;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int sub = lane / G, g = lane - sub * G, gbase = sub * G;
-    const bool lane_on = sub < cpw;
-    const int tile = blockIdx.x, TP = tm.TP, N = tm.N;
-    const TileOrigin org = tile_origin(tm, tile);
+__global__ void __launch_bounds__(TILE_POINTS, RSS_TILE_MINB)
+    meanfield_point_kernel(const __grid_constant__ FusedArgs a, const float* __restrict__ unary, float* __restrict__ Q,
+                           uint8_t* __restrict__ labels, const __grid_constant__ TileMap tm,
+                           const __grid_constant__ FusedLayers ls) {
+    constexpr int MP = 4 * G, TP = TILE_POINTS, RC = TILE_ROW_CAP;
     constexpr bool do_slice = MODE & 1, do_splat = MODE & 2, store_q = MODE & 4;
-    const int c0 = 4 * g;
-    // The tile's splat inputs - segment metadata (start | length, vertex) and the pair lists - go to shared memory with
-    // TMA bulk copies (cp.async.bulk, completion on an mbarrier): ONE thread issues four copies, they run during
-    // phase 1, and phase 2 never waits for L2.  The metadata region holds 2 * TP segments shared by the lattices;
-    // segments beyond the staged ones (never seen in practice) are read from global memory.
-    __shared__ alignas(8) unsigned long long stage_bar;
-    int2* metaA = reinterpret_cast<int2*>(qtile + (size_t)TP * G);
+    extern __shared__ float4 smem_f4[];
+    if (a.lat[0].counts[1]) return;  // lattice overflow: the host rebuilds with a larger table and runs again
+    if constexpr (D1B > 0) { if (a.lat[1].counts[1]) return; }
+    float4* qtile = smem_f4;            // [TP][G]  unary rows on arrival, marginals after phase 1
+    float4* rowsA = qtile + TP * G;     // [RC][G]  staged value rows of lattice A ...
+    float4* rowsB = rowsA + RC * G;     //          ... and B
+    int2* metaA = reinterpret_cast<int2*>(rowsB + (D1B > 0 ? RC * G : 0));  // 2 * TP segment slots shared by the lattices
     int2* metaB = metaA;
     uint2* spairsA = reinterpret_cast<uint2*>(metaA + 2 * TP);
     uint2* spairsB = spairsA + TP * D1A;
-    int neA = 0, neB = 0, capA = 0, capB = 0;
-    if (do_splat) {
-        neA = __ldg(a.tile_nent[0] + tile);
-        capA = min(neA, 2 * TP);
-        if constexpr (D1B > 0) {
-            neB = __ldg(a.tile_nent[1] + tile);
-            metaB = metaA + ((capA + 1) & ~1);  // keep 16-byte alignment for the bulk copy
-            capB = min(neB, 2 * TP - ((capA + 1) & ~1));
+    __shared__ alignas(8) unsigned long long stage_bar[2];  // [0] unary + value rows (phase 1), [1] splat lists (phase 2)
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&stage_bar[0]);
+    const unsigned bar1 = (unsigned)__cvta_generic_to_shared(&stage_bar[1]);
+    const int tile = blockIdx.x, N = tm.N, lp = threadIdx.x;
+    const TileOrigin org = tile_origin(tm, tile);
+    const size_t tbA = (size_t)tile * TP * D1A, tbB = (size_t)tile * TP * D1B;
+    const int2 infoA = __ldg(a.lat[0].tile_info + tile);
+    int2 infoB = make_int2(0, 0);
+    if constexpr (D1B > 0) infoB = __ldg(a.lat[1].tile_info + tile);
+    const int nrA = min(infoA.y, RC), nrB = min(infoB.y, RC);
+    const int neA = infoA.x, neB = infoB.x;
+    const int capA = min(neA, 2 * TP);
+    int capB = 0;
+    if constexpr (D1B > 0) {
+        metaB = metaA + ((capA + 1) & ~1);  // keep 16-byte alignment for the bulk copy
+        capB = min(neB, 2 * TP - ((capA + 1) & ~1));
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1 + (do_slice ? TP : 0));  // thread 0's expect_tx + (slice passes) every thread's cp.async arrival
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();  // the barriers exist before anybody's copy can complete on them
+    // ---- staging: everything below is issued up front and lands while the threads fetch their own inputs
+    if (threadIdx.x == 0) {
+        // unary rows of the tile -> Q tile
+        unsigned ubytes = 0;
+        if (tm.W == 0) {
+            const long long n = min((long long)TP, (long long)N - org.base);
+            ubytes = (unsigned)n * MP * 4;
+            mbar_expect_tx(bar0, ubytes);
+            bulk_g2s(qtile, unary + (size_t)org.base * MP, ubytes, bar0);
+        } else {
+            const int w = min(tm.TW, tm.W - org.x0), h = min(tm.TH, tm.H - org.y0);
+            ubytes = (unsigned)(w * h) * MP * 4;
+            mbar_expect_tx(bar0, ubytes);
+            for (int ly = 0; ly < h; ly++)
+                bulk_g2s(qtile + (size_t)ly * tm.TW * G, unary + ((size_t)(org.y0 + ly) * tm.W + org.x0) * MP,
+                         (unsigned)w * MP * 4, bar0);
         }
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            auto bulk = [&](void* dst, const void* src, unsigned bytes) {
-                if (bytes == 0) return;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 (unsigned)__cvta_generic_to_shared(dst)),
-                             "l"(src), "r"(bytes), "r"(bar)
-                             : "memory");
-            };
+        if (do_splat) {
             // sizes rounded up to 16 bytes: the arrays have TP * D1 (even) slots per tile, so the extra 8 bytes exist
             const unsigned szMA = ((unsigned)capA * 8 + 15) & ~15u, szMB = ((unsigned)capB * 8 + 15) & ~15u;
             const unsigned szPA = (unsigned)TP * D1A * 8, szPB = (unsigned)TP * D1B * 8;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(szMA + szMB + szPA + szPB) : "memory");
-            bulk(metaA, a.ent_meta[0] + (size_t)tile * TP * D1A, szMA);
-            bulk(spairsA, a.pairs[0] + (size_t)tile * TP * D1A, szPA);
+            mbar_expect_tx(bar1, szMA + szMB + szPA + szPB);
+            if (szMA) bulk_g2s(metaA, a.lat[0].ent_meta + tbA, szMA, bar1);
+            bulk_g2s(spairsA, a.lat[0].pairs + tbA, szPA, bar1);
             if constexpr (D1B > 0) {
-                bulk(metaB, a.ent_meta[1] + (size_t)tile * TP * D1B, szMB);
-                bulk(spairsB, a.pairs[1] + (size_t)tile * TP * D1B, szPB);
+                if (szMB) bulk_g2s(metaB, a.lat[1].ent_meta + tbB, szMB, bar1);
+                bulk_g2s(spairsB, a.lat[1].pairs + tbB, szPB, bar1);
             }
         }
     }
-    // per channel group (host-precomputed, FusedLayers): which of my four channels belong to which layer (one nibble per
-    // layer), and for aligned layers my layer, my valid channels and which lanes of the group share the layer
-    const unsigned lmask = ls.group_lmask[g];
-    const unsigned vm = ls.group_valid[g];
-    const int my_l = ls.group_layer[g];
-    // bit i: lane i of my group holds channels of MY layer (a pad-only lane keeps itself as its only peer so that its
-    // discarded result stays finite)
-    unsigned peer_mask = 0;
+    PointIn<D1A> inA;
+    PointIn<D1B> inB;
+    if constexpr (do_slice) {
+        // the DISTINCT value rows the tile's points reference: ~100 rows per lattice instead of (d+1) * 256 gathers
+        stage_rows<G>(a.lat[0], tbA, nrA, rowsA);
+        if constexpr (D1B > 0) stage_rows<G>(a.lat[1], tbB, nrB, rowsB);
+        // this thread's cp.asyncs arrive on bar0 when they have landed (the arrival is pre-counted in the init)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0) : "memory");
+        inA.load(a.lat[0], tbA, lp);
+        inB.load(a.lat[1], tbB, lp);
+    }
+    // ---- phase 1: one thread = one point
+    const int p = tile_point(tm, org, lp);
+    mbar_wait(bar0, 0);
+    if (p >= 0) {
+        float t[MP];
 #pragma unroll
-    for (int i = 0; i < G; i++)
-        if (my_l >= 0 ? ls.group_layer[i] == my_l : i == g) peer_mask |= 1u << i;
-
-    // one warp-step = 32 / G points per warp: load the streaming inputs, then gather / soft-max / store
-    struct StepIn {
-        float4 u;
-        PointIn<D1A> A;
-        PointIn<D1B> B;
-        int p;
-        bool valid;
-    };
-    auto load_step = [&](int s, StepIn& in) {
-        const int lp = (s * 8 + wib) * cpw + sub;
-        const int p = lane_on ? tile_point(tm, org, lp) : -1;
-        in.valid = p >= 0;
-        in.p = p;
-        in.u = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in.valid) {
-            in.u = __ldg(reinterpret_cast<const float4*>(unary + (size_t)p * Mp) + g);
-            if (do_slice) { in.A.load(a.lat[0], p); in.B.load(a.lat[1], p); }
+        for (int g = 0; g < G; g++) {
+            const float4 u = qtile[lp * G + g];
+            t[4 * g] = -u.x; t[4 * g + 1] = -u.y; t[4 * g + 2] = -u.z; t[4 * g + 3] = -u.w;
         }
-    };
-    auto run_step = [&](int s, const StepIn& in) {
-        const int lp = (s * 8 + wib) * cpw + sub;
-        const int p = in.p;
-        const bool valid = in.valid;
-        float4 t = make_float4(-in.u.x, -in.u.y, -in.u.z, -in.u.w);
-        if (valid && do_slice) {
-            slice_lattice<D1A>(a.lat[0], in.A, Mp, g, t);
-            if constexpr (D1B > 0) slice_lattice<D1B>(a.lat[1], in.B, Mp, g, t);
+        if constexpr (do_slice) {
+            // tmp = -unary - (-w * (alpha * filtered) * norm)   (densecrf.cpp:126, pairwise.cpp:78-79, permutohedral.cpp:571)
+            slice_lattice<G, D1A>(a.lat[0], tbA, inA, rowsA, t);
+            if constexpr (D1B > 0) slice_lattice<G, D1B>(a.lat[1], tbB, inB, rowsB, t);
         }
-        // expAndNormalize per label layer across the G lanes of the point (densecrf.cpp:98-106)
-        const float tv[4] = {t.x, t.y, t.z, t.w};
-        float qv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ls.aligned) {
-            // every lane's four channels lie in ONE layer: a single pass, the lanes of the other layers are masked out
-            // of the all-gathers by a -inf bias (max) and a 0/1 weight (sum); same summation order on every lane
+        // expAndNormalize per label layer (densecrf.cpp:98-106).  Layers are whole float4 groups and their padding
+        // channels carry t = -inf (unary = +inf), so everything below is per GROUP: no per-channel predicates.
+        constexpr float L2E = 1.4426950408889634f;
+        float gm[G], gs[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) gs[g] = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; g++) gm[g] = fmaxf(fmaxf(t[4 * g], t[4 * g + 1]), fmaxf(t[4 * g + 2], t[4 * g + 3]));
+        for (int l = 0; l < ls.n_layers; l++) {  // every group takes the maximum of its layer
+            const unsigned m = ls.gmask[l];
             float mx = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 4; k++) mx = fmaxf(mx, (vm >> k) & 1u ? tv[k] : -INFINITY);
-            float m = -INFINITY;
+            for (int g = 0; g < G; g++)
+                if ((m >> g) & 1u) mx = fmaxf(mx, gm[g]);
 #pragma unroll
-            for (int i = 0; i < G; i++) {
-                const float o = __shfl_sync(0xffffffffu, mx, (gbase + i) & 31);
-                m = fmaxf(m, (peer_mask >> i) & 1u ? o : -INFINITY);
-            }
-            float e[4], sl = 0.f;
+            for (int g = 0; g < G; g++)
+                if ((m >> g) & 1u) gs[g] = mx;
+        }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                e[k] = (vm >> k) & 1u ? fast_exp(tv[k] - m) : 0.f;
-                sl += e[k];
-            }
+        for (int g = 0; g < G; g++) {
+            const float nm = -gs[g] * L2E;  // exp(t - m) = ex2(t * log2(e) - m * log2(e)): one FFMA + one MUFU per channel
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < G; i++) {
-                const float o = __shfl_sync(0xffffffffu, sl, (gbase + i) & 31);
-                sum += (peer_mask >> i) & 1u ? o : 0.f;
+            for (int k = 0; k < 4; k++) {
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(t[4 * g + k], L2E, nm)));
+                t[4 * g + k] = e;
+                sum += e;
             }
+            gm[g] = sum;
+        }
+        for (int l = 0; l < ls.n_layers; l++) {
+            const unsigned m = ls.gmask[l];
+            float sum = 0.f;
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if ((m >> g) & 1u) sum += gm[g];
             const float rs = __fdividef(1.0f, sum);
 #pragma unroll
-            for (int k = 0; k < 4; k++) qv[k] = e[k] * rs;
-        } else {
-            for (int l = 0; l < ls.n_layers; l++) {
-                const unsigned m4 = (lmask >> (4 * l)) & 15u;
-                float mx = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 4; k++) mx = fmaxf(mx, (m4 >> k) & 1u ? tv[k] : -INFINITY);
-                const float m = group_gather_max<G>(mx, gbase);
-                float e[4], sl = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    e[k] = (m4 >> k) & 1u ? fast_exp(tv[k] - m) : 0.f;
-                    sl += e[k];
-                }
-                const float rs = __fdividef(1.0f, group_gather_sum<G>(sl, gbase));
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if ((m4 >> k) & 1u) qv[k] = e[k] * rs;
-            }
+            for (int g = 0; g < G; g++)
+                if ((m >> g) & 1u) gs[g] = rs;
         }
-        const float4 q = make_float4(qv[0], qv[1], qv[2], qv[3]);
-        if (valid) {
-            qtile[lp * G + g] = q;
-            if (store_q) reinterpret_cast<float4*>(Q + (size_t)p * Mp)[g] = q;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const float4 v = make_float4(t[4 * g] * gs[g], t[4 * g + 1] * gs[g], t[4 * g + 2] * gs[g], t[4 * g + 3] * gs[g]);
+            t[4 * g] = v.x; t[4 * g + 1] = v.y; t[4 * g + 2] = v.z; t[4 * g + 3] = v.w;
+            if (do_splat) qtile[lp * G + g] = v;
+            if (store_q) reinterpret_cast<float4*>(Q + (size_t)p * MP)[g] = v;
         }
         if (labels) {
-            // gated argmax (segmenter.cpp:645-657) / plain argmax (densecrf.cpp:200-208); ties -> lower label
+            // gated argmax (segmenter.cpp:645-657) / plain argmax (densecrf.cpp:200-208); strict '>' keeps the first maximum
             for (int l = 0; l < ls.n_layers; l++) {
-                const unsigned m4 = (lmask >> (4 * l)) & 15u;
-                const float gate = ls.gate[l];
-                float bv = gate;
-                int best = 1 << 20;
+                const int ca = ls.off[l], cb = ca + ls.count[l];
+                float bv = ls.gate[l];
+                int best = ls.unknown[l] >= 0 ? ls.unknown[l] : 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (((m4 >> k) & 1u) && qv[k] > bv) { bv = qv[k]; best = c0 + k - ls.off[l]; }
-                float fv = gate;
-                int fb = 1 << 20;
-#pragma unroll
-                for (int i = 0; i < G; i++) {  // lanes in channel order: strict '>' keeps the first maximum
-                    const float ov = __shfl_sync(0xffffffffu, bv, (gbase + i) & 31);
-                    const int ob = __shfl_sync(0xffffffffu, best, (gbase + i) & 31);
-                    if (ob < (1 << 20) && ov > fv) { fv = ov; fb = ob; }
-                }
-                if (valid && g == 0)
-                    labels[(size_t)l * N + p] = (uint8_t)(fb < (1 << 20) ? fb : (ls.unknown[l] >= 0 ? ls.unknown[l] : 0));
+                for (int c = 0; c < MP; c++)
+                    if (c >= ca && c < cb && t[c] > bv) { bv = t[c]; best = c - ca; }
+                labels[(size_t)l * N + p] = (uint8_t)best;
             }
         }
-    };
-    // (a register double-buffer that requests step s + 1 before step s gathers its rows was measured slower: it costs
-    // half of the resident warps, and phase 1 is issue-bound, not latency-bound)
-    for (int s = 0; s < steps; s++) {
-        StepIn in0;
-        load_step(s, in0);
-        run_step(s, in0);
     }
     if (!do_splat) return;
-    __syncthreads();  // the tile's marginals are complete (and thread 0's mbarrier.init is visible)
-    {                 // wait for the bulk copies (phase 0 of the barrier)
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&stage_bar);
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(bar) : "memory");
-    }
-    // phase 2: tile-local gather splat out of shared memory
-    {
-        const size_t tbA = (size_t)tile * TP * D1A;
-        gather_entries<G, RSS_TILE_IU>(spairsA, metaA, capA, a.ent_meta[0] + tbA, neA, a.lat[0].vout, qtile);
-    }
-    if constexpr (D1B > 0) {
-        const size_t tbB = (size_t)tile * TP * D1B;
-        gather_entries<G, RSS_TILE_IU>(spairsB, metaB, capB, a.ent_meta[1] + tbB, neB, a.lat[1].vout, qtile);
-    }
+    __syncthreads();  // the tile's marginals are complete
+    mbar_wait(bar1, 0);
+    // ---- phase 2: tile-local gather splat out of shared memory
+    gather_entries<G>(spairsA, metaA, capA, a.lat[0].ent_meta + tbA, neA, a.lat[0].vout, qtile);
+    if constexpr (D1B > 0) gather_entries<G>(spairsB, metaB, capB, a.lat[1].ent_meta + tbB, neB, a.lat[1].vout, qtile);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Blur of every lattice of the CRF in ONE cooperative launch (permutohedral.cpp:555-569).  Phase j blurs axis j of
-// each lattice that has one; phases are separated by a grid barrier on an L2 counter (lattice.cuh).  Prefetching the
-// neighbour pairs ahead of the rows was measured and does not help: the rows' L2 round trip dominates a round.
-// Phase 0 additionally clears `zero` (the table the
-// point kernel sliced from one iteration ago), which becomes the next splat target - so no phase follows the last axis.
+// each lattice that has one; phases are separated by a grid barrier on an L2 counter (lattice.cuh).  A phase is
+// L2-throughput-bound (random 16*G-byte rows): tools/micro/blur_bench.cu.  A MISSING neighbour is the zero row
+// (index vcap): its load is skipped - on sparse lattices a large share of the neighbours is missing, and reading them
+// would send all those requests to the one L2 slice that holds the zero row.
+// Phase 0 additionally clears `zero` (the table the point kernel sliced from one iteration ago), which becomes the
+// next splat target - so no phase follows the last axis.
 // ---------------------------------------------------------------------------------------------------------------
 // one axis of one lattice: items are (vertex, channel group); U independent items per thread are in flight at once
 template <int U>
 __device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4* __restrict__ dst, const int2* __restrict__ nb_j,
-                                          uint32_t items, int G, uint32_t tid, uint32_t nthr) {
+                                          uint32_t items, int G, int vcap, uint32_t tid, uint32_t nthr) {
     for (uint32_t base = tid; base < items; base += U * nthr) {
         int2 nb[U];
         uint32_t gq[U];
@@ -572,10 +612,11 @@ __device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t it = base + u * nthr;
+            x[u] = y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (it < items) {
                 o[u] = __ldcg(src + it);
-                x[u] = __ldcg(src + (size_t)nb[u].x * G + gq[u]);
-                y[u] = __ldcg(src + (size_t)nb[u].y * G + gq[u]);
+                if (nb[u].x != vcap) x[u] = __ldcg(src + (size_t)nb[u].x * G + gq[u]);
+                if (nb[u].y != vcap) y[u] = __ldcg(src + (size_t)nb[u].y * G + gq[u]);
             }
         }
 #pragma unroll
@@ -600,7 +641,7 @@ __global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __
             const float4* src = (j & 1) ? a.pong[k] : a.ping[k];
             float4* dst = (j & 1) ? a.ping[k] : a.pong[k];
             const uint32_t items = V[k] * (uint32_t)G;
-            blur_axis<RSS_BLUR_U>(src, dst, a.nbr[k] + (size_t)j * a.vcap[k], items, G, tid, nthr);
+            blur_axis<RSS_BLUR_U>(src, dst, a.nbr[k] + (size_t)j * a.vcap[k], items, G, (int)a.vcap[k], tid, nthr);
             if (j == 0 && a.zero[k])
                 for (uint32_t it = tid; it < items; it += nthr) __stcg(a.zero[k] + it, make_float4(0.f, 0.f, 0.f, 0.f));
         }
@@ -609,7 +650,7 @@ __global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __
 }
 
 // splat of the all-ones vector for the normalisation (pairwise.cpp:44): values[v][0] += sum of barycentric weights.
-// Same run-accumulation as the point kernel, one thread per chunk, rows of 4 floats with channel 0 live.
+// Run-accumulation over consecutive points, one thread per chunk, rows of 4 floats with channel 0 live.
 template <int D1>
 __global__ void __launch_bounds__(256) splat_ones_runs_kernel(const int* __restrict__ offsets, const float* __restrict__ bary,
                                                               int N, int Pc, const uint32_t* __restrict__ counts,
@@ -645,44 +686,22 @@ __global__ void __launch_bounds__(256) splat_ones_runs_kernel(const int* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static int fused_tile_steps(int G, int TP) {  // warp-steps a CTA needs for TP points: 8 warps x (32 / G) points per step
-    const int per_step = 8 * (32 / G);
-    return (TP + per_step - 1) / per_step;
-}
-// The point kernel is latency-bound per CTA, so ONE full wave of resident CTAs is the sweet spot: when the default
-// tile size would need slightly more tiles than fit at once (sm_count * RSS_TILE_MINB), the tiles grow (up to
-// TILE_MAX_POINTS) until they fit.
-#ifndef RSS_TILE_MAX_POINTS
-#define RSS_TILE_MAX_POINTS 576
-#endif
-constexpr int TILE_MAX_POINTS = RSS_TILE_MAX_POINTS;
-TileMap fused_tile_map(int G, int N, int W, int H, int sm_count) {
+TileMap fused_tile_map(int N, int W, int H) {
     TileMap m;
     m.N = N;
-    const int slots = std::max(1, sm_count * RSS_TILE_MINB);
+    m.TP = TILE_POINTS;
     if (W > 0 && H > 0 && (long long)W * H == N) {
-        m.W = W; m.H = H; m.TW = 32; m.TH = RSS_TILE_POINTS / 32;
+        m.W = W; m.H = H; m.TW = TILE_W; m.TH = TILE_H;
         m.tiles_x = (W + m.TW - 1) / m.TW;
-        if (RSS_TILE_SINGLE_WAVE && m.tiles_x <= slots) {
-            const int rows_fit = slots / m.tiles_x;                 // tile rows of one wave
-            const int th = (H + rows_fit - 1) / rows_fit;           // tile height that makes the image fit in one wave
-            if (th > m.TH && th * m.TW <= TILE_MAX_POINTS) m.TH = th;
-        }
-        m.TP = m.TW * m.TH;
         m.ntiles = m.tiles_x * ((H + m.TH - 1) / m.TH);
     } else {
-        const int per_step = 8 * (32 / G);
         m.W = m.H = 0; m.TW = m.TH = 0; m.tiles_x = 0;
-        m.TP = per_step * std::max(1, (RSS_TILE_POINTS + per_step / 2) / per_step);
-        const long long fit = ((long long)N + slots - 1) / slots;  // points per tile for one wave
-        const int tp_fit = (int)((fit + per_step - 1) / per_step) * per_step;
-        if (RSS_TILE_SINGLE_WAVE && tp_fit > m.TP && tp_fit <= TILE_MAX_POINTS) m.TP = tp_fit;
         m.ntiles = (int)(((long long)N + m.TP - 1) / m.TP);
     }
     return m;
 }
 
-bool fused_group_supported(int G) { return G == 1 || G == 2 || G == 3 || G == 5 || G == 6; }
+bool fused_group_supported(int G) { return G >= 1 && G <= 6; }
 bool fused_signature_supported(int G, int d1a, int d1b) {
     if (!fused_group_supported(G)) return false;
     switch (d1a * 16 + d1b) {
@@ -691,65 +710,68 @@ bool fused_signature_supported(int G, int d1a, int d1b) {
     }
 }
 
-template <int G>
-static void launch_tile_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
-                          uint8_t* labels, const TileMap& tm, const FusedLayers& ls, int mode) {
-    const int TP = tm.TP, steps = fused_tile_steps(G, TP);
-    const int grid = tm.ntiles;
-#define RSS_TILE_M(A, B, M)                                                                                             \
-    do {                                                                                                                \
-        auto kfn = meanfield_tile_kernel<G, A, B, M>;                                                                   \
-        const size_t smem = (size_t)TP * G * sizeof(float4) + (size_t)2 * TP * sizeof(int2) +                           \
-                            (size_t)TP * (A + B) * sizeof(uint2);                                                       \
-        if (c->smem_attr_done.insert((const void*)kfn).second) { /* once per context (= per device) and instantiation */ \
-            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                        \
-            cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  \
-        }                                                                                                               \
-        RSS_LAUNCH_NAMED(c, "meanfield_tile_kernel", kfn, grid, 256, smem, st, a, unary, Q, labels, tm, steps, ls);     \
-    } while (0)
-#define RSS_TILE(A, B)                                                                                                  \
-    do {                                                                                                                \
-        if (mode == 2) RSS_TILE_M(A, B, 2);                                                                             \
-        else if (mode == 3) RSS_TILE_M(A, B, 3);                                                                        \
-        else RSS_TILE_M(A, B, 5);                                                                                       \
-    } while (0)
-    switch (d1a * 16 + d1b) {
-        case 0x46: RSS_TILE(4, 6); break;
-        case 0x36: RSS_TILE(3, 6); break;
-        case 0x70: RSS_TILE(7, 0); break;
-        case 0x60: RSS_TILE(6, 0); break;
-        case 0x40: RSS_TILE(4, 0); break;
-        case 0x30: RSS_TILE(3, 0); break;
-        default: break;
+template <int G, int A, int B, int M>
+static cudaError_t launch_point_m(rss_ctx* c, cudaStream_t st, const FusedArgs& a, const float* unary, float* Q, uint8_t* labels,
+                                  const TileMap& tm, const FusedLayers& ls) {
+    auto kfn = meanfield_point_kernel<G, A, B, M>;
+    const size_t smem = (size_t)TILE_POINTS * G * sizeof(float4) + (size_t)TILE_ROW_CAP * G * sizeof(float4) * (B > 0 ? 2 : 1) +
+                        (size_t)2 * TILE_POINTS * sizeof(int2) + (size_t)TILE_POINTS * (A + B) * sizeof(uint2);
+    if (c->smem_attr_done.insert((const void*)kfn).second) { /* once per context (= per device) and instantiation */
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
     }
-#undef RSS_TILE
-#undef RSS_TILE_M
+    RSS_LAUNCH_NAMED(c, M == 3 ? "meanfield_point_kernel" : (M == 2 ? "meanfield_point_kernel<first>" : "meanfield_point_kernel<last>"),
+                     kfn, tm.ntiles, TILE_POINTS, smem, st, a, unary, Q, labels, tm, ls);
+    return cudaPeekAtLastError();
 }
-void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
-                            uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode) {
+template <int G, int A, int B>
+static cudaError_t launch_point_ab(rss_ctx* c, cudaStream_t st, const FusedArgs& a, const float* unary, float* Q, uint8_t* labels,
+                                   const TileMap& tm, const FusedLayers& ls, int mode) {
+    if (mode == 2) return launch_point_m<G, A, B, 2>(c, st, a, unary, Q, labels, tm, ls);
+    if (mode == 3) return launch_point_m<G, A, B, 3>(c, st, a, unary, Q, labels, tm, ls);
+    return launch_point_m<G, A, B, 5>(c, st, a, unary, Q, labels, tm, ls);
+}
+template <int G>
+static cudaError_t launch_point_g(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
+                                  uint8_t* labels, const TileMap& tm, const FusedLayers& ls, int mode) {
+    switch (d1a * 16 + d1b) {
+        case 0x46: return launch_point_ab<G, 4, 6>(c, st, a, unary, Q, labels, tm, ls, mode);
+        case 0x36: return launch_point_ab<G, 3, 6>(c, st, a, unary, Q, labels, tm, ls, mode);
+        case 0x70: return launch_point_ab<G, 7, 0>(c, st, a, unary, Q, labels, tm, ls, mode);
+        case 0x60: return launch_point_ab<G, 6, 0>(c, st, a, unary, Q, labels, tm, ls, mode);
+        case 0x40: return launch_point_ab<G, 4, 0>(c, st, a, unary, Q, labels, tm, ls, mode);
+        case 0x30: return launch_point_ab<G, 3, 0>(c, st, a, unary, Q, labels, tm, ls, mode);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
+                                   uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode) {
     switch (G) {
-        case 1: launch_tile_g<1>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
-        case 2: launch_tile_g<2>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
-        case 3: launch_tile_g<3>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
-        case 5: launch_tile_g<5>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
-        case 6: launch_tile_g<6>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode); break;
-        default: break;
+        case 1: return launch_point_g<1>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode);
+        case 2: return launch_point_g<2>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode);
+        case 3: return launch_point_g<3>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode);
+        case 4: return launch_point_g<4>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode);
+        case 5: return launch_point_g<5>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode);
+        case 6: return launch_point_g<6>(c, st, a, d1a, d1b, unary, Q, labels, tm, ls, mode);
+        default: return cudaErrorInvalidValue;
     }
 }
 
-void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm,
-                           const TileMap& tm, int d1, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta,
-                           int* tile_nent) {
-    const int grid = tm.ntiles, TP = tm.TP;
+void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, bool pre,
+                           bool post, float slice_scale, const TileMap& tm, int d1, int row_bytes, const uint32_t* counts,
+                           const TileCsrOut& out) {
+    const int grid = tm.ntiles, TP = TILE_POINTS;
     int HC = 1024;  // power of two with load factor <= 0.8 even when every pair of the tile hits a different vertex
     while (HC * 4 < TP * d1 * 5) HC *= 2;
-    const size_t tsm = (size_t)2 * HC * 4 + (size_t)TP * d1 * 2;
+    const size_t tsm = (size_t)4 * HC * 4 + (size_t)TP * d1 * (2 + 8 + 4);
+    const int ipre = pre ? 1 : 0, ipost = post ? 1 : 0;
 #define RSS_TCB(D)                                                                                                      \
     do {                                                                                                                \
         if (c->smem_attr_done.insert((const void*)tile_csr_build_kernel<D>).second)  /* once per context (= per device) */ \
-            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);     \
-        RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, tsm, st, offsets, bary, norm, tm, row_bytes, HC, counts, pairs,    \
-                   ent_meta, tile_nent);                                                                                \
+            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);     \
+        RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, tsm, st, offsets, bary, norm, ipre, ipost, slice_scale, tm,  \
+                   row_bytes, HC, counts, out);                                                                         \
     } while (0)
     switch (d1) {
         case 2: RSS_TCB(2); break;
@@ -764,14 +786,15 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
 }
 
 int blur_multi_grid(const rss_ctx* c) { return c->sm_count; }  // one CTA per SM
-void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
+cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
     const int grid = blur_multi_grid(c), block = RSS_BLUR_MAXT;
     void* args[] = {&a, &G, &barrier, &barrier_base};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }
-    cudaLaunchCooperativeKernel((const void*)blur_multi_coop_kernel, dim3(grid), dim3(block), args, 0, st);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)blur_multi_coop_kernel, dim3(grid), dim3(block), args, 0, st);
     c->launches++;
     if (c->profile) { cudaEventRecord(eb, st); c->prof_pending.push_back(rss_ctx::Pending{"blur_multi_coop_kernel", ea, eb}); }
+    return e;
 }
 
 void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,

@@ -5,11 +5,17 @@
 namespace rss {
 
 constexpr int FUSED_MAX_LAT = 2;
+constexpr int TILE_POINTS = 256;  // points per tile = threads per CTA of the point kernel (one thread per point)
+constexpr int TILE_W = 32, TILE_H = 8;  // pixel block of an image tile
+#ifndef RSS_TILE_ROW_CAP
+#define RSS_TILE_ROW_CAP 160
+#endif
+constexpr int TILE_ROW_CAP = RSS_TILE_ROW_CAP;  // value rows per lattice a tile stages in shared memory (more: read from L2)
 
 // How a tile's local point index maps to the point index.  W == 0: tile t owns the TP consecutive points starting at
 // t * TP (generic point sets).  W > 0: the points are the pixels of a W x H image in raster order and a tile is a
 // TW x TH pixel block - neighbouring pixels in BOTH directions share lattice vertices, so a block touches several
-// times fewer distinct vertices than a strip of the same size (fewer splat atomics, better L1 reuse of value rows).
+// times fewer distinct vertices than a strip of the same size (fewer splat atomics, fewer value rows to stage).
 struct TileMap {
     int N, TP, W, H, TW, TH, tiles_x, ntiles;  // TW is a power of two
 };
@@ -45,35 +51,45 @@ __device__ __forceinline__ int tile_point(const TileMap& m, const TileOrigin& o,
     return (x < m.W && y < m.H) ? y * m.W + x : -1;
 }
 
+// Per-tile data of one lattice, built once per lattice by tile_csr_build_kernel (tile t owns the slice
+// [t * TP * d1, (t + 1) * TP * d1) of every array):
+//   point-major, for the slice: pt_w(j, lp) = barycentric weight * post-normalisation * Potts weight * alpha, and
+//     pt_slot(j, lp) = the tile-local row slot of the vertex (index into the value rows staged in shared memory);
+//   vertex-major, for the splat: the distinct vertices the tile touches, cut into segments of <= TILE_SEG
+//     (local point, weight * pre-normalisation) pairs; tile_vert[slot] = vertex id of a row slot.
 struct FusedLat {
-    const int* offsets;   // [N][d+1] vertex ids
-    const float* bary;    // [N][d+1]
-    const float* norm;    // [N]
-    const float* vin;     // blurred value table of the previous iteration (slice source)
-    float* vout;          // all-zero table receiving this iteration's splat
-    float potts, alpha;   // Potts weight w, slice scale 1/(1+2^-d)
-    int pre, post;        // normalisation applied before the splat / after the slice (NormalizationType)
+    const float* pt_w;         // D1 * TP floats per tile, pt_index() order
+    const uint16_t* pt_slot;   // D1 * TP row slots per tile, pt_index() order
+    const uint2* pairs;        // (byte offset of the local point's row in the shared Q tile, weight bits), by segment
+    const int2* ent_meta;      // per segment: x = start in the tile's pair array | length << 16, y = vertex id
+    const int* tile_vert;      // row slot -> vertex id
+    const int2* tile_info;     // per tile: x = segments, y = distinct vertices (row slots)
+    const float* vin;          // blurred value table of the previous iteration (slice source)
+    float* vout;               // all-zero table receiving this iteration's splat
+    const uint32_t* counts;    // [0] V, [1] overflow flag
 };
 struct FusedArgs {
     FusedLat lat[FUSED_MAX_LAT];
-    const uint32_t* counts[FUSED_MAX_LAT];  // [0] V, [1] overflow flag
-    // tile-local CSR of the splat matrix (tile t owns the slice [t * TP * d1, (t + 1) * TP * d1) of each array)
-    const uint2* pairs[FUSED_MAX_LAT];      // (byte offset of the local point's row in the shared tile, weight bits), by entry
-    const int2* ent_meta[FUSED_MAX_LAT];    // per segment: x = start in the tile's pair array | length << 16, y = vertex id
-    const int* tile_nent[FUSED_MAX_LAT];    // segments per tile
 };
+// Label layers of the CRF in the device channel layout: every layer starts at a multiple of 4 channels (a float4
+// group) and its padding channels carry unary = +inf, so that exp(-unary - max) = 0 without any per-channel predicate.
 struct FusedLayers {
     int n_layers;
-    int off[RSS_MAX_LAYERS + 1];
+    int off[RSS_MAX_LAYERS];      // first channel of the layer (multiple of 4)
+    int count[RSS_MAX_LAYERS];    // labels of the layer
+    unsigned gmask[RSS_MAX_LAYERS];  // bit g: float4 group g belongs to the layer
     int unknown[RSS_MAX_LAYERS];  // < 0: plain argmax
     float gate[RSS_MAX_LAYERS];   // 2 / M_l when gated (segmenter.cpp:647), else -inf
-    int aligned;                  // every layer boundary is a multiple of 4 channels
-    // per channel group g (channels 4g..4g+3): layer membership nibbles (4 bits per layer), and for aligned layers the
-    // group's layer (-1: padding only) and its valid-channel nibble
-    unsigned group_lmask[8];
-    unsigned group_valid[8];
-    int group_layer[8];
 };
+// position of (corner j, local point lp) inside a tile's point-major block of D1 * TILE_POINTS elements: corners are
+// packed in vectors of 4, then 2, then 1, each vector array indexed by lp - so a thread fetches its D1 weights (floats)
+// with ceil-ish(D1 / 4) fully coalesced vector loads, and its D1 row slots (uint16) likewise
+__host__ __device__ constexpr int pt_index(int D1, int j, int lp) {
+    const int n4 = D1 / 4, n2 = (D1 % 4) / 2;
+    if (j < 4 * n4) return ((j / 4) * TILE_POINTS + lp) * 4 + j % 4;
+    if (j < 4 * n4 + 2 * n2) return 4 * n4 * TILE_POINTS + lp * 2 + (j - 4 * n4);
+    return (4 * n4 + 2 * n2) * TILE_POINTS + lp;
+}
 struct BlurMultiArgs {
     int K;
     float4* ping[FUSED_MAX_LAT];  // holds the splat on entry
@@ -84,17 +100,27 @@ struct BlurMultiArgs {
     int d1[FUSED_MAX_LAT];
     uint32_t vcap[FUSED_MAX_LAT];
 };
+// what the build kernel writes for one lattice
+struct TileCsrOut {
+    uint2* pairs;
+    int2* ent_meta;
+    int* tile_vert;
+    int2* tile_info;
+    float* pt_w;
+    uint16_t* pt_slot;
+};
 
-bool fused_group_supported(int G);  // channel-group counts the tile kernel is instantiated for
+bool fused_group_supported(int G);  // channel-group counts the point kernel is instantiated for
 bool fused_signature_supported(int G, int d1a, int d1b);
-TileMap fused_tile_map(int G, int N, int W, int H, int sm_count);  // W = H = 0 for point sets without an image grid
-void launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
-                            uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode);
-void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm,
-                           const TileMap& tm, int d1, int row_bytes, const uint32_t* counts, uint2* pairs, int2* ent_meta,
-                           int* tile_nent);
+TileMap fused_tile_map(int N, int W, int H);  // W = H = 0 for point sets without an image grid
+cudaError_t launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary, float* Q,
+                                   uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode);
+// pre / post: fold norm[] into the splat / slice weights (NormalizationType); slice_scale = Potts weight * alpha
+void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, bool pre,
+                           bool post, float slice_scale, const TileMap& tm, int d1, int row_bytes, const uint32_t* counts,
+                           const TileCsrOut& out);
 int blur_multi_grid(const rss_ctx* c);  // CTAs of the cooperative blur (one barrier arrival each)
-void launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base);
+cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base);
 void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
                             const uint32_t* counts, float* values);
 

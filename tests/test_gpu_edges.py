@@ -322,7 +322,9 @@ def test_corrupt_forest_returns_model_error():
         one += struct.pack("<ii", 1, 0)                               # histograms: 1 node, 0 floats
         one += struct.pack("<iiii", 1, 2, 0, 0)                       # multi: 1 node, 2 layers of 0 classes
         assert load(one) == 4
-        assert load(good) == 0 and c.info.num_trees == 4               # the context is still usable
+        assert load(good) == 0                                         # the context is still usable
+        info = rss.Info()
+        assert lib.rss_get_info(c.h, ctypes.byref(info)) == 0 and info.num_trees == 4 and info.total_classes == 17
 
 
 def test_config_forest_mismatch_is_rejected():
