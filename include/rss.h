@@ -188,6 +188,10 @@ rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, const uint16_t
 
 /* Makes a frame resident on the device (H2D copy only).  Every call that takes rgb/depth_mm accepts NULL for
  * both to work on the resident frame instead: that is how the device-resident throughput is measured. */
+/* The device part of rss_segment_keyframe is captured into a CUDA graph after the first calls with a given size and
+ * parameter set and replayed afterwards (the pose may change from call to call; per-stage timings are only measured on
+ * eager calls).  enable = 0 turns the replay off for this context (on by default; RSS_NO_GRAPH=1 disables it globally). */
+rss_status rss_keyframe_graph(rss_ctx* ctx, int enable);
 rss_status rss_upload_frame(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth_mm, int W, int H);
 /* Page-locked host memory for frame / label staging buffers (so that a C++ host needs no CUDA headers): copies
  * from and to such buffers run at full PCIe rate and asynchronously.  Not tied to a context. */

@@ -226,6 +226,10 @@ class Context:
                                                    C.byref(params), _ptr(labels, C.c_uint8), _ptr(Q, C.c_float)))
         return (labels, Q) if want_Q else labels
 
+    def keyframe_graph(self, enable=True):
+        """Turn the CUDA-graph replay of segment_keyframe's device part on / off for this context (rss_keyframe_graph)."""
+        self._check(self._lib.rss_keyframe_graph(self.h, int(bool(enable))))
+
     def keyframe_lattice_info(self, k):
         """(feature dimension, vertex count) of lattice k of the last segment_keyframe call."""
         d, v = C.c_int(0), C.c_int(0)

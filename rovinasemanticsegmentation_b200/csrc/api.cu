@@ -14,6 +14,7 @@ using namespace rss;
 
 namespace rss {
 void crf_release_cached(rss_ctx* ctx);  // crf.cu
+void keyframe_graph_release(rss_ctx* ctx);  // crf.cu
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
 rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
 rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out = nullptr, int unary_stride = 0);
@@ -302,17 +303,19 @@ static rss_status upload_tables(rss_ctx* ctx) {
 static void free_ctx(rss_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    keyframe_graph_release(ctx);
     crf_release_cached(ctx);
     FrameState& f = ctx->fr;
     DevBuf* bufs[] = {&f.rgb, &f.depth, &f.labels, &f.lab, &f.xyz, &f.dist_a, &f.dist_b, &f.integ, &f.integ_cnt,
                       &f.normals, &f.grad, &f.fin, &f.flags, &f.sidx, &f.scan_tmp, &f.xs, &f.ys, &f.slabels,
                       &f.n_dev, &f.feats, &f.leaf_ids, &f.post, &f.lowres, &f.posteriors, &ctx->forest.nodes,
                       &ctx->forest.tree_off_dev, &ctx->forest.leaves, &ctx->lab_gamma, &ctx->lab_cbrt, &ctx->tapx,
-                      &ctx->tapy, &ctx->feat_xy};
+                      &ctx->tapy, &ctx->feat_xy, &ctx->pose_dev};
     for (DevBuf* b : bufs) b->release();
     ctx->pin_in.release();
     ctx->pin_out.release();
     ctx->pin_small.release();
+    ctx->pin_pose.release();
     for (cudaEvent_t& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     ctx->prof_collect();
@@ -519,7 +522,22 @@ rss_status frame_upload(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth,
 }
 
 // Lab+border on s0; cloud and the normals preparation on s1, joined back into s0.
-rss_status frame_prepare(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float dmin, float dmax) {
+// host part of the pose: M = R * Kinv, row by column, (a0*b0 + a1*b1) + a2*b2 in float (Eigen 3x3 product,
+// feature_extractor.h:223), into the pinned staging block the device copy is refreshed from
+rss_status frame_set_pose(rss_ctx* ctx, const float* Kinv, const float* R, const float* t) {
+    RSS_CU(ctx, ctx->pin_pose.reserve(sizeof(PoseParams)));
+    RSS_CU(ctx, ctx->pose_dev.reserve(sizeof(PoseParams)));
+    PoseParams* p = ctx->pin_pose.as<PoseParams>();
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            const float p0 = R[3 * i] * Kinv[j], p1 = R[3 * i + 1] * Kinv[3 + j], p2 = R[3 * i + 2] * Kinv[6 + j];
+            const float s = p0 + p1;
+            p->M[3 * i + j] = s + p2;
+        }
+    for (int i = 0; i < 3; i++) p->t[i] = t[i];
+    return RSS_OK;
+}
+rss_status frame_prepare(rss_ctx* ctx, float dmin, float dmax) {
     FrameState& f = ctx->fr;
     const HostConfig& cfg = ctx->cfg;
     const int W = f.W, H = f.H, P = cfg.patch_size;
@@ -530,15 +548,8 @@ rss_status frame_prepare(rss_ctx* ctx, const float* Kinv, const float* R, const 
         RSS_CU(ctx, f.xyz.reserve(NP * sizeof(float4)));
         RSS_CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->s0));
         RSS_CU(ctx, cudaStreamWaitEvent(ctx->s1, ctx->ev_fork, 0));
-        // M = R * Kinv, row by column, (a0*b0 + a1*b1) + a2*b2 in float (Eigen 3x3 product, feature_extractor.h:223)
-        float M[9];
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) {
-                const float p0 = R[3 * i] * Kinv[j], p1 = R[3 * i + 1] * Kinv[3 + j], p2 = R[3 * i + 2] * Kinv[6 + j];
-                const float s = p0 + p1;
-                M[3 * i + j] = s + p2;
-            }
-        launch_cloud(ctx, ctx->s1, f.depth.as<uint16_t>(), W, H, M, t, dmin, dmax, f.xyz.as<float4>());
+        RSS_CU(ctx, cudaMemcpyAsync(ctx->pose_dev.ptr, ctx->pin_pose.ptr, sizeof(PoseParams), cudaMemcpyHostToDevice, ctx->s1));
+        launch_cloud(ctx, ctx->s1, f.depth.as<uint16_t>(), W, H, ctx->pose_dev.as<PoseParams>(), dmin, dmax, f.xyz.as<float4>());
         RSS_CU(ctx, cudaEventRecord(ctx->ev_cloud, ctx->s1));
         f.have_cloud = true;
         if (cfg.use_normal) {
@@ -615,31 +626,6 @@ rss_status frame_extract(rss_ctx* ctx, int stride, float dmin, float dmax, int e
     return RSS_OK;
 }
 
-// forest straight from the frame: features evaluated on demand (features.cu), then the summed leaf rows
-rss_status frame_predict_from_frame(rss_ctx* ctx, int n) {
-    FrameState& f = ctx->fr;
-    const ForestDev& F = ctx->forest;
-    const HostConfig& cfg = ctx->cfg;
-    if (!F.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
-    RSS_CU(ctx, f.leaf_ids.reserve((size_t)F.T * (n > 0 ? n : 1) * 4));
-    RSS_CU(ctx, f.post.reserve((size_t)(n > 0 ? n : 1) * F.sumC * 4));
-    int pos = 0, pos_depth = -1, pos_height = -1, pos_normal = -1;
-    const int ncolor = cfg.use_color ? 3 * cfg.patch_size_reduce * cfg.patch_size_reduce : 0;
-    pos = ncolor;
-    if (cfg.use_depth) pos_depth = pos++;
-    if (cfg.use_height) pos_height = pos++;
-    if (cfg.use_normal) pos_normal = pos++;
-    launch_forest_traverse_frame(ctx, ctx->s0, F.nodes.as<Node>(), F.tree_off_dev.as<int>(), F.T, f.lab.as<uchar4>(),
-                                 f.depth.as<uint16_t>(), f.xyz.as<float4>(), f.dist_b.as<float>(), f.integ.as<double>(),
-                                 f.integ_cnt.as<int>(), ctx->tapx.as<ResizeTap>(), ctx->tapy.as<ResizeTap>(),
-                                 ctx->feat_xy.as<uint16_t>(), f.W, f.H, cfg.patch_size, cfg.patch_size_reduce, ncolor,
-                                 pos_depth, pos_height, pos_normal, f.xs.as<int>(), f.ys.as<int>(), n, n, f.leaf_ids.as<int>());
-    launch_forest_posterior(ctx, ctx->s0, F.nodes.as<Node>(), F.tree_off_dev.as<int>(), F.T, F.leaves.as<float>(),
-                            F.sumC, f.leaf_ids.as<int>(), n, n, f.post.as<float>());
-    RSS_CU(ctx, cudaGetLastError());
-    return RSS_OK;
-}
-
 // forest over the device-resident feature matrix
 rss_status frame_predict(rss_ctx* ctx, const float* feats_dev, int n) {
     FrameState& f = ctx->fr;
@@ -690,7 +676,11 @@ rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, 
     if (!ctx->forest.loaded) return ctx->fail(RSS_ERR_STATE, "no forest loaded");
     const int stride = cfg.rf_stride, W = f.W, H = f.H;
     if (W % stride || H % stride) return ctx->fail(RSS_ERR_INVALID, "image size must be a multiple of rf_prediction_stride");
-    return frame_prepare(ctx, Kinv, R, t, cfg.depth_min, cfg.depth_max);
+    if (Kinv) {  // NULL: the caller has already set the pose (keyframe path: before the graph capture / replay)
+        rss_status st = frame_set_pose(ctx, Kinv, R, t);
+        if (st != RSS_OK) return st;
+    }
+    return frame_prepare(ctx, cfg.depth_min, cfg.depth_max);
 }
 // second half: samples, features, forest, low-res scatter, upsample
 // unary_out != NULL: the up-sampled values go, negated, straight into that [pixel][unary_stride] energy matrix and the
@@ -700,22 +690,28 @@ rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out, int 
     const HostConfig& cfg = ctx->cfg;
     const ForestDev& F = ctx->forest;
     const int stride = cfg.rf_stride, W = f.W, H = f.H;
-    rss_status st = frame_extract(ctx, stride, cfg.depth_min, cfg.depth_max, RSS_NO_LABEL, nullptr, 0, false);
-    if (st != RSS_OK) return st;
-    cudaEventRecord(ctx->ev[2], ctx->s0);
-    const int n = f.n_samples;
-    st = frame_predict_from_frame(ctx, n);
-    if (st != RSS_OK) return st;
-    cudaEventRecord(ctx->ev[3], ctx->s0);
+    f.stride = stride; f.gw = rss_div_up(W, stride); f.gh = rss_div_up(H, stride);
+    f.n_samples = -1;  // no sample list on this path: the forest kernel walks the stride grid itself
+    f.have_feats = false;
     const size_t low_elems = (size_t)f.gw * f.gh * F.sumC;
     RSS_CU(ctx, f.lowres.reserve(low_elems * 4));
     if (!unary_out) RSS_CU(ctx, f.posteriors.reserve((size_t)W * H * F.sumC * 4));
-    launch_lowres_fill(ctx, ctx->s0, f.lowres.as<float>(), low_elems, fill);
-    launch_lowres_scatter(ctx, ctx->s0, f.post.as<float>(), F.sumC, f.xs.as<int>(), f.ys.as<int>(), n, stride, f.gw, f.gh,
-                          F.L, F.C, f.lowres.as<float>());
+    ctx->mark(2);
+    const int ncolor = cfg.use_color ? 3 * cfg.patch_size_reduce * cfg.patch_size_reduce : 0;
+    int pos = ncolor, pos_depth = -1, pos_height = -1, pos_normal = -1;
+    if (cfg.use_depth) pos_depth = pos++;
+    if (cfg.use_height) pos_height = pos++;
+    if (cfg.use_normal) pos_normal = pos++;
+    const float dmin_mm = (float)(cfg.depth_min * 1000.0), dmax_mm = (float)(cfg.depth_max * 1000.0);  // feature_extractor.h:43-44
+    launch_forest_frame_lowres(ctx, ctx->s0, F.nodes.as<Node>(), F.tree_off_dev.as<int>(), F.T, F.leaves.as<float>(), F.L, F.C,
+                               f.lab.as<uchar4>(), f.depth.as<uint16_t>(), f.xyz.as<float4>(), f.dist_b.as<float>(),
+                               f.integ.as<double>(), f.integ_cnt.as<int>(), ctx->tapx.as<ResizeTap>(), ctx->tapy.as<ResizeTap>(),
+                               ctx->feat_xy.as<uint16_t>(), W, H, cfg.patch_size, cfg.patch_size_reduce, ncolor, pos_depth,
+                               pos_height, pos_normal, stride, dmin_mm, dmax_mm, fill, f.lowres.as<float>());
+    ctx->mark(3);
     if (unary_out) launch_upsample(ctx, ctx->s0, f.lowres.as<float>(), f.gw, f.gh, W, H, F.L, F.C, unary_out, unary_stride);
     else launch_upsample(ctx, ctx->s0, f.lowres.as<float>(), f.gw, f.gh, W, H, F.L, F.C, f.posteriors.as<float>());
-    cudaEventRecord(ctx->ev[4], ctx->s0);
+    ctx->mark(4);
     RSS_CU(ctx, cudaGetLastError());
     f.have_post = unary_out == nullptr;
     return RSS_OK;
@@ -754,7 +750,9 @@ extern "C" rss_status rss_extract_features(rss_ctx* ctx, const uint8_t* rgb, con
         RSS_CU(ctx, f.labels.reserve(NP * n_label_layers));
         RSS_CU(ctx, cudaMemcpyAsync(f.labels.ptr, labels, NP * n_label_layers, cudaMemcpyHostToDevice, ctx->s0));
     }
-    st = frame_prepare(ctx, Kinv, R, t, dmin, dmax);
+    st = frame_set_pose(ctx, Kinv, R, t);
+    if (st != RSS_OK) return st;
+    st = frame_prepare(ctx, dmin, dmax);
     if (st != RSS_OK) return st;
     st = frame_extract(ctx, stride, dmin, dmax, extract_type, labels ? f.labels.as<int8_t>() : nullptr, n_label_layers);
     if (st != RSS_OK) return st;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -14,6 +15,13 @@
 
 namespace rss {
 
+// number of device (re)allocations so far in this process: a captured CUDA graph holds raw pointers, so it is only
+// replayed while this counter has not moved since the capture
+inline std::atomic<uint64_t>& device_alloc_events() {
+    static std::atomic<uint64_t> n{0};
+    return n;
+}
+
 // grow-only device / pinned-host buffers: no cudaMalloc on the steady-state path
 struct DevBuf {
     void* ptr = nullptr;
@@ -24,6 +32,7 @@ struct DevBuf {
         ptr = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
+        device_alloc_events()++;
         cudaError_t e = cudaMalloc(&ptr, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -67,6 +76,12 @@ struct __align__(16) Node {
 struct __align__(8) ResizeTap {
     short i0, i1;  // the two source indices (already clipped to the ROI)
     short w0, w1;  // 11-bit weights
+};
+
+// camera pose of the current frame as the kernels read it (device copy: rss_ctx::pose_dev)
+struct PoseParams {
+    float M[9];  // R * Kinv
+    float t[3];  // camera centre
 };
 
 struct HostConfig {
@@ -138,6 +153,14 @@ struct rss_ctx {
     rss::DevBuf tapx, tapy;           // ResizeTap[(P+1)][r]
     rss::DevBuf feat_xy;              // u16[r*r]: patch pixel k -> dx | dy << 8
     rss::PinBuf pin_in, pin_out, pin_small;
+    rss::PinBuf pin_pose;             // PoseParams staging: rewritten before every frame, copied by a (capturable) H2D
+    rss::DevBuf pose_dev;             // PoseParams
+    struct KeyframeGraph* kf_graph = nullptr;  // captured device part of rss_segment_keyframe (crf.cu)
+    bool graph_enabled = true;
+    bool capturing = false;           // the device part of a keyframe is being captured: no per-stage timing events
+    void mark(int i) {                // per-stage timing event on s0 (eager runs only)
+        if (!capturing) cudaEventRecord(ev[i], s0);
+    }
     rss_timings tim = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t launches = 0;
     std::set<const void*> smem_attr_done;  // kernels whose dynamic shared memory limit was raised on this device

@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(256) feat_xyzrgb_kernel(int N, const float* __
 // keyframe features from the frame's own buffers: back-projected points / sigma (invalid depth -> NaN is replaced
 // by the camera centre, i.e. depth 0), and (x, y, r, g, b) / sigma
 __global__ void __launch_bounds__(256) feat_frame_xyz_kernel(int N, const float4* __restrict__ xyz, float inv_sigma,
-                                                             float tx, float ty, float tz, float* __restrict__ f) {
+                                                             const PoseParams* __restrict__ pose, float* __restrict__ f) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     float4 v = xyz[p];
-    if (isnan(v.x)) { v.x = tx; v.y = ty; v.z = tz; }
+    if (isnan(v.x)) { v.x = pose->t[0]; v.y = pose->t[1]; v.z = pose->t[2]; }
     f[3 * (size_t)p] = __fmul_rn(v.x, inv_sigma);
     f[3 * (size_t)p + 1] = __fmul_rn(v.y, inv_sigma);
     f[3 * (size_t)p + 2] = __fmul_rn(v.z, inv_sigma);
@@ -482,6 +482,7 @@ rss_status crf_run(rss_crf* crf, int iters, const int* unknown, uint8_t* labels_
             const bool pre = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_BEFORE;
             const bool post = L.norm_type == RSS_NORMALIZE_SYMMETRIC || L.norm_type == RSS_NORMALIZE_AFTER;
             float* vals = lattice_splat_blur(ctx, sk, L, Q, Mp, pre ? L.norm.as<float>() : nullptr, Mp);
+            if (!vals) return ctx->fail(RSS_ERR_CUDA, std::string("cooperative blur launch: ") + cudaGetErrorString(cudaGetLastError()));
             if (K > 1) RSS_CU(ctx, cudaEventRecord(crf->ev_join[k], sk));
             sa.offsets[k] = L.offsets.as<int>();
             sa.bary[k] = L.bary.as<float>();
@@ -787,6 +788,7 @@ extern "C" rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float
         RSS_LAUNCH(ctx, interleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, stage, N, crf->M[l], M,
                    crf->hoff[l], Mp, crf->moff[l], 1.0f, padded);
     float* vals = lattice_splat_blur(ctx, ctx->s0, L, padded, Mp, nullptr, Mp);
+    if (!vals) return ctx->fail(RSS_ERR_CUDA, std::string("cooperative blur launch: ") + cudaGetErrorString(cudaGetLastError()));
     lattice_slice(ctx, ctx->s0, L, vals, Mp, Mp, M <= 2 ? 1 : 0, sliced, Mp);
     for (int l = 0; l < crf->n_layers; l++)
         RSS_LAUNCH(ctx, deinterleave_kernel, rss_div_up((long long)N * crf->M[l], 256), 256, 0, ctx->s0, sliced, N, crf->M[l], Mp,
@@ -931,7 +933,94 @@ rss_status frame_upload(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth,
 rss_status frame_segment_resident(rss_ctx* ctx, const float* Kinv, const float* R, const float* t, float fill);
 rss_status frame_segment_begin(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
 rss_status frame_segment_finish(rss_ctx* ctx, float fill, float* unary_out = nullptr, int unary_stride = 0);
+rss_status frame_set_pose(rss_ctx* ctx, const float* Kinv, const float* R, const float* t);
 void frame_collect_timings(rss_ctx* ctx, bool with_d2h);
+}
+
+// The device part of a keyframe, captured once into a CUDA graph and replayed: ~60 launches on four streams, no host
+// synchronisation inside (sample selection, vertex counts and overflow flags all stay on the device).  The graph holds
+// raw pointers and launch parameters, so it is only replayed while (W, H, parameters) are those of the capture and no
+// device buffer has been reallocated since; the pose travels through rss_ctx::pose_dev, so it may change every frame.
+struct KeyframeGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t alloc_gen = 0;      // device_alloc_events() at capture time
+    int W = 0, H = 0;
+    rss_keyframe_params prm{};
+    uint64_t launches = 0;       // kernel launches inside the graph
+    // stability detection: the previous eager call's signature and the allocation counter after it
+    int prev_W = 0, prev_H = 0;
+    rss_keyframe_params prev_prm{};
+    uint64_t prev_alloc_gen = ~0ull;
+    bool broken = false;         // a capture failed on this context: stay eager
+};
+namespace rss {
+void keyframe_graph_release(rss_ctx* ctx) {
+    if (!ctx->kf_graph) return;
+    if (ctx->kf_graph->exec) cudaGraphExecDestroy(ctx->kf_graph->exec);
+    delete ctx->kf_graph;
+    ctx->kf_graph = nullptr;
+}
+}  // namespace rss
+
+static bool same_params(const rss_keyframe_params& a, const rss_keyframe_params& b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+// everything between the frame upload and the label download; the frame is resident, the pose is in pin_pose
+static rss_status keyframe_enqueue(rss_ctx* ctx, rss_crf* crf, int W, int H, const rss_keyframe_params* prm) {
+    const int N = W * H;
+    float* f3 = crf->feat_stage.as<float>();
+    float* f5 = f3 + (size_t)N * 3;
+    cudaStream_t sA = crf->side[0], sB = crf->side[1];
+    rss_status st;
+    // lattices of the previous keyframe are rebuilt in place (pooled buffers keep their capacity)
+    while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
+    RSS_CU(ctx, cudaEventRecord(crf->ev_fork, ctx->s0));
+    RSS_CU(ctx, cudaStreamWaitEvent(sB, crf->ev_fork, 0));
+    RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(N, 256), 256, 0, sB, W, H, prm->sigma_px, prm->sigma_px,
+               prm->sigma_rgb, prm->sigma_rgb, prm->sigma_rgb, ctx->fr.rgb.as<uint8_t>(), f5);
+    // Enqueue order = start order: the bilateral lattice needs only the colour image, so its whole construction is
+    // queued on sB first; then the first half of the frame path (Lab on s0, cloud + normals on s1); then the Gaussian
+    // lattice on sA behind the cloud; then the forest and the up-sample.  kernels[0] = Gaussian, kernels[1] = bilateral.
+    Lattice* pooled[2] = {nullptr, nullptr};  // [0] 3-D, [1] 5-D buffers from the previous keyframe
+    for (Lattice* L : crf->pool) pooled[L->d == 3 ? 0 : 1] = L;
+    crf->pool.clear();
+    if (pooled[1]) crf->pool.push_back(pooled[1]);
+    st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false, true);
+    if (st != RSS_OK) return st;
+    st = frame_segment_begin(ctx, nullptr, nullptr, nullptr);
+    if (st != RSS_OK) return st;
+    RSS_CU(ctx, cudaStreamWaitEvent(sA, ctx->ev_cloud, 0));
+    RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, sA, N, ctx->fr.xyz.as<float4>(), 1.0f / prm->sigma_xyz,
+               ctx->pose_dev.as<PoseParams>(), f3);
+    if (pooled[0]) crf->pool.push_back(pooled[0]);
+    st = crf_add_kernel_dev(crf, sA, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, false, true);
+    if (st != RSS_OK) return st;
+    std::swap(crf->kernels[0], crf->kernels[1]);
+    // the up-sample writes the energies (-log-posteriors, src/segmenter.cpp:642) straight into the CRF's unary matrix
+    st = frame_segment_finish(ctx, prm->fill, crf->unary.as<float>(), crf->Mp);
+    if (st != RSS_OK) return st;
+    RSS_CU(ctx, cudaEventRecord(crf->ev_join[0], sA));
+    RSS_CU(ctx, cudaEventRecord(crf->ev_join[1], sB));
+    // ---- the mean-field loop once both lattices are ready
+    ctx->mark(8);
+    RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[0], 0));
+    RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[1], 0));
+    ctx->mark(9);
+    int unk[RSS_MAX_LAYERS];
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = l < ctx->cfg.layer_count ? ctx->cfg.unknown_label[l] : 0;
+    st = crf_run(crf, prm->iters, unk, crf->labels.as<uint8_t>());
+    if (st != RSS_OK) return st;
+    ctx->mark(10);
+    // vertex counts and overflow flags of both lattices -> pinned memory (read after the final synchronisation)
+    for (size_t k = 0; k < crf->kernels.size(); k++)
+        RSS_CU(ctx, cudaMemcpyAsync(ctx->pin_small.as<uint32_t>() + 2 * k, crf->kernels[k]->counts.ptr, 8, cudaMemcpyDeviceToHost,
+                                    ctx->s0));
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_keyframe_graph(rss_ctx* ctx, int enable) {
+    if (!ctx) return RSS_ERR_INVALID;
+    ctx->graph_enabled = enable != 0;
+    return RSS_OK;
 }
 
 extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* depth_mm, int W, int H,
@@ -952,6 +1041,8 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
             if (ctx->cfg.class_counts[l] != F.C[l])
                 return ctx->fail(RSS_ERR_STATE, "config and forest disagree on the class count of a label layer");
     }
+    if (W % ctx->cfg.rf_stride || H % ctx->cfg.rf_stride)
+        return ctx->fail(RSS_ERR_INVALID, "image size must be a multiple of rf_prediction_stride");
     const int N = W * H;
     rss_crf* crf = ctx->keyframe_crf;
     rss_status st;
@@ -963,59 +1054,67 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     }
     crf->grid_w = W; crf->grid_h = H;
     RSS_CU(ctx, crf->feat_stage.reserve((size_t)N * 8 * 4));
-    float* f3 = crf->feat_stage.as<float>();
-    float* f5 = f3 + (size_t)N * 3;
-    cudaStream_t sA = crf->side[0], sB = crf->side[1];
-    // ---- upload; the bilateral lattice only needs the colour image, so its construction starts right away on sB
+    RSS_CU(ctx, ctx->pin_small.reserve(64));
+    if (!ctx->kf_graph) ctx->kf_graph = new KeyframeGraph();
+    KeyframeGraph& G = *ctx->kf_graph;
+    // ---- upload (outside the graph: the host pointers are the caller's) and the pose staging block
     cudaEventRecord(ctx->ev[0], ctx->s0);
     st = frame_upload(ctx, rgb, depth_mm, W, H);
     if (st != RSS_OK) return st;
     cudaEventRecord(ctx->ev[1], ctx->s0);
+    st = frame_set_pose(ctx, Kinv, R, t);
+    if (st != RSS_OK) return st;
+    const bool want_graph = ctx->graph_enabled && !ctx->profile && !G.broken && !getenv("RSS_NO_GRAPH");
+    bool staged = false;  // per-stage events recorded (eager runs only)
     for (int attempt = 0;; attempt++) {
-        // lattices of the previous keyframe are rebuilt in place (pooled buffers keep their capacity)
-        while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
-        RSS_CU(ctx, cudaEventRecord(crf->ev_fork, ctx->s0));
-        RSS_CU(ctx, cudaStreamWaitEvent(sB, crf->ev_fork, 0));
-        RSS_LAUNCH(ctx, feat_bilateral_kernel, rss_div_up(N, 256), 256, 0, sB, W, H, prm->sigma_px, prm->sigma_px,
-                   prm->sigma_rgb, prm->sigma_rgb, prm->sigma_rgb, ctx->fr.rgb.as<uint8_t>(), f5);
-        // Enqueue order = start order: the bilateral lattice needs only the colour image, so its whole construction is
-        // queued on sB first; then the first half of the frame path (Lab on s0, cloud + normals on s1); then the Gaussian
-        // lattice on sA behind the cloud; only then the rest of the frame path, which contains the one host
-        // synchronisation (sample count).  kernels[0] = Gaussian, kernels[1] = bilateral (slot order of the mean field).
-        Lattice* pooled[2] = {nullptr, nullptr};  // [0] 3-D, [1] 5-D buffers from the previous keyframe
-        for (Lattice* L : crf->pool) pooled[L->d == 3 ? 0 : 1] = L;
-        crf->pool.clear();
-        if (pooled[1]) crf->pool.push_back(pooled[1]);
-        st = crf_add_kernel_dev(crf, sB, f5, 5, prm->w_bilateral, RSS_NORMALIZE_SYMMETRIC, false, true);
-        if (st != RSS_OK) return st;
-        if (attempt == 0) {
-            st = frame_segment_begin(ctx, Kinv, R, t);
-            if (st != RSS_OK) return st;
+        const uint64_t gen = device_alloc_events().load();
+        bool ran = false;
+        if (want_graph && attempt == 0 && G.exec && G.W == W && G.H == H && same_params(G.prm, *prm) && G.alloc_gen == gen) {
+            // steady state: replay.  The frame-state flags the eager path maintains:
+            ctx->fr.have_cloud = ctx->cfg.use_height || ctx->cfg.use_normal;
+            ctx->fr.have_lab = ctx->cfg.use_color;
+            ctx->fr.have_integral = ctx->cfg.use_normal;
+            ctx->fr.have_post = false;
+            RSS_CU(ctx, cudaGraphLaunch(G.exec, ctx->s0));
+            ctx->launches += G.launches;
+            ran = true;
+        } else if (want_graph && attempt == 0 && G.prev_alloc_gen == gen && G.prev_W == W && G.prev_H == H &&
+                   same_params(G.prev_prm, *prm)) {
+            // the previous (eager) keyframe had this signature and nothing has been allocated since: capture
+            if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+            const uint64_t l0 = ctx->launches;
+            ctx->capturing = true;
+            cudaError_t e = cudaStreamBeginCapture(ctx->s0, cudaStreamCaptureModeThreadLocal);
+            rss_status cs = RSS_ERR_CUDA;
+            cudaGraph_t graph = nullptr;
+            if (e == cudaSuccess) {
+                cs = keyframe_enqueue(ctx, crf, W, H, prm);
+                e = cudaStreamEndCapture(ctx->s0, &graph);
+            }
+            ctx->capturing = false;
+            if (e == cudaSuccess && cs == RSS_OK && device_alloc_events().load() == gen)
+                e = cudaGraphInstantiate(&G.exec, graph, 0);
+            else if (e == cudaSuccess)
+                e = cudaErrorUnknown;
+            if (graph) cudaGraphDestroy(graph);
+            if (e == cudaSuccess) {
+                G.W = W; G.H = H; G.prm = *prm; G.alloc_gen = gen;
+                G.launches = ctx->launches - l0;
+                RSS_CU(ctx, cudaGraphLaunch(G.exec, ctx->s0));
+                ran = true;
+            } else {  // not capturable here (driver, or an allocation slipped in): stay eager on this context
+                cudaGetLastError();
+                G.exec = nullptr;
+                G.broken = true;
+                ctx->launches = l0;
+            }
         }
-        RSS_CU(ctx, cudaStreamWaitEvent(sA, ctx->ev_cloud, 0));
-        RSS_LAUNCH(ctx, feat_frame_xyz_kernel, rss_div_up(N, 256), 256, 0, sA, N, ctx->fr.xyz.as<float4>(),
-                   1.0f / prm->sigma_xyz, t[0], t[1], t[2], f3);
-        if (pooled[0]) crf->pool.push_back(pooled[0]);
-        st = crf_add_kernel_dev(crf, sA, f3, 3, prm->w_gauss, RSS_NORMALIZE_SYMMETRIC, false, true);
-        if (st != RSS_OK) return st;
-        std::swap(crf->kernels[0], crf->kernels[1]);
-        if (attempt == 0) {
-            // the up-sample writes the energies (-log-posteriors, src/segmenter.cpp:642) straight into the CRF's unary matrix
-            st = frame_segment_finish(ctx, prm->fill, crf->unary.as<float>(), crf->Mp);
+        if (!ran) {
+            st = keyframe_enqueue(ctx, crf, W, H, prm);
             if (st != RSS_OK) return st;
+            staged = true;
         }
-        RSS_CU(ctx, cudaEventRecord(crf->ev_join[0], sA));
-        RSS_CU(ctx, cudaEventRecord(crf->ev_join[1], sB));
-        // ---- the mean-field loop once both lattices are ready
-        cudaEventRecord(ctx->ev[8], ctx->s0);
-        RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[0], 0));
-        RSS_CU(ctx, cudaStreamWaitEvent(ctx->s0, crf->ev_join[1], 0));
-        cudaEventRecord(ctx->ev[9], ctx->s0);
-        int unk[RSS_MAX_LAYERS];
-        for (int l = 0; l < RSS_MAX_LAYERS; l++) unk[l] = l < ctx->cfg.layer_count ? ctx->cfg.unknown_label[l] : 0;
-        st = crf_run(crf, prm->iters, unk, crf->labels.as<uint8_t>());
-        if (st != RSS_OK) return st;
-        cudaEventRecord(ctx->ev[10], ctx->s0);
+        G.prev_W = W; G.prev_H = H; G.prev_prm = *prm;
         if (labels) RSS_CU(ctx, cudaMemcpyAsync(labels, crf->labels.ptr, (size_t)N * F.L, cudaMemcpyDeviceToHost, ctx->s0));
         if (Qout) {
             float* dstQ = Qout;
@@ -1029,16 +1128,36 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
         }
         cudaEventRecord(ctx->ev[5], ctx->s0);
         RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+        G.prev_alloc_gen = device_alloc_events().load();
+        // overflow flags (pinned copies made at the end of the device part)
         bool overflow = false;
-        st = crf_lattice_overflow(crf, &overflow);
-        if (st != RSS_OK) return st;
-        if (!overflow) break;  // otherwise: rebuild with larger hash tables and run the CRF again (rare)
+        for (size_t k = 0; k < crf->kernels.size(); k++) {
+            Lattice* L = crf->kernels[k];
+            const uint32_t* h = ctx->pin_small.as<uint32_t>() + 2 * k;
+            L->V_host = (int)h[0];
+            if (h[1]) {
+                const uint64_t maxv = (uint64_t)crf->N * (L->d + 1);
+                if ((uint64_t)L->hcap >= 2 * next_pow2(2 * maxv) || L->hcap >= (1u << 30))
+                    return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
+                L->want_hcap = L->hcap * 4;
+                overflow = true;
+            }
+        }
+        if (!overflow) break;
+        // rebuild with larger hash tables and run again, eagerly (rare); the captured graph no longer fits
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        G.prev_alloc_gen = ~0ull;
     }
-    frame_collect_timings(ctx, false);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]); ctx->tim.lattice_ms = ms;  // lattice time NOT hidden behind the frame path
-    cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]); ctx->tim.meanfield_ms = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[5]); ctx->tim.d2h_ms = ms;
+    ctx->tim = rss_timings{0, 0, 0, 0, 0, 0, 0, 0};
+    if (staged) {
+        frame_collect_timings(ctx, false);
+        cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]); ctx->tim.lattice_ms = ms;  // lattice time NOT hidden behind the frame path
+        cudaEventElapsedTime(&ms, ctx->ev[9], ctx->ev[10]); ctx->tim.meanfield_ms = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[5]); ctx->tim.d2h_ms = ms;
+    } else {
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->tim.h2d_ms = ms;
+    }
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[5]); ctx->tim.total_ms = ms;
     return RSS_OK;
 }

@@ -51,12 +51,12 @@ void launch_lab_border(rss_ctx* c, cudaStream_t st, const uint8_t* rgb, int W, i
 // F3: point cloud (:200-232).  rect = ((m0*v0 + m1*v1) + m2*v2) + t with v = [d*x, d*y, d], NaN when the
 // depth (in metres, float) is outside [dmin, dmax].  One thread per pixel, float4 store.
 // ------------------------------------------------------------------------------------------------
-struct CloudParams {
-    float M[9];
-    float t[3];
-};
-__global__ void __launch_bounds__(256) cloud_kernel(const uint16_t* __restrict__ depth, int W, int H, CloudParams p,
-                                                    float dmin, float dmax, float4* __restrict__ xyz) {
+// The pose (M = R * Kinv, t) is read from device memory (rss_ctx::pose_dev), not passed by value: the keyframe's CUDA
+// graph is captured once and replayed with a new pose every keyframe.
+__global__ void __launch_bounds__(256) cloud_kernel(const uint16_t* __restrict__ depth, int W, int H,
+                                                    const PoseParams* __restrict__ pose, float dmin, float dmax,
+                                                    float4* __restrict__ xyz) {
+    const PoseParams p = *pose;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const size_t i = (size_t)y * W + x;
@@ -78,13 +78,10 @@ __global__ void __launch_bounds__(256) cloud_kernel(const uint16_t* __restrict__
     }
     xyz[i] = make_float4(o[0], o[1], o[2], 0.f);
 }
-void launch_cloud(rss_ctx* c, cudaStream_t st, const uint16_t* depth, int W, int H, const float M[9],
-                  const float t[3], float dmin, float dmax, float4* xyz) {
-    CloudParams p;
-    for (int i = 0; i < 9; i++) p.M[i] = M[i];
-    for (int i = 0; i < 3; i++) p.t[i] = t[i];
+void launch_cloud(rss_ctx* c, cudaStream_t st, const uint16_t* depth, int W, int H, const PoseParams* pose_dev, float dmin,
+                  float dmax, float4* xyz) {
     dim3 grid(rss_div_up(W, 256), H);
-    RSS_LAUNCH(c, cloud_kernel, grid, 256, 0, st, depth, W, H, p, dmin, dmax, xyz);
+    RSS_LAUNCH(c, cloud_kernel, grid, 256, 0, st, depth, W, H, pose_dev, dmin, dmax, xyz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -235,70 +232,142 @@ __device__ __forceinline__ Node load_node_ro(const Node* p) {
 #ifndef RSS_FOREST_MINB
 #define RSS_FOREST_MINB 4  // resident CTAs per SM: the traversal is a chain of dependent loads, more warps hide it
 #endif
-__global__ void __launch_bounds__(256, RSS_FOREST_MINB) forest_traverse_frame_kernel(
-    const Node* __restrict__ nodes, const int* __restrict__ tree_off, int T, const uchar4* __restrict__ lab,
-    const uint16_t* __restrict__ depth, const float4* __restrict__ xyz, const float* __restrict__ dist,
-    const double* __restrict__ integ, const int* __restrict__ cnt, const ResizeTap* __restrict__ tapx,
-    const ResizeTap* __restrict__ tapy, const uint16_t* __restrict__ feat_xy, int W, int H, int P, int r, int ncolor,
-    int pos_depth, int pos_height, int pos_normal, const int* __restrict__ xs, const int* __restrict__ ys, int n, int ld,
-    int* __restrict__ leaf_ids) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)n * T) return;
-    // tree-major: the 32 lanes of a warp walk the SAME tree for 32 consecutive samples (neighbouring pixels), so near
-    // the root they visit the same nodes, take the same feature branch and read neighbouring pixels
-    const int t = (int)(gid / n), s = (int)(gid - (long long)t * n);
-    const Node* tree = nodes + tree_off[t];
-    const int x = xs[s], y = ys[s];
-    const size_t i = (size_t)y * W + x;
-    const int Wb = W + 2 * P;
-    const float dm = __fdiv_rn((float)depth[i], 1000.0f);
-    const int half = patch_half(P, dm);
-    const uchar4* roi = lab + (size_t)(y + P - half) * Wb + (x + P - half);
-    const ResizeTap* tx_h = tapx + half * r;
-    const ResizeTap* ty_h = tapy + half * r;
+struct FrameFeat {  // everything the on-demand feature evaluation reads
+    const uchar4* lab;
+    const uint16_t* depth;
+    const float4* xyz;
+    const float* dist;
+    const double* integ;
+    const int* cnt;
+    const ResizeTap* tapx;
+    const ResizeTap* tapy;
+    const uint16_t* feat_xy;
+    int W, H, P, r, ncolor, pos_depth, pos_height, pos_normal;
+};
+// findLeafNode for the sample at pixel (x, y); returns the leaf's row in the dense leaf table
+__device__ __forceinline__ int traverse_frame(const Node* __restrict__ tree, const FrameFeat& F, int x, int y) {
+    const size_t i = (size_t)y * F.W + x;
+    const int Wb = F.W + 2 * F.P;
+    const float dm = __fdiv_rn((float)F.depth[i], 1000.0f);
+    const int half = patch_half(F.P, dm);
+    const uchar4* roi = F.lab + (size_t)(y + F.P - half) * Wb + (x + F.P - half);
+    const ResizeTap* tx_h = F.tapx + half * F.r;
+    const ResizeTap* ty_h = F.tapy + half * F.r;
     bool have_normal = false;
     float normal_feature = 0.f;
-    int node = 0;
     Node nd = load_node_ro(tree);
     while (nd.left != 0) {
         float v;
         const int f = nd.feat;
-        if (f < ncolor) {
+        if (f < F.ncolor) {
             const int k = f / 3, ch = f - 3 * k;
-            const int xy = __ldg(feat_xy + k);
+            const int xy = __ldg(F.feat_xy + k);
             const ResizeTap tx = tx_h[xy & 255], ty = ty_h[xy >> 8];
             const uchar4 p00 = __ldg(roi + (size_t)ty.i0 * Wb + tx.i0), p01 = __ldg(roi + (size_t)ty.i0 * Wb + tx.i1);
             const uchar4 p10 = __ldg(roi + (size_t)ty.i1 * Wb + tx.i0), p11 = __ldg(roi + (size_t)ty.i1 * Wb + tx.i1);
             const int a = ch == 0 ? p00.x : (ch == 1 ? p00.y : p00.z), b = ch == 0 ? p01.x : (ch == 1 ? p01.y : p01.z);
             const int c = ch == 0 ? p10.x : (ch == 1 ? p10.y : p10.z), d = ch == 0 ? p11.x : (ch == 1 ? p11.y : p11.z);
             v = (float)sat_u8(resize_blend(a, b, c, d, tx.w0, tx.w1, ty.w0, ty.w1));
-        } else if (f == pos_depth) {
+        } else if (f == F.pos_depth) {
             v = dm;
-        } else if (f == pos_height) {
-            v = xyz[i].z;
+        } else if (f == F.pos_height) {
+            v = F.xyz[i].z;
         } else {
             if (!have_normal) {
-                const float3 nrm = pcl_normal_at(xyz, dist, integ, cnt, W, H, x, y);
+                const float3 nrm = pcl_normal_at(F.xyz, F.dist, F.integ, F.cnt, F.W, F.H, x, y);
                 normal_feature = isnan(nrm.x) ? -2.0f : (float)acos(fabs((double)nrm.z));
                 have_normal = true;
             }
             v = normal_feature;
         }
-        node = v < nd.thr ? nd.left : nd.left + 1;
-        nd = load_node_ro(tree + node);
+        nd = load_node_ro(tree + (v < nd.thr ? nd.left : nd.left + 1));
     }
-    leaf_ids[(size_t)t * ld + s] = node;
+    return nd.leaf;
 }
-void launch_forest_traverse_frame(rss_ctx* c, cudaStream_t st, const Node* nodes, const int* tree_off, int T,
-                                  const uchar4* lab, const uint16_t* depth, const float4* xyz, const float* dist,
-                                  const double* integ, const int* cnt, const ResizeTap* tapx, const ResizeTap* tapy,
-                                  const uint16_t* feat_xy, int W, int H, int P, int r, int ncolor, int pos_depth,
-                                  int pos_height, int pos_normal, const int* xs, const int* ys, int n, int ld,
-                                  int* leaf_ids) {
-    if (n <= 0) return;
-    RSS_LAUNCH(c, forest_traverse_frame_kernel, rss_div_up((long long)n * T, 256), 256, 0, st, nodes, tree_off, T, lab,
-               depth, xyz, dist, integ, cnt, tapx, tapy, feat_xy, W, H, P, r, ncolor, pos_depth, pos_height, pos_normal, xs,
-               ys, n, ld, leaf_ids);
+
+// The frame worker's forest stage in ONE kernel (segmenter.cpp:349-376): for the 32 consecutive stride-grid positions
+// of a CTA, warp w walks tree t0 + w for all 32 positions (tree-major: the lanes of a warp visit the same nodes near the
+// root and read neighbouring pixels), the leaf rows meet in shared memory, and the CTA sums them IN TREE ORDER
+// (RandomForest::multiClassLogPosterior, classifier.cpp:187-208: tree 0's row, then += trees 1..T-1, so the sums are
+// bit-identical) and writes the per-layer low-resolution images [gh][gw][C_l] directly - `fill` where the depth is out
+// of range (the reference's pre-fill).  No sample list, no leaf-id buffer, no count on the host.
+constexpr int FOREST_WARPS = 4;
+struct ForestLayers {
+    int L, sumC;
+    int C[RSS_MAX_LAYERS];
+    int coff[RSS_MAX_LAYERS];
+};
+__global__ void __launch_bounds__(32 * FOREST_WARPS, RSS_FOREST_MINB)
+    forest_frame_lowres_kernel(const Node* __restrict__ nodes, const int* __restrict__ tree_off, int T,
+                               const float* __restrict__ leaves, const ForestLayers fl, const FrameFeat F, int stride, int gw,
+                               int gh, float dmin_mm, float dmax_mm, float fill, float* __restrict__ lowres) {
+    __shared__ int srow[FOREST_WARPS][32];
+    __shared__ unsigned svalid;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g0 = blockIdx.x * 32, g = g0 + lane, ncell = gw * gh;
+    const int x = (g % gw) * stride, y = (g / gw) * stride;
+    bool ok = false;
+    if (g < ncell) {
+        const float d = (float)F.depth[(size_t)y * F.W + x];  // sample selection, feature_extractor.h:43-44,62
+        ok = d >= dmin_mm && d <= dmax_mm;
+    }
+    const unsigned valid = __ballot_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) svalid = valid;
+    // output element o of the CTA: layers back to back, inside a layer (position, class) - the order of the low-res image
+    constexpr int NT = 32 * FOREST_WARPS;
+    const int npos = min(32, ncell - g0), nout = npos * fl.sumC;
+    float acc[8];  // ceil(32 * sumC / NT) <= 8 for sumC <= 32
+    for (int t0 = 0; t0 < T; t0 += FOREST_WARPS) {
+        const int t = t0 + w;
+        if (t < T && ok) srow[w][lane] = traverse_frame(nodes + tree_off[t], F, x, y);
+        __syncthreads();
+        const int nt = min(FOREST_WARPS, T - t0);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int o = threadIdx.x + k * NT;
+            if (o >= nout) break;
+            int l = 0;
+            while (l + 1 < fl.L && o >= npos * fl.coff[l + 1]) l++;
+            const int q = o - npos * fl.coff[l], pos = q / fl.C[l], cl = q - pos * fl.C[l];
+            if (!((svalid >> pos) & 1u)) continue;
+            float a = t0 == 0 ? 0.f : acc[k];
+            for (int i = 0; i < nt; i++) {
+                const float h = __ldg(leaves + (size_t)srow[i][pos] * fl.sumC + fl.coff[l] + cl);
+                a = (t0 + i == 0) ? h : __fadd_rn(a, h);
+            }
+            acc[k] = a;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int o = threadIdx.x + k * NT;
+        if (o >= nout) break;
+        int l = 0;
+        while (l + 1 < fl.L && o >= npos * fl.coff[l + 1]) l++;
+        const int q = o - npos * fl.coff[l], pos = q / fl.C[l];
+        lowres[(size_t)ncell * fl.coff[l] + (size_t)g0 * fl.C[l] + q] = ((svalid >> pos) & 1u) ? acc[k] : fill;
+    }
+}
+void launch_forest_frame_lowres(rss_ctx* c, cudaStream_t st, const Node* nodes, const int* tree_off, int T, const float* leaves,
+                                int L, const int* C, const uchar4* lab, const uint16_t* depth, const float4* xyz,
+                                const float* dist, const double* integ, const int* cnt, const ResizeTap* tapx,
+                                const ResizeTap* tapy, const uint16_t* feat_xy, int W, int H, int P, int r, int ncolor,
+                                int pos_depth, int pos_height, int pos_normal, int stride, float dmin_mm, float dmax_mm,
+                                float fill, float* lowres) {
+    const int gw = rss_div_up(W, stride), gh = rss_div_up(H, stride);
+    ForestLayers fl;
+    fl.L = L;
+    int off = 0;
+    for (int l = 0; l < RSS_MAX_LAYERS; l++) {
+        fl.C[l] = l < L ? C[l] : 0;
+        fl.coff[l] = off;
+        off += fl.C[l];
+    }
+    fl.sumC = off;
+    const FrameFeat F{lab, depth, xyz, dist, integ, cnt, tapx, tapy, feat_xy, W, H, P, r, ncolor, pos_depth, pos_height, pos_normal};
+    RSS_LAUNCH(c, forest_frame_lowres_kernel, rss_div_up((long long)gw * gh, 32), 32 * FOREST_WARPS, 0, st, nodes, tree_off, T,
+               leaves, fl, F, stride, gw, gh, dmin_mm, dmax_mm, fill, lowres);
 }
 
 void launch_scalar_features(rss_ctx* c, cudaStream_t st, const uint16_t* depth, const float4* xyz,

@@ -8,9 +8,9 @@ namespace rss {
 // ---- features.cu -----------------------------------------------------------------------------
 // cvtColor(BGR2Lab) + copyMakeBorder(REFLECT, P) fused; lab is uchar4 per bordered pixel
 void launch_lab_border(rss_ctx* c, cudaStream_t st, const uint8_t* rgb, int W, int H, int P, uchar4* lab);
-// per-pixel back-projection (feature_extractor.h:200-232); M = R*Kinv (host, float), xyz as float4
-void launch_cloud(rss_ctx* c, cudaStream_t st, const uint16_t* depth, int W, int H, const float M[9],
-                  const float t[3], float dmin, float dmax, float4* xyz);
+// per-pixel back-projection (feature_extractor.h:200-232); pose_dev: M = R*Kinv (host, float) and t, xyz as float4
+void launch_cloud(rss_ctx* c, cudaStream_t st, const uint16_t* depth, int W, int H, const PoseParams* pose_dev, float dmin,
+                  float dmax, float4* xyz);
 // sample selection (:56-121): flags per grid position
 void launch_select(rss_ctx* c, cudaStream_t st, const uint16_t* depth, const int8_t* labels, int n_label_layers,
                    int extract_type, int W, int H, int stride, float dmin_mm, float dmax_mm, uint32_t* flags);
@@ -26,13 +26,14 @@ void launch_scalar_features(rss_ctx* c, cudaStream_t st, const uint16_t* depth, 
                             const int* xs, const int* ys, int n, float* feats, int D, int pos_depth,
                             int pos_height, int pos_normal);
 
-// forest traversal with the features evaluated on demand from the frame (no materialised feature matrix)
-void launch_forest_traverse_frame(rss_ctx* c, cudaStream_t st, const Node* nodes, const int* tree_off, int T,
-                                  const uchar4* lab, const uint16_t* depth, const float4* xyz, const float* dist,
-                                  const double* integ, const int* cnt, const ResizeTap* tapx, const ResizeTap* tapy,
-                                  const uint16_t* feat_xy, int W, int H, int P, int r, int ncolor, int pos_depth,
-                                  int pos_height, int pos_normal, const int* xs, const int* ys, int n, int ld,
-                                  int* leaf_ids);
+// the frame worker's forest stage in one kernel: on-demand features, traversal, leaf rows summed in tree order, the
+// per-layer low-resolution images written directly (`fill` where the depth is out of range)
+void launch_forest_frame_lowres(rss_ctx* c, cudaStream_t st, const Node* nodes, const int* tree_off, int T, const float* leaves,
+                                int L, const int* C, const uchar4* lab, const uint16_t* depth, const float4* xyz,
+                                const float* dist, const double* integ, const int* cnt, const ResizeTap* tapx,
+                                const ResizeTap* tapy, const uint16_t* feat_xy, int W, int H, int P, int r, int ncolor,
+                                int pos_depth, int pos_height, int pos_normal, int stride, float dmin_mm, float dmax_mm,
+                                float fill, float* lowres);
 
 // ---- normals.cu (PCL IntegralImageNormalEstimation, AVERAGE_3D_GRADIENT) ---------------------------
 // dist_b receives the final distance map; grad: float[6][H*W], fin: u8[2][H*W] scratch

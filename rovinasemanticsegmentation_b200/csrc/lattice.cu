@@ -577,7 +577,27 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     return RSS_OK;
 }
 
-// splat -> (d+1) blurs; returns the table holding the blurred values.  in: [N][in_stride] (in_stride % 4 == 0).
+// blur_coop_kernel on tables a (input) / b with G float4 items per vertex: result in a when d+1 is even, else in b; the
+// other table comes out all zero
+static cudaError_t launch_blur_coop(rss_ctx* ctx, cudaStream_t st, Lattice& L, float4* pa, float4* pb, int G) {
+    const int2* pn = L.nbr.as<int2>();
+    const uint32_t* pc = L.counts.as<uint32_t>();
+    int Garg = G, d1arg = L.d + 1;
+    uint32_t vc = L.vcap;
+    unsigned int* bar = L.counts.as<unsigned int>() + 8;  // counts[8]: the barrier word, zeroed at build time
+    const int grid = ctx->sm_count;
+    unsigned int base = L.barrier_base;
+    L.barrier_base += (unsigned int)d1arg * (unsigned int)grid;
+    void* args[] = {&pa, &pb, &pn, &pc, &Garg, &d1arg, &vc, &bar, &base};
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (ctx->profile) { ea = ctx->prof_event(); eb = ctx->prof_event(); cudaEventRecord(ea, st); }
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)blur_coop_kernel, dim3(grid), dim3(512), args, 0, st);
+    ctx->launches++;
+    if (ctx->profile) { cudaEventRecord(eb, st); ctx->prof_pending.push_back(rss_ctx::Pending{"blur_coop_kernel", ea, eb}); }
+    return e;
+}
+
+// splat -> (d+1) blurs; returns the table holding the blurred values (NULL when the launch failed).  in: [N][in_stride] (in_stride % 4 == 0).
 // Invariant: L.splat_target is all zero on entry; on exit the other table is (or becomes) the next target.
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
                           int Mp) {
@@ -589,22 +609,7 @@ float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float
                L.csr_w.as<float>(), in, in_stride, norm, G, Mp, a);
     const bool small = (size_t)L.vcap * G <= (size_t)BLUR_COOP_MAX_ITEMS;
     if (small) {
-        float4* pa = reinterpret_cast<float4*>(a);
-        float4* pb = reinterpret_cast<float4*>(b);
-        const int2* pn = L.nbr.as<int2>();
-        const uint32_t* pc = L.counts.as<uint32_t>();
-        int Garg = G, d1arg = d1;
-        uint32_t vc = L.vcap;
-        unsigned int* bar = L.counts.as<unsigned int>() + 8;  // counts[8]: the barrier word, zeroed at build time
-        const int grid = ctx->sm_count;
-        unsigned int base = L.barrier_base;
-        L.barrier_base += (unsigned int)d1 * (unsigned int)grid;
-        void* args[] = {&pa, &pb, &pn, &pc, &Garg, &d1arg, &vc, &bar, &base};
-        cudaEvent_t ea = nullptr, eb = nullptr;
-        if (ctx->profile) { ea = ctx->prof_event(); eb = ctx->prof_event(); cudaEventRecord(ea, st); }
-        cudaLaunchCooperativeKernel((const void*)blur_coop_kernel, dim3(grid), dim3(512), args, 0, st);
-        ctx->launches++;
-        if (ctx->profile) { cudaEventRecord(eb, st); ctx->prof_pending.push_back(rss_ctx::Pending{"blur_coop_kernel", ea, eb}); }
+        if (launch_blur_coop(ctx, st, L, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), G) != cudaSuccess) return nullptr;
     } else {
         float* s = a;
         float* d = b;
@@ -658,19 +663,28 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
                    L.seg_begin.as<uint32_t>(), L.seg_end.as<uint32_t>(), L.counts.as<uint32_t>(), L.csr_w.as<float>(), a);
     else  // no CSR (keyframe path): run-accumulating scatter over the points
         launch_splat_ones_runs(ctx, st, L.offsets.as<int>(), L.bary.as<float>(), N, d1, L.counts.as<uint32_t>(), a);
+    // all d+1 axes in one cooperative launch when the table is small (one float4 item per vertex); it leaves the result in
+    // `s` and has already cleared the other table
     float* s = a;
     float* d = b;
-    for (int j = 0; j < d1; j++) {
-        RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<const float4*>(s),
-                   reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), 1, (int)L.vcap);
-        float* t = s; s = d; d = t;
+    const bool small = (size_t)L.vcap <= (size_t)BLUR_COOP_MAX_ITEMS;
+    if (small) {
+        RSS_CU(ctx, launch_blur_coop(ctx, st, L, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), 1));
+        s = (d1 % 2 == 0) ? a : b;
+        d = (d1 % 2 == 0) ? b : a;
+    } else {
+        for (int j = 0; j < d1; j++) {
+            RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<const float4*>(s),
+                       reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap, L.counts.as<uint32_t>(), 1, (int)L.vcap);
+            float* t = s; s = d; d = t;
+        }
+        RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(d),
+                   L.counts.as<uint32_t>(), 1);
     }
     lattice_slice(ctx, st, L, s, 1, 4, 1, norm, 1);
     RSS_LAUNCH(ctx, norm_kernel, rss_div_up(N, 256), 256, 0, st, norm, N, L.norm_type);
-    // both tables are dirty in their first V*4 floats: clear them again for the filter proper
-    RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(a),
-               L.counts.as<uint32_t>(), 1);
-    RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(b),
+    // the result table is dirty in its first V*4 floats: clear it again for the filter proper
+    RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap, 256), 256, 0, st, reinterpret_cast<float4*>(s),
                L.counts.as<uint32_t>(), 1);
     RSS_CU(ctx, cudaGetLastError());
     return RSS_OK;

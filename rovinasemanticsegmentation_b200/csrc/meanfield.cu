@@ -799,7 +799,7 @@ cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int 
 
 void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
                             const uint32_t* counts, float* values) {
-    const int Pc = 16;
+    const int Pc = 4;  // points per thread: short runs, but 4x the threads of a 16-point chunk (the kernel is latency-bound)
     const int grid = rss_div_up(rss_div_up(N, Pc), 256);
 #define RSS_ONES(D) RSS_LAUNCH(c, splat_ones_runs_kernel<D>, grid, 256, 0, st, offsets, bary, N, Pc, counts, values)
     switch (d1) {
