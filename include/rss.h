@@ -168,6 +168,26 @@ rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx, const int3
 rss_status rss_crf_add_pairwise_xyzrgb(rss_crf* crf, const float* xyz, const float* rgb, float wxyz, float wrgb,
                                        float potts_w);
 
+/* The same map worker with the cloud, the key frames' posteriors and the index images all ON THE DEVICE
+ * (src/segmenter.cpp:559-637): nothing but the cloud goes up and nothing but the labels comes down.
+ *   rss_crf_set_cloud        uploads the local map's points (xyz, rgb: host [N][3] floats, N = the CRF's point count) once.
+ *   rss_posteriors_keep      copies the posteriors left resident by the last rss_segment_frame into device slot `slot`
+ *                            (slots grow on demand): the frame worker runs ahead of the map worker (:349-434 vs :518-719),
+ *                            so a local map's key frames are segmented before the map is fused.
+ *   rss_crf_project_accumulate  the projector of :581 as a z-buffer kernel (pinhole K row-major 3x3, key-frame pose R, t:
+ *                            camera -> map, nearest pixel, z in [zmin, zmax], the nearest point wins a pixel, equal z: the
+ *                            lower index), then unaries[l](c, idx) += posterior of that pixel (:597-616) straight from
+ *                            slot `slot` (-1: the posteriors of the last rss_segment_frame).  index_image_out: optional
+ *                            host [H][W] int32 copy of the index image (diagnostics / parity).
+ *   rss_crf_add_pairwise_cloud  the 6-D kernel of :629-637 from the resident cloud.
+ * fps_mapper's projector is not vendored in the reference; the projection rule above is this library's definition
+ * (oracle: orc_project_zbuffer). */
+rss_status rss_crf_set_cloud(rss_crf* crf, const float* xyz, const float* rgb);
+rss_status rss_posteriors_keep(rss_ctx* ctx, int slot);
+rss_status rss_crf_project_accumulate(rss_crf* crf, rss_ctx* frame_ctx, int slot, int W, int H, const float K[9],
+                                      const float R[9], const float t[3], float zmin, float zmax, int32_t* index_image_out);
+rss_status rss_crf_add_pairwise_cloud(rss_crf* crf, float wxyz, float wrgb, float potts_w);
+
 /* ---------------------------------------------------------------------------------------------------
  * Fused keyframe: rss_segment_frame, then per layer a DenseCRF over the frame's W*H pixels with
  * unary = -posteriors, a Gaussian kernel on the frame's 3-D points (xyz / sigma_xyz, weight w_gauss) and

@@ -229,8 +229,9 @@ class Lattice:
             self.h = None
 
 
-def crf_inference(unary, kernels, iters):
-    """unary: (N, M) energies; kernels: list of (feats (N,d), potts_w).  Returns Q (N, M)."""
+def crf_inference(unary, kernels, iters, norm_type=3):
+    """unary: (N, M) energies; kernels: list of (feats (N,d), potts_w); norm_type: pairwise.h NormalizationType
+    (3 = NORMALIZE_SYMMETRIC, the reference's default).  Returns Q (N, M)."""
     unary = np.ascontiguousarray(unary, np.float32)
     N, M = unary.shape
     keep = [np.ascontiguousarray(f, np.float32) for f, _ in kernels]
@@ -240,8 +241,18 @@ def crf_inference(unary, kernels, iters):
         arr[k].d = f.shape[1]
         arr[k].potts_w = w
     Q = np.empty_like(unary)
-    lib().orc_crf_inference(N, M, _p(unary, C.c_float), arr, len(kernels), iters, _p(Q, C.c_float))
+    lib().orc_crf_inference_ex(N, M, _p(unary, C.c_float), arr, len(kernels), iters, int(norm_type), _p(Q, C.c_float))
     return Q
+
+
+def project_zbuffer(xyz, K, R, t, W, H, zmin, zmax):
+    """Pinhole z-buffer projection of a cloud (map frame) into a key frame: (H, W) int32 index image, -1 = empty."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    K, R, t = _calib(K, R, t)
+    out = np.empty((H, W), np.int32)
+    lib().orc_project_zbuffer(_p(xyz, C.c_float), xyz.shape[0], _p(K, C.c_float), _p(R, C.c_float), _p(t, C.c_float), W, H,
+                              C.c_float(zmin), C.c_float(zmax), _p(out, C.c_int32))
+    return out
 
 
 def unary_accumulate(index_image, posterior, unary):
@@ -361,6 +372,47 @@ class RefForest:
         if getattr(self, "h", None):
             ref().ref_forest_free(self.h)
             self.h = None
+
+
+def ref_crf_inference(unary, kernels, iters, norm_type=3, want_map=False):
+    """DenseCRF::inference of the UNMODIFIED reference (densecrf.cpp / pairwise.cpp / labelcompatibility.cpp / unary.cpp
+    compiled against oracle/shim's Eigen stand-in).  Same arguments as crf_inference."""
+    unary = np.ascontiguousarray(unary, np.float32)
+    N, M = unary.shape
+    keep = [np.ascontiguousarray(f, np.float32) for f, _ in kernels]
+    K = len(kernels)
+    fp = (C.POINTER(C.c_float) * max(1, K))(*[_p(f, C.c_float) for f in keep])
+    d = (C.c_int * max(1, K))(*[f.shape[1] for f in keep])
+    w = (C.c_float * max(1, K))(*[float(k[1]) for k in kernels])
+    Q = np.empty_like(unary)
+    mp = np.empty(N, np.int16) if want_map else None
+    ref().ref_crf_inference(N, M, _p(unary, C.c_float), fp, d, w, K, int(norm_type), int(iters), _p(Q, C.c_float),
+                            _p(mp, C.c_int16) if want_map else None)
+    return (Q, mp) if want_map else Q
+
+
+def ref_crf2d_inference(W, H, unary, gauss, bilateral, im, iters):
+    """DenseCRF2D with addPairwiseGaussian(sx, sy, w) + addPairwiseBilateral(sx, sy, sr, sg, sb, im, w) of the reference."""
+    unary = np.ascontiguousarray(unary, np.float32)
+    im = np.ascontiguousarray(im, np.uint8)
+    M = unary.shape[1]
+    Q = np.empty_like(unary)
+    mp = np.empty(W * H, np.int16)
+    f = C.c_float
+    ref().ref_crf2d_inference(W, H, M, _p(unary, f), f(gauss[0]), f(gauss[1]), f(gauss[2]), f(bilateral[0]), f(bilateral[1]),
+                              f(bilateral[2]), f(bilateral[3]), f(bilateral[4]), _p(im, C.c_uint8), f(bilateral[5]), int(iters),
+                              _p(Q, f), _p(mp, C.c_int16))
+    return Q, mp
+
+
+def ref_crf_step_inference(unary, feats, w, steps):
+    unary = np.ascontiguousarray(unary, np.float32)
+    feats = np.ascontiguousarray(feats, np.float32)
+    N, M = unary.shape
+    Q = np.empty_like(unary)
+    ref().ref_crf_step_inference(N, M, _p(unary, C.c_float), _p(feats, C.c_float), feats.shape[1], C.c_float(w), int(steps),
+                                 _p(Q, C.c_float))
+    return Q
 
 
 class RefLattice:

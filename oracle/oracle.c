@@ -718,16 +718,29 @@ static void exp_and_normalize(float* out, const float* in, int M, int N) { /* de
         for (int k = 0; k < M; k++) o[k] = o[k] / s;
     }
 }
-void orc_crf_inference(int N, int M, const float* unary, const orc_pairwise* kernels, int K, int iters, float* Q) {
+/* norm_type: pairwise.h NormalizationType (0 NO_NORMALIZATION, 1 NORMALIZE_BEFORE, 2 NORMALIZE_AFTER, 3 NORMALIZE_SYMMETRIC) */
+void orc_crf_inference_ex(int N, int M, const float* unary, const orc_pairwise* kernels, int K, int iters, int norm_type,
+                          float* Q) {
     orc_lattice** lat = (orc_lattice**)malloc(sizeof(void*) * (K > 0 ? K : 1));
     float** norm = (float**)malloc(sizeof(void*) * (K > 0 ? K : 1));
     float* ones = (float*)malloc(sizeof(float) * N);
     for (int i = 0; i < N; i++) ones[i] = 1.f;
-    for (int k = 0; k < K; k++) { /* pairwise.cpp:40-62, NORMALIZE_SYMMETRIC */
+    const int pre = norm_type == 3 || norm_type == 1;  /* pairwise.cpp:65: SYMMETRIC || (BEFORE && !transpose) */
+    const int post = norm_type == 3 || norm_type == 2; /* pairwise.cpp:78: SYMMETRIC || (AFTER && !transpose) */
+    for (int k = 0; k < K; k++) { /* pairwise.cpp:40-62 */
         lat[k] = orc_lattice_init(kernels[k].feats, kernels[k].d, N);
         norm[k] = (float*)malloc(sizeof(float) * N);
         orc_lattice_compute(lat[k], ones, 1, norm[k]);
-        for (int i = 0; i < N; i++) norm[k][i] = (float)(1.0 / sqrt((double)norm[k][i] + 1e-20));
+        if (norm_type == 0) { /* :46-52: every point gets N / sum(norm); NO filter-time scaling (:65,:78) */
+            float mean_norm = 0;
+            for (int i = 0; i < N; i++) mean_norm += norm[k][i];
+            mean_norm = N / mean_norm;
+            for (int i = 0; i < N; i++) norm[k][i] = mean_norm;
+        } else if (norm_type == 3) {
+            for (int i = 0; i < N; i++) norm[k][i] = (float)(1.0 / sqrt((double)norm[k][i] + 1e-20));
+        } else {
+            for (int i = 0; i < N; i++) norm[k][i] = (float)(1.0 / ((double)norm[k][i] + 1e-20));
+        }
     }
     float* tmp1 = (float*)malloc(sizeof(float) * (size_t)M * N);
     float* tmp2 = (float*)malloc(sizeof(float) * (size_t)M * N);
@@ -736,20 +749,52 @@ void orc_crf_inference(int N, int M, const float* unary, const orc_pairwise* ker
     for (int it = 0; it < iters; it++) {
         for (size_t i = 0; i < (size_t)M * N; i++) tmp1[i] = -unary[i];
         for (int k = 0; k < K; k++) {
-            for (int i = 0; i < N; i++) /* pairwise.cpp:65-66 out = in*norm */
-                for (int c = 0; c < M; c++) tmp2[(size_t)i * M + c] = Q[(size_t)i * M + c] * norm[k][i];
+            for (int i = 0; i < N; i++) /* pairwise.cpp:65-68 out = in*norm, or out = in */
+                for (int c = 0; c < M; c++) tmp2[(size_t)i * M + c] = pre ? Q[(size_t)i * M + c] * norm[k][i] : Q[(size_t)i * M + c];
             orc_lattice_compute(lat[k], tmp2, M, tmp2);
             for (int i = 0; i < N; i++)
                 for (int c = 0; c < M; c++) {
-                    float v = tmp2[(size_t)i * M + c] * norm[k][i]; /* pairwise.cpp:78-79 */
-                    v = -kernels[k].potts_w * v;                    /* labelcompatibility.cpp:46-48 */
-                    tmp1[(size_t)i * M + c] -= v;                   /* densecrf.cpp:126 */
+                    float v = tmp2[(size_t)i * M + c];
+                    if (post) v = v * norm[k][i];       /* pairwise.cpp:78-79 */
+                    v = -kernels[k].potts_w * v;        /* labelcompatibility.cpp:46-48 */
+                    tmp1[(size_t)i * M + c] -= v;       /* densecrf.cpp:126 */
                 }
         }
         exp_and_normalize(Q, tmp1, M, N);
     }
     for (int k = 0; k < K; k++) { orc_lattice_free(lat[k]); free(norm[k]); }
     free(lat); free(norm); free(ones); free(tmp1); free(tmp2);
+}
+void orc_crf_inference(int N, int M, const float* unary, const orc_pairwise* kernels, int K, int iters, float* Q) {
+    orc_crf_inference_ex(N, M, unary, kernels, K, iters, 3, Q);
+}
+/* The projector of src/segmenter.cpp:581 (fps_mapper's pinhole projector, un-vendored) as THIS project defines it: points
+ * of the cloud (map frame) -> camera frame with the key-frame pose (R, t: camera -> map), pinhole projection with K
+ * (row-major 3x3: fx 0 cx / 0 fy cy / 0 0 1), nearest pixel, z inside [zmin, zmax]; per pixel the index of the NEAREST point
+ * wins (z-buffer; equal z: the lower index), -1 where nothing projects.  All arithmetic in float, every operation rounded
+ * separately, in this order. */
+void orc_project_zbuffer(const float* xyz, int N, const float* K, const float* R, const float* t, int W, int H, float zmin,
+                         float zmax, int* index_image) {
+    const float fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+    float* zbuf = (float*)malloc(sizeof(float) * (size_t)W * H);
+    for (size_t i = 0; i < (size_t)W * H; i++) { index_image[i] = -1; zbuf[i] = 0.f; }
+    for (int i = 0; i < N; i++) {
+        const float dx = xyz[3 * (size_t)i] - t[0], dy = xyz[3 * (size_t)i + 1] - t[1], dz = xyz[3 * (size_t)i + 2] - t[2];
+        /* p_cam = R^T (p - t): column k of R dotted with d, ((a + b) + c) */
+        float s;
+        s = R[0] * dx; s = s + R[3] * dy; const float x = s + R[6] * dz;
+        s = R[1] * dx; s = s + R[4] * dy; const float y = s + R[7] * dz;
+        s = R[2] * dx; s = s + R[5] * dy; const float z = s + R[8] * dz;
+        if (!(z >= zmin && z <= zmax)) continue;
+        const float iz = 1.0f / z;
+        float u = fx * x; u = u * iz; u = u + cx;
+        float v = fy * y; v = v * iz; v = v + cy;
+        const float fu = floorf(u + 0.5f), fv = floorf(v + 0.5f);
+        if (!(fu >= 0.f && fu < (float)W && fv >= 0.f && fv < (float)H)) continue;
+        const size_t pix = (size_t)(int)fv * W + (int)fu;
+        if (index_image[pix] < 0 || z < zbuf[pix]) { index_image[pix] = i; zbuf[pix] = z; }
+    }
+    free(zbuf);
 }
 void orc_unary_accumulate(const int* index_image, int npix, const float* posterior, int C, float* unary) {
     for (int p = 0; p < npix; p++) { /* segmenter.cpp:599-616 */

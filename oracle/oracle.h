@@ -82,7 +82,12 @@ typedef struct {
 } orc_pairwise;
 /* unary: M x N col-major energies; Q out: M x N.  NORMALIZE_SYMMETRIC, Potts. (densecrf.cpp:115-131) */
 void orc_crf_inference(int N, int M, const float* unary, const orc_pairwise* kernels, int K, int iters, float* Q);
+/* the same with an explicit NormalizationType (pairwise.h: 0 NO, 1 BEFORE, 2 AFTER, 3 SYMMETRIC) */
+void orc_crf_inference_ex(int N, int M, const float* unary, const orc_pairwise* kernels, int K, int iters, int norm_type,
+                          float* Q);
 /* segmenter.cpp:597-616: unary(c,idx) += posterior[px*C + c] for idx>=0 */
+void orc_project_zbuffer(const float* xyz, int N, const float* K, const float* R, const float* t, int W, int H, float zmin,
+                         float zmax, int* index_image);
 void orc_unary_accumulate(const int* index_image, int npix, const float* posterior, int C, float* unary);
 /* segmenter.cpp:645-657 */
 void orc_gated_argmax(const float* Q, int M, int N, int unknown_label, uint8_t* labels);

@@ -13,6 +13,7 @@
 
 #include "libforest/libforest.h"
 #include "permutohedral.h"
+#include "densecrf.h"
 
 extern "C" {
 
@@ -128,5 +129,60 @@ void ref_lattice_neighbors(void* l, int d, int* nb) {
         }
 }
 void ref_lattice_free(void* l) { delete (RefLattice*)l; }
+
+// ---------------------------------------------------------------------------------------------
+// DenseCRF glue, verbatim: densecrf.cpp (inference, expAndNormalize, currentMap, DenseCRF2D feature builders),
+// pairwise.cpp (DenseKernel::initLattice / filter, all four NormalizationTypes), labelcompatibility.cpp (Potts),
+// unary.cpp - compiled against the Eigen stand-in of oracle/shim.
+// ---------------------------------------------------------------------------------------------
+// unary, Q: M x N column-major (= the (N, M) row-major arrays of the Python side); feats[k]: d[k] x N column-major.
+// The call sequence is the map worker's (src/segmenter.cpp:639-643): setUnaryEnergy, addPairwiseEnergy(feature,
+// new PottsCompatibility(w)) with the default DIAG_KERNEL, then inference(iters); map (optional) = currentMap(Q).
+void ref_crf_inference(int N, int M, const float* unary, const float* const* feats, const int* d, const float* w, int K,
+                       int norm_type, int iters, float* Q, short* map) {
+    DenseCRF crf(N, M);
+    Eigen::MatrixXf U(M, N);
+    memcpy(U.data(), unary, sizeof(float) * (size_t)M * N);
+    crf.setUnaryEnergy(U);
+    for (int k = 0; k < K; k++) {
+        Eigen::MatrixXf f(d[k], N);
+        memcpy(f.data(), feats[k], sizeof(float) * (size_t)d[k] * N);
+        crf.addPairwiseEnergy(f, new PottsCompatibility(w[k]), DIAG_KERNEL, (NormalizationType)norm_type);
+    }
+    Eigen::MatrixXf R = crf.inference(iters);
+    memcpy(Q, R.data(), sizeof(float) * (size_t)M * N);
+    if (map) {
+        VectorXs m = crf.currentMap(R);
+        for (int i = 0; i < N; i++) map[i] = m[i];
+    }
+}
+// examples/dense_inference.cpp's model: DenseCRF2D with addPairwiseGaussian + addPairwiseBilateral (densecrf.cpp:61-81)
+void ref_crf2d_inference(int W, int H, int M, const float* unary, float gsx, float gsy, float gw, float bsx, float bsy,
+                         float bsr, float bsg, float bsb, const unsigned char* im, float bw, int iters, float* Q, short* map) {
+    DenseCRF2D crf(W, H, M);
+    Eigen::MatrixXf U(M, W * H);
+    memcpy(U.data(), unary, sizeof(float) * (size_t)M * W * H);
+    crf.setUnaryEnergy(U);
+    crf.addPairwiseGaussian(gsx, gsy, new PottsCompatibility(gw));
+    crf.addPairwiseBilateral(bsx, bsy, bsr, bsg, bsb, im, new PottsCompatibility(bw));
+    Eigen::MatrixXf R = crf.inference(iters);
+    memcpy(Q, R.data(), sizeof(float) * (size_t)M * W * H);
+    if (map) {
+        VectorXs m = crf.currentMap(R);
+        for (int i = 0; i < W * H; i++) map[i] = m[i];
+    }
+}
+// startInference / stepInference (densecrf.cpp:178-199)
+void ref_crf_step_inference(int N, int M, const float* unary, const float* feats, int d, float w, int steps, float* Q) {
+    DenseCRF crf(N, M);
+    Eigen::MatrixXf U(M, N), f(d, N);
+    memcpy(U.data(), unary, sizeof(float) * (size_t)M * N);
+    memcpy(f.data(), feats, sizeof(float) * (size_t)d * N);
+    crf.setUnaryEnergy(U);
+    crf.addPairwiseEnergy(f, new PottsCompatibility(w));
+    Eigen::MatrixXf R = crf.startInference(), t1, t2;
+    for (int s = 0; s < steps; s++) crf.stepInference(R, t1, t2);
+    memcpy(Q, R.data(), sizeof(float) * (size_t)M * N);
+}
 
 }  // extern "C"

@@ -226,6 +226,10 @@ class Context:
                                                    C.byref(params), _ptr(labels, C.c_uint8), _ptr(Q, C.c_float)))
         return (labels, Q) if want_Q else labels
 
+    def posteriors_keep(self, slot):
+        """Keep the posteriors of the last segment_frame in device slot `slot` for the map worker (rss_posteriors_keep)."""
+        self._check(self._lib.rss_posteriors_keep(self.h, int(slot)))
+
     def keyframe_graph(self, enable=True):
         """Turn the CUDA-graph replay of segment_keyframe's device part on / off for this context (rss_keyframe_graph)."""
         self._check(self._lib.rss_keyframe_graph(self.h, int(bool(enable))))
@@ -329,6 +333,25 @@ class DenseCRF:
         if want_Q and want_labels:
             return Qbuf, lab
         return Qbuf if want_Q else lab
+
+    def set_cloud(self, xyz, rgb):
+        """Upload the local map's points once; they stay resident (rss_crf_set_cloud)."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        self.ctx._check(self._lib.rss_crf_set_cloud(self.h, _ptr(xyz, C.c_float), _ptr(rgb, C.c_float)))
+
+    def project_accumulate(self, W, H, K, R, t, zmin, zmax, slot=-1, want_index=False):
+        """Device projector + unary accumulation from device-resident posteriors (rss_crf_project_accumulate)."""
+        K, R, t = _calib(K, R, t)
+        idx = np.empty((H, W), np.int32) if want_index else None
+        self.ctx._check(self._lib.rss_crf_project_accumulate(self.h, self.ctx.h, int(slot), W, H, _ptr(K, C.c_float),
+                                                             _ptr(R, C.c_float), _ptr(t, C.c_float), C.c_float(zmin),
+                                                             C.c_float(zmax), _ptr(idx, C.c_int32)))
+        return idx
+
+    def add_pairwise_cloud(self, wxyz, wrgb, potts_w):
+        self.ctx._check(self._lib.rss_crf_add_pairwise_cloud(self.h, C.c_float(wxyz), C.c_float(wrgb), C.c_float(potts_w)))
+        self.n_kernels += 1
 
     def unary_reset(self):
         self.ctx._check(self._lib.rss_crf_unary_reset(self.h))

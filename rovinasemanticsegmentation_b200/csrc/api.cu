@@ -312,6 +312,7 @@ static void free_ctx(rss_ctx* ctx) {
                       &ctx->forest.tree_off_dev, &ctx->forest.leaves, &ctx->lab_gamma, &ctx->lab_cbrt, &ctx->tapx,
                       &ctx->tapy, &ctx->feat_xy, &ctx->pose_dev};
     for (DevBuf* b : bufs) b->release();
+    for (DevBuf& b : f.kept) b.release();
     ctx->pin_in.release();
     ctx->pin_out.release();
     ctx->pin_small.release();
@@ -833,6 +834,20 @@ extern "C" rss_status rss_forest_predict(rss_ctx* ctx, const float* feats, int n
     if (leaf_ids) RSS_CU(ctx, cudaMemcpyAsync(leaf_ids, f.leaf_ids.ptr, (size_t)F.T * n * 4, cudaMemcpyDeviceToHost, ctx->s0));
     if (log_post) RSS_CU(ctx, cudaMemcpyAsync(log_post, f.post.ptr, (size_t)n * F.sumC * 4, cudaMemcpyDeviceToHost, ctx->s0));
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_posteriors_keep(rss_ctx* ctx, int slot) {
+    if (!ctx) return RSS_ERR_INVALID;
+    if (slot < 0 || slot > 4096) return ctx->fail(RSS_ERR_INVALID, "bad slot");
+    FrameState& f = ctx->fr;
+    if (!f.have_post) return ctx->fail(RSS_ERR_STATE, "no resident posteriors (call rss_segment_frame first)");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    if ((int)f.kept.size() <= slot) { f.kept.resize(slot + 1); f.kept_npix.resize(slot + 1, 0); }
+    const size_t bytes = (size_t)f.W * f.H * ctx->forest.sumC * 4;
+    RSS_CU(ctx, f.kept[slot].reserve(bytes));
+    RSS_CU(ctx, cudaMemcpyAsync(f.kept[slot].ptr, f.posteriors.ptr, bytes, cudaMemcpyDeviceToDevice, ctx->s0));
+    f.kept_npix[slot] = f.W * f.H;
     return RSS_OK;
 }
 

@@ -137,6 +137,8 @@ struct FrameState {
     DevBuf post;               // float [cap][sumC]
     DevBuf lowres;             // float, per layer [gh][gw][C_l]
     DevBuf posteriors;         // float [layer][H][W][C_l]
+    std::vector<DevBuf> kept;  // posteriors of earlier key frames kept for the map worker (rss_posteriors_keep)
+    std::vector<int> kept_npix; // pixels of each kept slot (0 = empty)
 };
 
 }  // namespace rss

@@ -299,6 +299,38 @@ __global__ void __launch_bounds__(256) unary_accumulate_kernel(const int* __rest
     if (idx < 0 || idx >= N) return;
     atomicAdd(unary + (size_t)idx * Mp + off + c, -post[gid]);
 }
+// The projector of src/segmenter.cpp:581 (fps_mapper's pinhole projector, un-vendored) as a z-buffer kernel: every
+// point of the resident cloud goes to the camera frame, p_cam = R^T (p - t), is projected with K to the nearest pixel
+// and competes for it with key = (float bits of z) << 32 | index through one 64-bit atomicMin (z > 0, so the bit pattern
+// orders like the value): the nearest point wins, equal depths resolve to the lower index - the rule of the oracle's
+// serial loop (orc_project_zbuffer), with the same float operations in the same order.
+struct ProjParams {
+    float R[9], t[3], fx, fy, cx, cy, zmin, zmax;
+};
+__global__ void __launch_bounds__(256) project_zbuffer_kernel(const float* __restrict__ xyz, int N, ProjParams P, int W, int H,
+                                                              unsigned long long* __restrict__ zbuf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float dx = __fsub_rn(xyz[3 * (size_t)i], P.t[0]), dy = __fsub_rn(xyz[3 * (size_t)i + 1], P.t[1]),
+                dz = __fsub_rn(xyz[3 * (size_t)i + 2], P.t[2]);
+    const float x = __fadd_rn(__fadd_rn(__fmul_rn(P.R[0], dx), __fmul_rn(P.R[3], dy)), __fmul_rn(P.R[6], dz));
+    const float y = __fadd_rn(__fadd_rn(__fmul_rn(P.R[1], dx), __fmul_rn(P.R[4], dy)), __fmul_rn(P.R[7], dz));
+    const float z = __fadd_rn(__fadd_rn(__fmul_rn(P.R[2], dx), __fmul_rn(P.R[5], dy)), __fmul_rn(P.R[8], dz));
+    if (!(z >= P.zmin && z <= P.zmax)) return;
+    const float iz = __fdiv_rn(1.0f, z);
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, x), iz), P.cx), v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, y), iz), P.cy);
+    const float fu = floorf(__fadd_rn(u, 0.5f)), fv = floorf(__fadd_rn(v, 0.5f));
+    if (!(fu >= 0.f && fu < (float)W && fv >= 0.f && fv < (float)H)) return;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned)i;
+    atomicMin(zbuf + (size_t)(int)fv * W + (int)fu, key);
+}
+__global__ void __launch_bounds__(256) zbuffer_to_index_kernel(const unsigned long long* __restrict__ zbuf, int npix,
+                                                               int* __restrict__ index_image) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    const unsigned long long k = zbuf[p];
+    index_image[p] = k == ~0ull ? -1 : (int)(unsigned)(k & 0xffffffffull);
+}
 // feature builders: DenseCRF2D::addPairwiseGaussian / Bilateral (densecrf.cpp:61-81), segmenter.cpp:629-637
 __global__ void __launch_bounds__(256) feat_gaussian_kernel(int W, int H, float sx, float sy, float* __restrict__ f) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -526,7 +558,7 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
                               bool sync, bool raster = false) {
     rss_ctx* ctx = crf->ctx;
     if ((int)crf->kernels.size() >= CRF_MAX_KERNELS) return ctx->fail(RSS_ERR_INVALID, "too many pairwise terms (max 4)");
-    if (norm_type < RSS_NORMALIZE_BEFORE || norm_type > RSS_NORMALIZE_SYMMETRIC)
+    if (norm_type < RSS_NO_NORMALIZATION || norm_type > RSS_NORMALIZE_SYMMETRIC)
         return ctx->fail(RSS_ERR_INVALID, "unsupported normalization type");
     Lattice* L;
     if (!crf->pool.empty()) {  // rebuild in place: buffers (and the capacity that worked last time) are reused
@@ -611,6 +643,7 @@ void crf_free(rss_crf* crf) {
     crf->kernels.clear();
     crf->pool.clear();
     crf->unary.release(); crf->Q.release(); crf->scratch.release(); crf->labels.release(); crf->feat_stage.release();
+    crf->cloud_xyz.release(); crf->cloud_rgb.release(); crf->zbuf.release(); crf->index_dev.release();
     for (int k = 0; k < 4; k++) {
         if (crf->side[k]) cudaStreamDestroy(crf->side[k]);
         if (crf->ev_join[k]) cudaEventDestroy(crf->ev_join[k]);
@@ -923,6 +956,81 @@ extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx,
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     crf->unary_set = true;
     return RSS_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// map worker with the cloud, the posteriors and the index images on the device (src/segmenter.cpp:559-637)
+// --------------------------------------------------------------------------------------------------------------------
+extern "C" rss_status rss_crf_set_cloud(rss_crf* crf, const float* xyz, const float* rgb) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (!xyz || !rgb) return ctx->fail(RSS_ERR_INVALID, "null point cloud");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)crf->N * 12;
+    RSS_CU(ctx, crf->cloud_xyz.reserve(bytes));
+    RSS_CU(ctx, crf->cloud_rgb.reserve(bytes));
+    RSS_CU(ctx, cudaMemcpyAsync(crf->cloud_xyz.ptr, xyz, bytes, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_CU(ctx, cudaMemcpyAsync(crf->cloud_rgb.ptr, rgb, bytes, cudaMemcpyHostToDevice, ctx->s0));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));  // the host buffers may be reused by the caller
+    crf->have_cloud = true;
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_project_accumulate(rss_crf* crf, rss_ctx* frame_ctx, int slot, int W, int H, const float K[9],
+                                                 const float R[9], const float t[3], float zmin, float zmax,
+                                                 int32_t* index_image_out) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (!K || !R || !t || W < 1 || H < 1) return ctx->fail(RSS_ERR_INVALID, "null calibration or bad image size");
+    if (!crf->have_cloud) return ctx->fail(RSS_ERR_STATE, "no resident cloud (call rss_crf_set_cloud first)");
+    if (!frame_ctx || frame_ctx != ctx) return ctx->fail(RSS_ERR_INVALID, "frame context must be the CRF's context");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    const int npix = W * H;
+    const FrameState& f = ctx->fr;
+    const float* post_dev = nullptr;
+    if (slot < 0) {
+        if (!f.have_post || f.W * f.H != npix) return ctx->fail(RSS_ERR_STATE, "no resident posteriors matching this image size");
+        post_dev = f.posteriors.as<float>();
+    } else {
+        if (slot >= (int)f.kept.size() || f.kept_npix[slot] != npix)
+            return ctx->fail(RSS_ERR_STATE, "no kept posteriors of this image size in this slot");
+        post_dev = f.kept[slot].as<float>();
+    }
+    if (ctx->forest.sumC != crf->Mtot) return ctx->fail(RSS_ERR_STATE, "the CRF's layers do not match the forest's");
+    RSS_CU(ctx, crf->zbuf.reserve((size_t)npix * 8));
+    RSS_CU(ctx, crf->index_dev.reserve((size_t)npix * 4));
+    ProjParams P;
+    for (int i = 0; i < 9; i++) P.R[i] = R[i];
+    for (int i = 0; i < 3; i++) P.t[i] = t[i];
+    P.fx = K[0]; P.cx = K[2]; P.fy = K[4]; P.cy = K[5]; P.zmin = zmin; P.zmax = zmax;
+    RSS_CU(ctx, cudaMemsetAsync(crf->zbuf.ptr, 0xFF, (size_t)npix * 8, ctx->s0));
+    RSS_LAUNCH(ctx, project_zbuffer_kernel, rss_div_up(crf->N, 256), 256, 0, ctx->s0, crf->cloud_xyz.as<float>(), crf->N, P, W, H,
+               crf->zbuf.as<unsigned long long>());
+    RSS_LAUNCH(ctx, zbuffer_to_index_kernel, rss_div_up(npix, 256), 256, 0, ctx->s0, crf->zbuf.as<unsigned long long>(), npix,
+               crf->index_dev.as<int>());
+    // a point projects to one pixel, so every index occurs at most once per key frame: the adds below never collide
+    for (int l = 0; l < crf->n_layers; l++) {
+        RSS_LAUNCH(ctx, unary_accumulate_kernel, rss_div_up((long long)npix * crf->M[l], 256), 256, 0, ctx->s0,
+                   crf->index_dev.as<int>(), npix, post_dev + (size_t)npix * crf->hoff[l], crf->M[l], crf->Mp, crf->moff[l],
+                   crf->N, crf->unary.as<float>());
+    }
+    if (index_image_out)
+        RSS_CU(ctx, cudaMemcpyAsync(index_image_out, crf->index_dev.ptr, (size_t)npix * 4, cudaMemcpyDeviceToHost, ctx->s0));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    crf->unary_set = true;
+    return RSS_OK;
+}
+
+extern "C" rss_status rss_crf_add_pairwise_cloud(rss_crf* crf, float wxyz, float wrgb, float potts_w) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (!crf->have_cloud) return ctx->fail(RSS_ERR_STATE, "no resident cloud (call rss_crf_set_cloud first)");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    const size_t N = crf->N;
+    RSS_CU(ctx, crf->feat_stage.reserve(N * 6 * 4));
+    RSS_LAUNCH(ctx, feat_xyzrgb_kernel, rss_div_up((long long)N, 256), 256, 0, ctx->s0, (int)N, crf->cloud_xyz.as<float>(),
+               crf->cloud_rgb.as<float>(), wxyz, wrgb, crf->feat_stage.as<float>());
+    return crf_add_kernel_dev(crf, ctx->s0, crf->feat_stage.as<float>(), 6, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
 }
 
 // --------------------------------------------------------------------------------------------------------------------

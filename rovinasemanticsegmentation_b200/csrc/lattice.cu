@@ -654,8 +654,9 @@ __global__ void __launch_bounds__(256) splat_ones_kernel(const int* __restrict__
 rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
     const int N = L.N, d1 = L.d + 1;
     float* norm = L.norm.as<float>();
-    if (L.norm_type == RSS_NO_NORMALIZATION)
-        return ctx->fail(RSS_ERR_INVALID, "NO_NORMALIZATION is not supported on the device path");
+    // NO_NORMALIZATION: DenseKernel::filter applies norm_ neither before nor after the lattice (pairwise.cpp:65,78); the
+    // mean norm it computes (:46-52) only enters the parameter gradients, so nothing is needed here
+    if (L.norm_type == RSS_NO_NORMALIZATION) return RSS_OK;
     float* a = L.splat_target ? L.val_b.as<float>() : L.val_a.as<float>();
     float* b = L.splat_target ? L.val_a.as<float>() : L.val_b.as<float>();
     if (L.have_csr)

@@ -102,6 +102,9 @@ struct rss_crf {
     rss::DevBuf scratch;           // float[N][Mp] staging for host-layout conversions / filter tests
     rss::DevBuf labels;            // uint8[n_layers][N]
     rss::DevBuf feat_stage;        // float[N][d] staging for feature upload
+    rss::DevBuf cloud_xyz, cloud_rgb;  // float[N][3] each: the local map's points, resident (rss_crf_set_cloud)
+    rss::DevBuf zbuf, index_dev;   // u64[H*W] z-buffer keys, int32[H*W] index image of the device projector
+    bool have_cloud = false;
     int grid_w = 0, grid_h = 0;    // the points are the pixels of a grid_w x grid_h image in raster order (0 = unknown)
     std::vector<rss::Lattice*> kernels;
     std::vector<rss::Lattice*> pool;  // released lattices whose device buffers are reused by the next build

@@ -115,3 +115,24 @@ def unary_from_labels(labels, M, seed=0, conf=0.6):
     p *= rng.uniform(0.6, 1.4, size=p.shape)
     p /= p.sum(axis=1, keepdims=True)
     return (-np.log(p)).astype(np.float32)
+
+
+def map_keyframe_pose(k, n):
+    """Pose (R, t: camera -> map) of key frame k of n inside the room of local_map(): the camera walks along the room's
+    long axis at 1.5 m height and looks at alternating walls, slightly downwards."""
+    a = (k + 0.5) / n
+    t = np.array([1.5 + 9.0 * a, 2.5, 1.5], np.float64)
+    yaw = (np.pi / 2 if k % 2 == 0 else -np.pi / 2) + 0.3 * np.sin(3.0 * a)
+    pitch = 0.15
+    # camera axes in the map frame: z forward, x right, y down
+    fwd = np.array([np.cos(yaw) * np.cos(pitch), np.sin(yaw) * np.cos(pitch), -np.sin(pitch)])
+    right = np.array([np.sin(yaw), -np.cos(yaw), 0.0])
+    down = np.cross(fwd, right)
+    R = np.stack([right, down, fwd], axis=1)
+    return R.astype(np.float32), t.astype(np.float32)
+
+
+def intrinsics(W=640, H=480):
+    """K (row-major 3x3) of the pinhole camera that calibration() inverts."""
+    f = 525.0 * W / 640.0
+    return np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1]], np.float32)

@@ -297,6 +297,57 @@ def test_normalization_types(ctx, norm_type):
     crf.close()
 
 
+@pytest.mark.parametrize("name", ["node6d", "two_kernels"])
+@pytest.mark.parametrize("norm_type", [0, 1, 2, 3])
+def test_normalization_types_vs_compiled_reference(ctx, orc, name, norm_type):
+    """All four NormalizationTypes of DenseKernel::filter (pairwise.cpp:40-80) against outputs of the UNMODIFIED reference
+    (tests/golden/crf_golden.npz, generated by tests/golden/make_crf_golden.py from the compiled densecrf sources) and
+    against the oracle.  Unordered point clouds: the generic (vertex-major CSR) mean-field path."""
+    g = np.load(os.path.join(os.path.dirname(FOREST), "crf_golden.npz"))
+    U = g[name + "_unary"]
+    kernels, k = [], 0
+    while "%s_feat%d" % (name, k) in g:
+        kernels.append((g["%s_feat%d" % (name, k)], float(g["%s_w%d" % (name, k)])))
+        k += 1
+    iters = int(g[name + "_iters"])
+    crf = ctx.crf(U.shape[0], U.shape[1])
+    crf.set_unary(U)
+    for f, w in kernels:
+        crf.add_pairwise(f, w, norm_type)
+    Q1, l1 = crf.inference(iters, want_labels=True)
+    ref = g["%s_Q_norm%d" % (name, norm_type)]
+    assert np.abs(Q1 - ref).max() <= 1e-4
+    assert (l1 == g["%s_map_norm%d" % (name, norm_type)]).mean() >= 0.999
+    assert np.abs(Q1 - orc.crf_inference(U, kernels, iters, norm_type)).max() <= 1e-4
+    crf.close()
+
+
+@pytest.mark.parametrize("norm_type", [0, 1, 2, 3])
+def test_normalization_types_fused_path(ctx, orc, norm_type):
+    """The same on an image grid (raster order: the fused tile path, where the normalisation is folded into the per-tile
+    splat / slice weights): DenseCRF2D-style Gaussian + bilateral kernels with an explicit NormalizationType."""
+    from rovinasemanticsegmentation_b200 import synth
+    W, H, M = 96, 64, 5
+    rgb, _ = synth.frame(29, W, H)
+    U = synth.unary_from_labels((np.arange(W * H) // 500) % M, M, 6)
+    f2 = orc.features_gaussian2d(W, H, 3, 3)
+    f5 = orc.features_bilateral2d(W, H, 60, 60, 10, 10, 10, rgb)
+    if norm_type == 3:  # two kernels on the 2-D tile grid (DenseCRF2D's builders use SYMMETRIC)
+        crf = ctx.crf(W * H, M)
+        crf.set_unary(U)
+        crf.add_pairwise_gaussian(W, H, 3, 3, 3.0)
+        crf.add_pairwise(f5, 5.0, norm_type)
+        assert np.abs(orc.crf_inference(U, [(f2, 3.0), (f5, 5.0)], 5, 3) - crf.inference(5)).max() <= 1e-4
+        crf.close()
+    # one kernel alone, every type; raster order is detected from the run statistic -> fused path with 1-D tiles
+    crf = ctx.crf(W * H, M)
+    crf.set_unary(U)
+    crf.add_pairwise(f5, 5.0, norm_type)
+    Q1 = crf.inference(5)
+    assert np.abs(orc.crf_inference(U, [(f5, 5.0)], 5, norm_type) - Q1).max() <= 1e-4
+    crf.close()
+
+
 def test_corrupt_forest_returns_model_error():
     """ADVICE r1 (api.cu load_forest_bytes): truncated files, absurd node counts and class-less leaves come back as
     RSS_ERR_MODEL (4) - no bad_alloc through the C boundary, no division by zero."""

@@ -80,3 +80,48 @@ def test_local_map_15m_points_properties(ctx, wxyz, wrgb, min_vertices):
     t = ctx.timings()
     print("15M points, %d vertices: %.1f ms per mean-field iteration" % (V, t["meanfield_ms"] / 10))
     crf.close()
+
+
+def _map_problem(N, M, seed):
+    from rovinasemanticsegmentation_b200 import synth
+    xyz, col = synth.local_map(seed=seed, n_points=N)
+    lab = (np.floor(xyz[:, 0]).astype(int) + np.floor(xyz[:, 1] * 2).astype(int)) % M
+    return xyz, col, synth.unary_from_labels(lab, M, seed=3)
+
+
+@pytest.mark.timeout(900)
+def test_local_map_15m_points_vs_oracle(ctx, orc):
+    """BASELINE configs[3] at full size against the ORACLE (not only filter properties): 15 M points, the node's kernel
+    widths (a few thousand vertices: every point shares its vertices with ~10^4 others), 9 labels, 3 iterations.
+    Reference: permutohedral.cpp:140-321,529-589, densecrf.cpp:110-131."""
+    N, M = 15_000_000, 9
+    xyz, col, U = _map_problem(N, M, 47)
+    f6 = orc.features_xyzrgb(xyz, col, 0.5, 4.0)
+    Q0 = orc.crf_inference(U, [(f6, 10.0)], 3)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise_xyzrgb(xyz, col, 0.5, 4.0, 10.0)
+    Q1, l1 = crf.inference(3, unknown=M - 1, want_labels=True)
+    assert np.abs(Q0 - Q1).max() <= 1e-4
+    assert (orc.gated_argmax(Q0, M - 1) == l1).mean() >= 0.999
+    crf.close()
+
+
+@pytest.mark.timeout(900)
+def test_local_map_fine_scales_vs_oracle(ctx, orc):
+    """The many-vertices regime (xyz * 20, rgb * 40: about one vertex per point-corner, V >= 5 * 10^5) against the oracle:
+    2 M points, vertex count equal to the reference's, marginals and labels within the bar."""
+    N, M = 2_000_000, 9
+    xyz, col, U = _map_problem(N, M, 53)
+    f6 = orc.features_xyzrgb(xyz, col, 20.0, 40.0)
+    lat = orc.Lattice(f6)
+    assert lat.V >= 500_000
+    Q0 = orc.crf_inference(U, [(f6, 10.0)], 3)
+    crf = ctx.crf(N, M)
+    crf.set_unary(U)
+    crf.add_pairwise_xyzrgb(xyz, col, 20.0, 40.0, 10.0)
+    assert crf.lattice_size(0) == lat.V  # N % 4 == 0: no padding point in the reference either
+    Q1, l1 = crf.inference(3, unknown=M - 1, want_labels=True)
+    assert np.abs(Q0 - Q1).max() <= 1e-4
+    assert (orc.gated_argmax(Q0, M - 1) == l1).mean() >= 0.999
+    crf.close()
