@@ -243,6 +243,228 @@ def algo_bytes(name, env):
     return table.get(re.sub(r"<[0-9, ]+>", "<D>", name))
 
 
+# ------------------------------------------------------------------------------------------------ local-map sweep
+# BASELINE configs[4]: independent local maps sharded over the GPUs (src/segmenter.cpp:518-719, the map worker's unit of
+# work).  One map = MAP_KF key frames (640x480, the frame worker's forest pass each) fused into one cloud of MAP_POINTS points:
+# projector -> unary accumulation -> one 6-D Potts kernel (xyz * 0.5, rgb * 4, w = 10) -> 10 mean-field iterations for
+# both label layers -> gated argmax.  Host buffers in (cloud 48 MB, frames) and label maps out, all inside the timed region.
+MAP_POINTS, MAP_KF, MAP_DISTINCT = 2_000_000, 4, 2
+MAP_METRIC = "local maps/sec (2M points, 4 keyframes 640x480, RF + 6-D DenseCRF, 10 iters, 2 layers)"
+MAP_Z = (0.3, 8.0)
+
+
+def map_inputs(seed):
+    from rovinasemanticsegmentation_b200 import synth
+    xyz, col = synth.local_map(seed=seed, n_points=MAP_POINTS)
+    frames = [synth.frame(seed * 16 + k) for k in range(MAP_KF)]
+    poses = [synth.map_keyframe_pose(k, MAP_KF) for k in range(MAP_KF)]
+    return xyz, col, frames, poses
+
+
+def cpu_local_map(seed, want_labels=False):
+    """One local map through the oracle, single thread (the reference's map worker is one thread)."""
+    import oracle
+    from rovinasemanticsegmentation_b200 import synth
+    if _CPU_FOREST is None:
+        _cpu_init()
+    xyz, col, frames, poses = map_inputs(seed)
+    Kinv, Rc, tc = synth.calibration()
+    K = synth.intrinsics()
+    if _CPU_BARRIER is not None:
+        _CPU_BARRIER.wait(timeout=600)
+    t0 = time.perf_counter()
+    un = [np.zeros((MAP_POINTS, m), np.float32) for m in (8, 9)]
+    for (rgb, depth), (R, t) in zip(frames, poses):
+        post = oracle.segment_frame(oracle.default_config(), _CPU_FOREST, 2, rgb, depth, Kinv, Rc, tc, 0.5, 15.0, 0.0)
+        idx = oracle.project_zbuffer(xyz, K, R, t, W, H, *MAP_Z)
+        off = 0
+        for l, m in enumerate((8, 9)):
+            oracle.unary_accumulate(idx, post[off:off + W * H * m].reshape(W * H, m), un[l])
+            off += W * H * m
+    f6 = oracle.features_xyzrgb(xyz, col, 0.5, 4.0)
+    labels = np.empty((2, MAP_POINTS), np.uint8)
+    for l, unk in enumerate((7, 8)):
+        labels[l] = oracle.gated_argmax(oracle.crf_inference(-un[l], [(f6, 10.0)], 10), unk)
+    dt = time.perf_counter() - t0
+    return (dt, labels) if want_labels else (dt, None)
+
+
+def _cpu_map_worker(arg):
+    seed, want = arg
+    return cpu_local_map(seed, want)
+
+
+def cpu_map_throughput(procs, rounds, first_seed=None):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(ctx.Barrier(procs),)) as pool:
+        total, labels = 0.0, None
+        for r in range(rounds):
+            seeds = [(5000 + r * procs + i, False) for i in range(procs)]
+            if r == 0 and first_seed is not None:
+                seeds[0] = (first_seed, True)
+            res = pool.map(_cpu_map_worker, seeds, chunksize=1)
+            total += max(dt for dt, _ in res)
+            if r == 0 and first_seed is not None:
+                labels = res[0][1]
+    return procs * rounds / total, total, labels
+
+
+def run_local_maps_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    oracle.build(ref=False)
+    procs = max(1, min(os.cpu_count() or 1, 16))  # ~1.5 GB per pipeline
+    rounds = max(1, min(args.steps, 2))
+    val, dt, _ = cpu_map_throughput(procs, rounds)
+    print(json.dumps({
+        "impl": "reference", "metric": MAP_METRIC, "value": val, "unit": "maps/s", "n_gpus": args.gpus, "steps": rounds,
+        "warmup": 0, "ms_per_step": 1000.0 * dt / rounds, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "local_maps", "step": "%d maps side by side, one single-thread oracle pipeline per core" % procs},
+        "cpu_baseline": {"value": val, "unit": "maps/s", "cores": procs, "kind": "port",
+                         "sample": "%d rounds of %d maps (oracle/oracle.c)" % (rounds, procs)},
+        "e2e": {"value": val, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_local_maps(args, rank, world, local_rank):
+    import threading as th
+
+    import torch
+    import rovinasemanticsegmentation_b200 as rss
+    from rovinasemanticsegmentation_b200 import synth
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if dist is not None:
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    NC = max(1, min(2, (os.cpu_count() or 1) // max(world, 1)))  # maps in flight per GPU
+    ctxs = [rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank) for _ in range(NC)]
+    crfs = [c.crf(MAP_POINTS, [8, 9]) for c in ctxs]
+    Kinv, Rc, tc = synth.calibration()
+    K = synth.intrinsics()
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t.numpy()
+
+    maps = []
+    seeds = [7000 + rank * MAP_DISTINCT + i for i in range(MAP_DISTINCT)]
+    for seed in seeds:
+        xyz, col, frames, poses = map_inputs(seed)
+        pf = []
+        for rgb, depth in frames:
+            pd = torch.empty(depth.shape, dtype=torch.int16, pin_memory=True)
+            pd.numpy().view(np.uint16)[...] = depth
+            pf.append((pinned(rgb), pd.numpy().view(np.uint16)))
+        maps.append((pinned(xyz), pinned(col), pf, poses))
+    outs = [None] * NC
+
+    def one_map(i, m):
+        c, crf = ctxs[i], crfs[i]
+        xyz, col, frames, poses = maps[m]
+        for k, (rgb, depth) in enumerate(frames):  # frame worker: forest pass, posteriors stay on the device
+            c.segment_frame(rgb, depth, Kinv, Rc, tc, 0.0, want_host=False)
+            c.posteriors_keep(k)
+        crf.unary_reset()
+        crf.clear_pairwise()
+        crf.set_cloud(xyz, col)
+        for k, (R, t) in enumerate(poses):       # map worker: projector + accumulation on the device
+            crf.project_accumulate(W, H, K, R, t, MAP_Z[0], MAP_Z[1], slot=k)
+        crf.add_pairwise_cloud(0.5, 4.0, 10.0)
+        outs[i] = crf.inference(10, unknown=[7, 8], want_Q=False, want_labels=True)
+
+    def run(steps):
+        per = [steps // NC + (1 if i < steps % NC else 0) for i in range(NC)]
+        errs = []
+
+        def worker(i):
+            try:
+                for k in range(per[i]):
+                    one_map(i, (i + k) % MAP_DISTINCT)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [th.Thread(target=worker, args=(i,)) for i in range(NC)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        torch.cuda.synchronize()
+        e1.record()
+        e1.synchronize()
+        if errs:
+            raise errs[0]
+        return e0.elapsed_time(e1)
+
+    l0 = sum(c.kernel_launches for c in ctxs)
+    run(max(args.warmup, NC))
+    launches_warm = sum(c.kernel_launches for c in ctxs) - l0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = sum(c.kernel_launches for c in ctxs)
+    ms = run(args.steps)
+    launches = sum(c.kernel_launches for c in ctxs) - l0
+    one_map(0, 0)
+    labels0 = outs[0].copy()
+    barrier()
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    ms_max, = max_over_ranks([ms], dist, dev)
+    if rank == 0:
+        value = job_throughput(args.steps, world, ms_max)
+        bytes_in = MAP_POINTS * 24 + MAP_KF * (W * H * 5)
+        line = {"metric": MAP_METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, NC), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "local_maps: %d points, %d keyframes 640x480 per map, device projector, 6-D kernel "
+                                       "(xyz*0.5, rgb*4, w=10), 10 iterations, 2 layers; %d distinct maps per rank cycled; "
+                                       "%d maps in flight per GPU" % (MAP_POINTS, MAP_KF, MAP_DISTINCT, NC),
+                           "l2": "inputs (48 MB cloud per map) exceed nothing by themselves; the working set of a map's mean "
+                                 "field (2 M x 20 floats x 3 + lattice) is ~0.6 GB >> L2"},
+                "clocks": sampler.summary(),
+                "e2e": {"value": value, "unit": "maps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 2 * MAP_POINTS,
+                        "ms_per_step": ms_max / args.steps,
+                        "note": "this workload is end to end by construction: every map's cloud and frames come from pinned host "
+                                "buffers and its label maps go back, inside the timed region"},
+                "gpu_launches": int(launches)}
+        if world == 1 and not args.no_cpu:
+            import oracle
+            oracle.build(ref=False)
+            procs = max(1, min(os.cpu_count() or 1, 16))
+            cv, cdt, cpu_labels = cpu_map_throughput(procs, 1, first_seed=seeds[0])
+            line["cpu_baseline"] = {"value": cv, "unit": "maps/s", "cores": procs, "kind": "port",
+                                    "sample": "%d maps, one single-thread oracle pipeline per core (%.1f s compute)" % (procs, cdt)}
+            agree = [float((labels0[l] == cpu_labels[l]).mean()) for l in range(2)]
+            line["parity_check"] = {"label_agreement": min(agree), "per_layer": agree, "bar": 0.999, "ok": bool(min(agree) >= 0.999),
+                                    "what": "labels of local map 0 (device projector, resident posteriors) vs the oracle's map worker"}
+        print(json.dumps(line), flush=True)
+    for crf in crfs:
+        crf.close()
+    for c in ctxs:
+        c.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def local_map_bench(ctx, synth, NM, wxyz, wrgb, peak, regime):
     """BASELINE configs[3] side measurement: one local map of NM points, both label layers through one 6-D lattice
     (src/segmenter.cpp:629-643), 10 mean-field iterations; device time from the library's events."""
@@ -547,6 +769,8 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="keyframes", choices=["keyframes", "local_maps"],
+                    help="keyframes: the headline metric (BASELINE configs[1]+[2]); local_maps: the configs[4] sweep")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="skip the keyframes-in-flight sweep and the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-15m", dest="no_15m", action="store_true", help="skip the 15 M-point local-map side measurement")
@@ -559,14 +783,21 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "local_maps":
+            run_local_maps_reference(args, rank, world)
+        else:
+            run_reference(args, rank, world)
         return
     if world == 1 and args.gpus > 1:
         # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
-               "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu"] if args.no_cpu else [])
+               "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload] + \
+              (["--no-cpu"] if args.no_cpu else [])
         sys.exit(subprocess.call(cmd))
+    if args.workload == "local_maps":
+        run_local_maps(args, rank, world, local_rank)
+        return
     run_gpu(args, rank, world, local_rank)
 
 

@@ -163,6 +163,9 @@ rss_status rss_crf_destroy(rss_crf* crf);
  * rss_crf_add_pairwise_xyzrgb: the 6-D feature matrix of :629-637 (points xyz * wxyz, rgb * wrgb).
  * ------------------------------------------------------------------------------------------------- */
 rss_status rss_crf_unary_reset(rss_crf* crf);
+/* Drops every pairwise term (their device buffers are pooled and reused by the next ones): with rss_crf_unary_reset this
+ * lets one CRF object serve a sequence of local maps of the same size without reallocating. */
+rss_status rss_crf_clear_pairwise(rss_crf* crf);
 rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx, const int32_t* index_image, int npix,
                                     const float* posteriors);
 rss_status rss_crf_add_pairwise_xyzrgb(rss_crf* crf, const float* xyz, const float* rgb, float wxyz, float wrgb,

@@ -353,6 +353,10 @@ class DenseCRF:
         self.ctx._check(self._lib.rss_crf_add_pairwise_cloud(self.h, C.c_float(wxyz), C.c_float(wrgb), C.c_float(potts_w)))
         self.n_kernels += 1
 
+    def clear_pairwise(self):
+        self.ctx._check(self._lib.rss_crf_clear_pairwise(self.h))
+        self.n_kernels = 0
+
     def unary_reset(self):
         self.ctx._check(self._lib.rss_crf_unary_reset(self.h))
 

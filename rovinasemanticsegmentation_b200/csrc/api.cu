@@ -303,6 +303,7 @@ static rss_status upload_tables(rss_ctx* ctx) {
 static void free_ctx(rss_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->counted_live) live_contexts(ctx->device)--;
     keyframe_graph_release(ctx);
     crf_release_cached(ctx);
     FrameState& f = ctx->fr;
@@ -377,6 +378,8 @@ extern "C" rss_status rss_create(const char* config_json_path, const char* fores
         st = load_forest(ctx, forest_dat_path);
         if (st != RSS_OK) return bail(st);
     }
+    live_contexts(cuda_device)++;
+    ctx->counted_live = true;
     *out = ctx;
     return RSS_OK;
 }

@@ -929,6 +929,15 @@ extern "C" rss_status rss_crf_unary_reset(rss_crf* crf) {
     return RSS_OK;
 }
 
+extern "C" rss_status rss_crf_clear_pairwise(rss_crf* crf) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
+    return RSS_OK;
+}
+
 extern "C" rss_status rss_crf_unary_accumulate(rss_crf* crf, rss_ctx* frame_ctx, const int32_t* index_image, int npix,
                                                const float* posteriors) {
     if (!crf) return RSS_ERR_INVALID;

@@ -787,7 +787,9 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
 
 int blur_multi_grid(const rss_ctx* c) { return c->sm_count; }  // one CTA per SM
 cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
-    const int grid = blur_multi_grid(c), block = RSS_BLUR_MAXT;
+    // alone on the GPU: 512 threads per SM (the phases are L2-latency/throughput-bound); sharing it with other keyframes in
+    // flight: 256, which leaves room for their kernels while this one waits at its barriers
+    const int grid = blur_multi_grid(c), block = live_contexts(c->device).load() > 1 ? RSS_BLUR_MAXT / 2 : RSS_BLUR_MAXT;
     void* args[] = {&a, &G, &barrier, &barrier_base};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }

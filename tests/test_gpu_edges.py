@@ -343,8 +343,13 @@ def test_normalization_types_fused_path(ctx, orc, norm_type):
     crf = ctx.crf(W * H, M)
     crf.set_unary(U)
     crf.add_pairwise(f5, 5.0, norm_type)
-    Q1 = crf.inference(5)
-    assert np.abs(orc.crf_inference(U, [(f5, 5.0)], 5, norm_type) - Q1).max() <= 1e-4
+    Q1, l1 = crf.inference(5, want_labels=True)
+    Q0 = orc.crf_inference(U, [(f5, 5.0)], 5, norm_type)
+    # NO_NORMALIZATION leaves the filter response unscaled: the messages are w * (sum of ~10^3 kernel weights) ~ 10^4, one
+    # float ulp of that is ~1e-3 in the logit, so the marginals of the few undecided pixels move by a few 1e-4 with the
+    # summation order alone (pairwise.h calls this mode "a substantial approximation error"): 1e-3 there, 1e-4 elsewhere
+    assert np.abs(Q0 - Q1).max() <= (1e-3 if norm_type == 0 else 1e-4)
+    assert (Q0.argmax(1) == l1).mean() >= 0.999
     crf.close()
 
 
