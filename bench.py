@@ -525,7 +525,9 @@ def run_gpu(args, rank, world, local_rank):
     # keyframes in flight on this GPU: one context + one host thread each (the threads spin in cudaStreamSynchronize, so
     # never more of them than host cores over all ranks)
     NC = max(1, min(args.inflight, (os.cpu_count() or 1) // max(world, 1)))
-    ctxs = [rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank) for _ in range(NC)]
+    # ONE context first: the latency and one-keyframe-in-flight numbers are those of a single synchronous caller (the library
+    # sizes its cooperative kernels by the number of live contexts on the device); the other contexts are created afterwards
+    ctxs = [rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank)]
     ctx = ctxs[0]
     lib = ctx._lib
     Kinv, R, t = synth.calibration()
@@ -558,11 +560,14 @@ def run_gpu(args, rank, world, local_rank):
             flushes[i].zero_()
         streams[i].synchronize()
 
-    # ---- warm-up (untimed): every context, host buffers (allocations, lattice capacities)
-    for k in range(args.warmup):
-        for i, c in enumerate(ctxs):
-            call(c, frames[(i + k) % N_FRAMES][0], frames[(i + k) % N_FRAMES][1], outs[i])
-    barrier()
+    # ---- warm-up (untimed): every context, host buffers (allocations, lattice capacities, graph capture)
+    def warm():
+        for k in range(max(args.warmup, 4)):
+            for i, c in enumerate(ctxs):
+                call(c, frames[(i + k) % N_FRAMES][0], frames[(i + k) % N_FRAMES][1], outs[i])
+        barrier()
+
+    warm()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -636,19 +641,23 @@ def run_gpu(args, rank, world, local_rank):
             raise errs[0]
         return e0.elapsed_time(e1), sum(c.kernel_launches for c in ctxs) - l0
 
+    R = max(1, args.repeats)
+    # one keyframe in flight per GPU (no overlap between keyframes: what a single synchronous caller gets)
+    throughput_pass(False, steps=2, nc=1)
+    res1_all = [throughput_pass(False, nc=1)[0] for _ in range(R)]
+    e2e1_all = [throughput_pass(True, nc=1)[0] for _ in range(R)]
+    # ---- now the other contexts: NC keyframes in flight
+    ctxs.extend(rss.Context(rss.DEFAULT_CONFIG, FOREST, local_rank) for _ in range(NC - 1))
+    warm()
     throughput_pass(False, steps=2 * NC)  # untimed: worker threads, side streams and flush buffers warm
     # The timed region of K keyframes is short (tens of ms), so it is REPEATED `repeats` times back to back; every repeat
     # times exactly K steps, the slowest rank decides per repeat, and the MEDIAN repeat is reported (min / max beside it).
-    R = max(1, args.repeats)
     res_all, e2e_all, launches = [], [], 0
     for _ in range(R):
         ms, launches = throughput_pass(False)
         res_all.append(ms)
     for _ in range(R):
         e2e_all.append(throughput_pass(True)[0])
-    # the same with ONE keyframe in flight (no overlap between keyframes: what a single synchronous caller gets)
-    res1_all = [throughput_pass(False, nc=1)[0] for _ in range(R)] if NC > 1 else list(res_all)
-    e2e1_all = [throughput_pass(True, nc=1)[0] for _ in range(R)] if NC > 1 else list(e2e_all)
     # parity of the timed path: the label maps the e2e entry point writes for this rank's first frame (checked on rank 0
     # against the CPU arm's label maps of the same keyframe, below)
     call(ctx, frames[0][0], frames[0][1], outs[0])

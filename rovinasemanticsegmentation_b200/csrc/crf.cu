@@ -1064,6 +1064,7 @@ struct KeyframeGraph {
     int W = 0, H = 0;
     rss_keyframe_params prm{};
     uint64_t launches = 0;       // kernel launches inside the graph
+    bool shared_gpu = false;     // captured while other contexts were alive on the device (smaller blur CTAs)
     // stability detection: the previous eager call's signature and the allocation counter after it
     int prev_W = 0, prev_H = 0;
     rss_keyframe_params prev_prm{};
@@ -1186,7 +1187,9 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     for (int attempt = 0;; attempt++) {
         const uint64_t gen = device_alloc_events().load();
         bool ran = false;
-        if (want_graph && attempt == 0 && G.exec && G.W == W && G.H == H && same_params(G.prm, *prm) && G.alloc_gen == gen) {
+        const bool shared_gpu = live_contexts(ctx->device).load() > 1;
+        if (want_graph && attempt == 0 && G.exec && G.W == W && G.H == H && same_params(G.prm, *prm) && G.alloc_gen == gen &&
+            G.shared_gpu == shared_gpu) {
             // steady state: replay.  The frame-state flags the eager path maintains:
             ctx->fr.have_cloud = ctx->cfg.use_height || ctx->cfg.use_normal;
             ctx->fr.have_lab = ctx->cfg.use_color;
@@ -1215,7 +1218,7 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
                 e = cudaErrorUnknown;
             if (graph) cudaGraphDestroy(graph);
             if (e == cudaSuccess) {
-                G.W = W; G.H = H; G.prm = *prm; G.alloc_gen = gen;
+                G.W = W; G.H = H; G.prm = *prm; G.alloc_gen = gen; G.shared_gpu = shared_gpu;
                 G.launches = ctx->launches - l0;
                 RSS_CU(ctx, cudaGraphLaunch(G.exec, ctx->s0));
                 ran = true;
