@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
                                                             uint32_t* __restrict__ first_ref,
                                                             uint32_t* __restrict__ counts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Next) return;
-    if (*reinterpret_cast<volatile uint32_t*>(counts + 1)) return;  // overflow already detected: the build is void anyway
+    // no early exit: the lanes of a warp agree on duplicate vertices below (full-mask match / shuffle)
+    const bool live = i < Next && !*reinterpret_cast<volatile uint32_t*>(counts + 1);  // overflow: the build is void anyway
     // i == N (only when N % 4 != 0): the reference's SSE loop pads its last block of four points with ZERO features and
     // still inserts their vertices (permutohedral.cpp:192-198,268-275).  Those vertices never receive a splat, but they
     // exist for the blur and pass values on between their neighbours - so they must exist here too.
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
     float sm = 0.f;
 #pragma unroll
     for (int j = D; j > 0; j--) {
-        const float cf = __fmul_rn(padding ? 0.0f : feat[(size_t)i * D + (j - 1)], sf.s[j - 1]);
+        const float cf = __fmul_rn((padding || !live) ? 0.0f : feat[(size_t)i * D + (j - 1)], sf.s[j - 1]);
         elevated[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
         sm = __fadd_rn(sm, cf);
     }
@@ -177,11 +177,25 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
             const int canon = irank[k] <= D - rem ? rem : rem - (D + 1);
             key[k] = irem[k] + canon;
         }
-        const int slot = hash_insert(table, mask, key_pack<D>(key));
-        if (slot < 0) counts[1] = 1u;
-        else atomicMin(first_ref + slot, (uint32_t)i * (D + 1) + rem);  // first (point, corner) pair that touches the vertex
-        offsets[(size_t)i * (D + 1) + rem] = slot;
-        bary_out[(size_t)i * (D + 1) + rem] = bary[rem];
+        // Neighbouring pixels land on the same vertices: the lanes of the warp that hold the SAME key elect the lowest one,
+        // which alone probes / claims the hash slot and records the first (point, corner) pair (it has the smallest point
+        // index of the group); the others get the slot by shuffle.  Dead lanes carry a key nobody else can have.
+        Key128 kk = key_pack<D>(key);
+        if (!live) { kk.lo = 0xFFFF000000000000ull | (unsigned long long)(threadIdx.x & 31); kk.hi = ~0ull; }
+        unsigned grp = __match_any_sync(0xffffffffu, kk.lo);
+        if (D > 4) grp &= __match_any_sync(0xffffffffu, kk.hi);
+        const int leader = __ffs(grp) - 1;
+        int slot = -1;
+        if (live && (int)(threadIdx.x & 31) == leader) {
+            slot = hash_insert(table, mask, kk);
+            if (slot < 0) counts[1] = 1u;
+            else atomicMin(first_ref + slot, (uint32_t)i * (D + 1) + rem);  // first (point, corner) pair that touches the vertex
+        }
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (live) {
+            offsets[(size_t)i * (D + 1) + rem] = slot;
+            bary_out[(size_t)i * (D + 1) + rem] = bary[rem];
+        }
     }
 }
 
