@@ -203,27 +203,67 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
 // table produces (permutohedral.cpp:118-120).  Besides making offsets comparable with the reference one to one, it
 // is what makes the filter cache friendly: consecutive points (neighbouring pixels) share vertices, so vertices that
 // are close in the lattice get close ids, and the value rows a warp gathers sit in a few cache lines.
-//   flag[k] = 1 iff pair k is the first to touch its vertex;  id = exclusive_scan(flag)[k] for those pairs.
-__global__ void __launch_bounds__(256) first_flags_kernel(const int* __restrict__ offsets, size_t n,
-                                                          const uint32_t* __restrict__ first_ref,
-                                                          const uint32_t* __restrict__ counts, uint32_t* __restrict__ flags) {
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    flags[k] = (!counts[1] && first_ref[offsets[k]] == (uint32_t)k) ? 1u : 0u;
+// Computed WITHOUT a pass over the (point, corner) pairs: every occupied hash slot marks the index of its first
+// pair (first_ref, an atomicMin of the embedding kernel) in a bitmap over pair indices (one thread per SLOT: 10^5, not 10^6 pairs), one CTA turns the bitmap's word
+// popcounts into prefix sums, and every slot reads its rank = vertices whose first pair comes earlier.
+__global__ void __launch_bounds__(256) first_bitmap_kernel(const uint32_t* __restrict__ first_ref, uint32_t hcap,
+                                                           const uint32_t* __restrict__ counts, uint32_t* __restrict__ bitmap) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= hcap || counts[1]) return;
+    const uint32_t r = first_ref[s];
+    if (r != 0xFFFFFFFFu) atomicOr(bitmap + (r >> 5), 1u << (r & 31));
 }
-__global__ void __launch_bounds__(256) assign_ids_kernel(const int* __restrict__ offsets, size_t n,
-                                                         const uint32_t* __restrict__ first_ref,
-                                                         const uint32_t* __restrict__ rank, const Key128* __restrict__ table,
-                                                         uint32_t vcap, uint32_t* __restrict__ slot_id,
-                                                         Key128* __restrict__ vkeys, uint32_t* __restrict__ counts) {
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n || counts[1]) return;
-    const int slot = offsets[k];
-    if (first_ref[slot] != (uint32_t)k) return;
-    const uint32_t id = rank[k];
-    slot_id[slot] = id;
-    if (id < vcap) vkeys[id] = load_key(table + slot);
-    else counts[1] = 1u;  // load factor above 1/2: the host retries with a bigger table
+__global__ void __launch_bounds__(1024) bitmap_prefix_kernel(const uint32_t* __restrict__ bitmap, uint32_t nwords,
+                                                             uint32_t* __restrict__ prefix, uint32_t* __restrict__ counts,
+                                                             uint32_t vcap) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t per = (nwords + blockDim.x - 1) / blockDim.x;
+    const uint32_t w0 = threadIdx.x * per, w1 = min(nwords, w0 + per);
+    uint32_t s = 0;
+    for (uint32_t w = w0; w < w1; w++) s += __popc(bitmap[w]);
+    // exclusive scan of the per-thread sums over the CTA
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        wsum[lane] = iv - v;
+        if (lane == 31) {  // total = number of vertices
+            counts[0] = iv;
+            if (iv > vcap) counts[1] = 1u;  // load factor above 1/2: the host retries with a bigger table
+        }
+    }
+    __syncthreads();
+    uint32_t run = wsum[wid] + inc - s;
+    for (uint32_t w = w0; w < w1; w++) {
+        prefix[w] = run;
+        run += __popc(bitmap[w]);
+    }
+}
+__global__ void __launch_bounds__(256) assign_ids_bitmap_kernel(const uint32_t* __restrict__ first_ref, uint32_t hcap,
+                                                                const uint32_t* __restrict__ bitmap,
+                                                                const uint32_t* __restrict__ prefix,
+                                                                const Key128* __restrict__ table, uint32_t vcap,
+                                                                uint32_t* __restrict__ slot_id, Key128* __restrict__ vkeys,
+                                                                const uint32_t* __restrict__ counts) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= hcap || counts[1]) return;
+    const uint32_t r = first_ref[s];
+    if (r == 0xFFFFFFFFu) return;
+    const uint32_t id = prefix[r >> 5] + __popc(bitmap[r >> 5] & ((1u << (r & 31)) - 1u));
+    slot_id[s] = id;
+    if (id < vcap) vkeys[id] = load_key(table + s);
 }
 __global__ void __launch_bounds__(256) remap_offsets_kernel(int* __restrict__ offsets, size_t n,
                                                             const uint32_t* __restrict__ slot_id,
@@ -552,14 +592,17 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
         case 6: launch_embed<6>(ctx, st, feat, N, L); break;
         default: launch_embed<7>(ctx, st, feat, N, L); break;
     }
-    // vertex numbering by first appearance: flags over the (point, corner) pairs -> exclusive scan; counts[0] = V
-    RSS_LAUNCH(ctx, first_flags_kernel, rss_div_up((long long)nnz_ext, 256), 256, 0, st, L.offsets.as<int>(), nnz_ext,
-               L.first_ref.as<uint32_t>(), counts, L.rank.as<uint32_t>());
-    exclusive_scan_u32(L.rank.as<uint32_t>(), L.rank.as<uint32_t>(), nnz_ext, L.scan_tmp.as<uint32_t>(), counts, st,
-                       &ctx->launches);
-    RSS_LAUNCH(ctx, assign_ids_kernel, rss_div_up((long long)nnz_ext, 256), 256, 0, st, L.offsets.as<int>(), nnz_ext,
-               L.first_ref.as<uint32_t>(), L.rank.as<uint32_t>(), L.table.as<Key128>(), L.vcap, L.slot_id.as<uint32_t>(),
-               L.vkeys.as<Key128>(), counts);
+    // vertex numbering by first appearance (bitmap of first pairs -> popcount prefix -> rank per slot); counts[0] = V
+    {
+        const uint32_t nwords = (uint32_t)((nnz_ext + 31) / 32);
+        uint32_t* bitmap = L.rank.as<uint32_t>();
+        uint32_t* prefix = bitmap + nwords;
+        RSS_CU(ctx, cudaMemsetAsync(bitmap, 0, (size_t)nwords * 4, st));
+        RSS_LAUNCH(ctx, first_bitmap_kernel, rss_div_up(hcap, 256), 256, 0, st, L.first_ref.as<uint32_t>(), hcap, counts, bitmap);
+        RSS_LAUNCH(ctx, bitmap_prefix_kernel, 1, 1024, 0, st, bitmap, nwords, prefix, counts, L.vcap);
+        RSS_LAUNCH(ctx, assign_ids_bitmap_kernel, rss_div_up(hcap, 256), 256, 0, st, L.first_ref.as<uint32_t>(), hcap, bitmap, prefix,
+                   L.table.as<Key128>(), L.vcap, L.slot_id.as<uint32_t>(), L.vkeys.as<Key128>(), counts);
+    }
     RSS_LAUNCH(ctx, remap_offsets_kernel, rss_div_up((long long)nnz, 256), 256, 0, st, L.offsets.as<int>(), nnz,  // real pairs only
                L.slot_id.as<uint32_t>(), want_csr ? L.deg.as<uint32_t>() : (uint32_t*)nullptr, counts, L.vcap);
     switch (d) {
