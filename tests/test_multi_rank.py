@@ -53,7 +53,7 @@ def test_algorithmic_bytes_table():
     import bench
     env = {"N": 640 * 480, "M": 17, "Ns": 70000, "D": 366, "T": 4, "nodes": 16000, "leaves": 8000, "P": 77,
            "lat": [(3, 40000), (5, 11000)]}
-    b = bench.algo_bytes("meanfield_tile_kernel", env)
+    b = bench.algo_bytes("meanfield_point_kernel", env)
     # one mean-field iteration of this CRF moves on the order of 80 MB
     assert 60e6 < b < 110e6
     assert bench.algo_bytes("patch_features_kernel", env) > 4 * 363 * 70000

@@ -13,6 +13,6 @@ if [ "$2" != "noncu" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --quick --inflight 1 > $OUT/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'meanfield_tile_kernel|blur_multi_coop|integral_wavefront|lattice_embed|patch_features|tile_csr_build|splat_ones_runs|forest_traverse|upsample_kernel' \
+    -k regex:'meanfield_point_kernel|blur_multi_coop|integral_wavefront|lattice_embed|bitmap_prefix|tile_csr_build|forest_frame_lowres|upsample_kernel|remap_offsets|assign_ids' \
     --launch-skip 60 --launch-count 36 -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 3 --quick --inflight 1 > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 fi
