@@ -213,16 +213,44 @@ __global__ void __launch_bounds__(256) first_bitmap_kernel(const uint32_t* __res
     const uint32_t r = first_ref[s];
     if (r != 0xFFFFFFFFu) atomicOr(bitmap + (r >> 5), 1u << (r & 31));
 }
-__global__ void __launch_bounds__(1024) bitmap_prefix_kernel(const uint32_t* __restrict__ bitmap, uint32_t nwords,
-                                                             uint32_t* __restrict__ prefix, uint32_t* __restrict__ counts,
-                                                             uint32_t vcap) {
-    __shared__ uint32_t wsum[32];
-    const uint32_t per = (nwords + blockDim.x - 1) / blockDim.x;
-    const uint32_t w0 = threadIdx.x * per, w1 = min(nwords, w0 + per);
-    uint32_t s = 0;
-    for (uint32_t w = w0; w < w1; w++) s += __popc(bitmap[w]);
-    // exclusive scan of the per-thread sums over the CTA
+// prefix[w] = number of set bits in words [0, w): two launches, every load coalesced and independent.  A CTA owns a chunk
+// of 4096 words (1024 threads x one uint4); pass 1 writes the chunks' popcounts, pass 2 adds up the chunks before its own
+// (a few hundred words even for a 15 M-point map) and scans its chunk.  nwords is a multiple of 4 (the host rounds up).
+constexpr uint32_t BMP_CHUNK = 4096;
+__device__ __forceinline__ uint32_t block_sum_1024(uint32_t v, uint32_t* wsum) {  // result valid in every thread
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if (lane == 0) wsum[wid] = v;
+    __syncthreads();
+    uint32_t t = wsum[lane];
+    t = __reduce_add_sync(0xffffffffu, t);
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(1024) bitmap_chunk_sums_kernel(const uint32_t* __restrict__ bitmap, uint32_t nwords,
+                                                                 uint32_t* __restrict__ sums) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t w = blockIdx.x * BMP_CHUNK + threadIdx.x * 4;
+    uint32_t s = 0;
+    if (w < nwords) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(bitmap + w));
+        s = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    s = block_sum_1024(s, wsum);
+    if (threadIdx.x == 0) sums[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(1024) bitmap_prefix_kernel(const uint32_t* __restrict__ bitmap, uint32_t nwords,
+                                                             const uint32_t* __restrict__ sums, uint32_t* __restrict__ prefix,
+                                                             uint32_t* __restrict__ counts, uint32_t vcap) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * BMP_CHUNK + threadIdx.x * 4;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (w < nwords) v = __ldg(reinterpret_cast<const uint4*>(bitmap + w));
+    uint32_t before = 0;
+    for (uint32_t c = threadIdx.x; c < blockIdx.x; c += blockDim.x) before += __ldg(sums + c);
+    before = block_sum_1024(before, wsum);
+    const uint32_t p0 = __popc(v.x), p1 = __popc(v.y), p2 = __popc(v.z), p3 = __popc(v.w), s = p0 + p1 + p2 + p3;
     uint32_t inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -232,24 +260,23 @@ __global__ void __launch_bounds__(1024) bitmap_prefix_kernel(const uint32_t* __r
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t v = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0u, iv = v;
+        const uint32_t x = wsum[lane];
+        uint32_t ix = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, ix, o);
+            if (lane >= o) ix += t;
         }
-        wsum[lane] = iv - v;
-        if (lane == 31) {  // total = number of vertices
-            counts[0] = iv;
-            if (iv > vcap) counts[1] = 1u;  // load factor above 1/2: the host retries with a bigger table
+        wsum[lane] = ix - x;
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) {  // total = number of vertices
+            const uint32_t V = before + ix;
+            counts[0] = V;
+            if (V > vcap) counts[1] = 1u;  // load factor above 1/2: the host retries with a bigger table
         }
     }
     __syncthreads();
-    uint32_t run = wsum[wid] + inc - s;
-    for (uint32_t w = w0; w < w1; w++) {
-        prefix[w] = run;
-        run += __popc(bitmap[w]);
-    }
+    const uint32_t run = before + wsum[wid] + inc - s;
+    if (w < nwords) *reinterpret_cast<uint4*>(prefix + w) = make_uint4(run, run + p0, run + p0 + p1, run + p0 + p1 + p2);
 }
 __global__ void __launch_bounds__(256) assign_ids_bitmap_kernel(const uint32_t* __restrict__ first_ref, uint32_t hcap,
                                                                 const uint32_t* __restrict__ bitmap,
@@ -547,7 +574,7 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     RSS_CU(ctx, L.table.reserve((size_t)hcap * sizeof(Key128)));
     RSS_CU(ctx, L.slot_id.reserve((size_t)hcap * 4));
     RSS_CU(ctx, L.first_ref.reserve((size_t)hcap * 4));
-    RSS_CU(ctx, L.rank.reserve((nnz_ext + 8) * 4));
+    RSS_CU(ctx, L.rank.reserve((nnz_ext + 64) * 4));  // bitmap + prefix (nnz / 32 words each, rounded) + chunk sums
     RSS_CU(ctx, L.vkeys.reserve((size_t)L.vcap * sizeof(Key128)));
     RSS_CU(ctx, L.offsets.reserve(nnz_ext * 4));
     RSS_CU(ctx, L.bary.reserve(nnz_ext * 4));
@@ -594,12 +621,15 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
     }
     // vertex numbering by first appearance (bitmap of first pairs -> popcount prefix -> rank per slot); counts[0] = V
     {
-        const uint32_t nwords = (uint32_t)((nnz_ext + 31) / 32);
+        const uint32_t nwords = (uint32_t)(((nnz_ext + 31) / 32 + 3) & ~(size_t)3);  // whole uint4s
+        const uint32_t nchunks = (nwords + BMP_CHUNK - 1) / BMP_CHUNK;
         uint32_t* bitmap = L.rank.as<uint32_t>();
         uint32_t* prefix = bitmap + nwords;
+        uint32_t* sums = prefix + nwords;
         RSS_CU(ctx, cudaMemsetAsync(bitmap, 0, (size_t)nwords * 4, st));
         RSS_LAUNCH(ctx, first_bitmap_kernel, rss_div_up(hcap, 256), 256, 0, st, L.first_ref.as<uint32_t>(), hcap, counts, bitmap);
-        RSS_LAUNCH(ctx, bitmap_prefix_kernel, 1, 1024, 0, st, bitmap, nwords, prefix, counts, L.vcap);
+        RSS_LAUNCH(ctx, bitmap_chunk_sums_kernel, nchunks, 1024, 0, st, bitmap, nwords, sums);
+        RSS_LAUNCH(ctx, bitmap_prefix_kernel, nchunks, 1024, 0, st, bitmap, nwords, sums, prefix, counts, L.vcap);
         RSS_LAUNCH(ctx, assign_ids_bitmap_kernel, rss_div_up(hcap, 256), 256, 0, st, L.first_ref.as<uint32_t>(), hcap, bitmap, prefix,
                    L.table.as<Key128>(), L.vcap, L.slot_id.as<uint32_t>(), L.vkeys.as<Key128>(), counts);
     }
