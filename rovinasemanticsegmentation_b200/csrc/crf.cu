@@ -442,7 +442,8 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
         ba.nbr[k] = L.nbr.as<int2>(); ba.counts[k] = L.counts.as<uint32_t>(); ba.d1[k] = L.d + 1; ba.vcap[k] = L.vcap;
     }
     const int d1a = Ls[0]->d + 1, d1b = K > 1 ? Ls[1]->d + 1 : 0;
-    const int maxd1 = std::max(d1a, d1b);
+    int phases_of[FUSED_MAX_LAT] = {0};
+    const int blur_phases = blur_multi_plan(ba, G, phases_of);
     const float* U = crf->unary.as<float>();
     float* Q = crf->Q.as<float>();
     Lattice& L0 = *Ls[0];
@@ -455,10 +456,10 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
             ba.ping[k] = tgt[k]->as<float4>(); ba.pong[k] = spare[k]->as<float4>(); ba.zero[k] = res[k]->as<float4>();
         }
         RSS_CU(ctx, launch_blur_multi(ctx, s0, ba, G, L0.counts.as<unsigned int>() + 8, L0.barrier_base));
-        L0.barrier_base += (unsigned int)(maxd1 - 1) * (unsigned int)blur_multi_grid(ctx);
+        L0.barrier_base += (unsigned int)(blur_phases - 1) * (unsigned int)blur_multi_grid(ctx);
         for (int k = 0; k < K; k++) {
-            DevBuf* X = (ba.d1[k] % 2 == 0) ? tgt[k] : spare[k];  // blurred result
-            DevBuf* Y = (ba.d1[k] % 2 == 0) ? spare[k] : tgt[k];
+            DevBuf* X = (phases_of[k] % 2 == 0) ? tgt[k] : spare[k];  // blurred result
+            DevBuf* Y = (phases_of[k] % 2 == 0) ? spare[k] : tgt[k];
             DevBuf* Z = res[k];                                    // cleared by the blur kernel: next splat target
             res[k] = X; spare[k] = Y; tgt[k] = Z;
             fa.lat[k].vin = res[k]->as<float>();

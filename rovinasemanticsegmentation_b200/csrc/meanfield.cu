@@ -44,6 +44,16 @@
 #ifndef RSS_TILE_SEG
 #define RSS_TILE_SEG 32
 #endif
+#ifndef RSS_BLUR_FUSE
+#define RSS_BLUR_FUSE 2  // lattice axes blurred per phase of the cooperative blur (1 = one grid barrier per axis); measured on
+                         // the keyframe workload: 30.4 us (1), 28.0 us (2), 29.9 us (3) per launch
+#endif
+#ifndef RSS_BLUR_FUSE3_ITEMS
+#define RSS_BLUR_FUSE3_ITEMS (400u << 10)  // float4 items (vcap * G) up to which 3 axes are fused (27 row reads per item) ...
+#endif
+#ifndef RSS_BLUR_FUSE2_ITEMS
+#define RSS_BLUR_FUSE2_ITEMS (1u << 20)    // ... and 2 axes (9 row reads per item)
+#endif
 
 namespace rss {
 
@@ -626,26 +636,58 @@ __device__ __forceinline__ void blur_axis(const float4* __restrict__ src, float4
         }
     }
 }
+// F consecutive axes in ONE phase: the value of vertex v after axes j0 .. j0+F-1 is computed recursively from the 3^F raw
+// values of its neighbourhood, with exactly the arithmetic of F separate passes (every intermediate is the same
+// blur_item of the same operands, so the result is bit-identical); a missing vertex (index vcap) is not part of the
+// lattice and contributes 0 whatever its own neighbours are.  This trades L2 reads (3^F instead of 3 F rows per item,
+// the L2 is at 15 % of its throughput in the one-axis-per-phase kernel) for grid barriers, each of which costs a full
+// store -> fence -> atomic -> poll -> load round trip of ~5 us on 148 SMs.
+template <int F>
+__device__ __forceinline__ float4 blur_value(const float4* __restrict__ src, const int2* __restrict__ nbr, int j0, int vcap, int G,
+                                             int v, int g) {
+    if (v == vcap) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (F == 0) {
+        return __ldcg(src + (size_t)v * G + g);
+    } else {
+        const int2 nb = __ldg(nbr + (size_t)(j0 + F - 1) * vcap + v);
+        const float4 o = blur_value<F - 1>(src, nbr, j0, vcap, G, v, g);
+        const float4 x = blur_value<F - 1>(src, nbr, j0, vcap, G, nb.x, g);
+        const float4 y = blur_value<F - 1>(src, nbr, j0, vcap, G, nb.y, g);
+        return blur_item(o, x, y);
+    }
+}
+template <int F>
+__device__ __forceinline__ void blur_axes(const float4* __restrict__ src, float4* __restrict__ dst, const int2* __restrict__ nbr,
+                                          int j0, uint32_t items, int G, int vcap, uint32_t tid, uint32_t nthr) {
+    for (uint32_t it = tid; it < items; it += nthr) {
+        const uint32_t v = it / (uint32_t)G, g = it - v * (uint32_t)G;
+        __stcg(dst + it, blur_value<F>(src, nbr, j0, vcap, G, (int)v, (int)g));
+    }
+}
 __global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __grid_constant__ BlurMultiArgs a, int G,
                                                               unsigned int* barrier, unsigned int barrier_base) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     uint32_t V[FUSED_MAX_LAT];
-    int maxd1 = 0;
-    for (int k = 0; k < a.K; k++) {
-        V[k] = a.counts[k][1] ? 0u : a.counts[k][0];
-        maxd1 = max(maxd1, a.d1[k]);
+    int j0[FUSED_MAX_LAT];
+    for (int k = 0; k < FUSED_MAX_LAT; k++) {
+        V[k] = k < a.K && !a.counts[k][1] ? a.counts[k][0] : 0u;
+        j0[k] = 0;
     }
-    for (int j = 0; j < maxd1; j++) {
+    for (int p = 0; p < a.phases; p++) {
         for (int k = 0; k < a.K; k++) {
-            if (j >= a.d1[k]) continue;
-            const float4* src = (j & 1) ? a.pong[k] : a.ping[k];
-            float4* dst = (j & 1) ? a.ping[k] : a.pong[k];
+            const int f = a.fuse[k][p];
+            if (f == 0) continue;
+            const float4* src = (p & 1) ? a.pong[k] : a.ping[k];
+            float4* dst = (p & 1) ? a.ping[k] : a.pong[k];
             const uint32_t items = V[k] * (uint32_t)G;
-            blur_axis<RSS_BLUR_U>(src, dst, a.nbr[k] + (size_t)j * a.vcap[k], items, G, (int)a.vcap[k], tid, nthr);
-            if (j == 0 && a.zero[k])
+            if (f == 1) blur_axis<RSS_BLUR_U>(src, dst, a.nbr[k] + (size_t)j0[k] * a.vcap[k], items, G, (int)a.vcap[k], tid, nthr);
+            else if (f == 2) blur_axes<2>(src, dst, a.nbr[k], j0[k], items, G, (int)a.vcap[k], tid, nthr);
+            else blur_axes<3>(src, dst, a.nbr[k], j0[k], items, G, (int)a.vcap[k], tid, nthr);
+            j0[k] += f;
+            if (p == 0 && a.zero[k])
                 for (uint32_t it = tid; it < items; it += nthr) __stcg(a.zero[k] + it, make_float4(0.f, 0.f, 0.f, 0.f));
         }
-        if (j + 1 < maxd1) grid_barrier(barrier, barrier_base + (unsigned int)(j + 1) * gridDim.x);
+        if (p + 1 < a.phases) grid_barrier(barrier, barrier_base + (unsigned int)(p + 1) * gridDim.x);
     }
 }
 
@@ -786,6 +828,28 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
 }
 
 int blur_multi_grid(const rss_ctx* c) { return c->sm_count; }  // one CTA per SM
+// Splits the d+1 axes of every lattice into phases of up to `RSS_BLUR_FUSE` fused axes (fewer grid barriers, more L2
+// reads): 3 axes per phase for tables of at most RSS_BLUR_FUSE3_ITEMS float4 items, 2 up to RSS_BLUR_FUSE2_ITEMS, else 1.
+// Returns the number of phases of the launch; phases_of[k] = phases lattice k takes part in (the blurred table is `ping`
+// when that is even, else `pong`).
+int blur_multi_plan(BlurMultiArgs& a, int G, int* phases_of) {
+    a.phases = 0;
+    for (int k = 0; k < FUSED_MAX_LAT; k++) {
+        for (int p = 0; p < BLUR_MAX_PHASES; p++) a.fuse[k][p] = 0;
+        if (k >= a.K) continue;
+        const size_t items = (size_t)a.vcap[k] * G;
+        const int fmax = std::min(RSS_BLUR_FUSE, items <= RSS_BLUR_FUSE3_ITEMS ? 3 : (items <= RSS_BLUR_FUSE2_ITEMS ? 2 : 1));
+        const int np = (a.d1[k] + fmax - 1) / fmax;
+        for (int p = 0, left = a.d1[k]; p < np; p++) {  // as even as possible, larger chunks first
+            const int f = (left + (np - p) - 1) / (np - p);
+            a.fuse[k][p] = f;
+            left -= f;
+        }
+        phases_of[k] = np;
+        a.phases = std::max(a.phases, np);
+    }
+    return a.phases;
+}
 cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
     // alone on the GPU: 512 threads per SM (the phases are L2-latency/throughput-bound); sharing it with other keyframes in
     // flight: 256, which leaves room for their kernels while this one waits at its barriers

@@ -90,8 +90,11 @@ __host__ __device__ constexpr int pt_index(int D1, int j, int lp) {
     if (j < 4 * n4 + 2 * n2) return 4 * n4 * TILE_POINTS + lp * 2 + (j - 4 * n4);
     return (4 * n4 + 2 * n2) * TILE_POINTS + lp;
 }
+constexpr int BLUR_MAX_PHASES = 8;
 struct BlurMultiArgs {
     int K;
+    int phases;                   // grid phases of the launch (blur_multi_plan)
+    int fuse[FUSED_MAX_LAT][BLUR_MAX_PHASES];  // axes lattice k blurs in phase p (0 = it has finished)
     float4* ping[FUSED_MAX_LAT];  // holds the splat on entry
     float4* pong[FUSED_MAX_LAT];
     float4* zero[FUSED_MAX_LAT];  // table to clear (next splat target) or NULL
@@ -120,6 +123,7 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
                            bool post, float slice_scale, const TileMap& tm, int d1, int row_bytes, const uint32_t* counts,
                            const TileCsrOut& out);
 int blur_multi_grid(const rss_ctx* c);  // CTAs of the cooperative blur (one barrier arrival each)
+int blur_multi_plan(BlurMultiArgs& a, int G, int* phases_of);  // fills a.phases / a.fuse; phases per lattice -> phases_of
 cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base);
 void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
                             const uint32_t* counts, float* values);
