@@ -122,6 +122,17 @@ rss_status rss_segment_frame(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* d
                              const float Kinv[9], const float R[9], const float t[3], float fill, float* posteriors);
 
 /* ---------------------------------------------------------------------------------------------------
+ * srv/SingleFrameSegmentation.srv (the node's external-semantics service, client side src/segmenter.cpp:446-514,
+ * stub server scripts/single_frame_segmentation_server.py:12-52): request = the RGB8 image and, as "depth", the
+ * rectified world-frame cloud the node computes at :463-488 (TYPE_32FC3, NaN where the raw depth is outside
+ * [0.5, 15] m); response = float32[] label_distribution in [layer][y][x][class] order.  depth3d: H*W*3 float.
+ * Kinv / R / t are the calibration of the camera the frame came from (the node rectifies with the same one).
+ * Equal to rss_segment_frame(fill = 0) on the raw depth image the cloud was made from.
+ * ------------------------------------------------------------------------------------------------- */
+rss_status rss_service_single_frame(rss_ctx* ctx, const uint8_t* rgb, const float* depth3d, int W, int H,
+                                    const float Kinv[9], const float R[9], const float t[3], float* label_distribution);
+
+/* ---------------------------------------------------------------------------------------------------
  * DenseCRF (third-party/densecrf/include/densecrf.h:36-121).  N points; n_layers label layers with
  * M[l] labels each share every lattice (the reference rebuilds the same lattice per layer,
  * src/segmenter.cpp:639-643; results are identical).  rss_crf_create(ctx,N,M) = one layer.

@@ -211,6 +211,19 @@ class Context:
                                                 C.c_float(fill), _ptr(out, C.c_float)))
         return out
 
+    # ---- srv/SingleFrameSegmentation.srv payloads (rss_service_single_frame)
+    def service_single_frame(self, rgb, depth3d, Kinv, R, t):
+        """rgb [H][W][3] u8 and the node's rectified cloud [H][W][3] f32 (src/segmenter.cpp:463-488) -> label_distribution."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth3d = np.ascontiguousarray(depth3d, np.float32)
+        H, W = depth3d.shape[:2]
+        Kinv, R, t = _calib(Kinv, R, t)
+        out = np.empty(self.sumC * H * W, np.float32)
+        self._check(self._lib.rss_service_single_frame(self.h, _ptr(rgb, C.c_uint8), _ptr(depth3d, C.c_float), W, H,
+                                                       _ptr(Kinv, C.c_float), _ptr(R, C.c_float), _ptr(t, C.c_float),
+                                                       _ptr(out, C.c_float)))
+        return out
+
     def segment_keyframe(self, rgb, depth, Kinv, R, t, params, W=None, H=None, want_Q=False, want_labels=True):
         """rgb/depth may be None to reuse the frame already resident on the device (then pass W, H)."""
         if rgb is not None:

@@ -870,3 +870,38 @@ extern "C" rss_status rss_segment_frame(rss_ctx* ctx, const uint8_t* rgb, const 
     frame_collect_timings(ctx, true);
     return RSS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// srv/SingleFrameSegmentation.srv served by this library: the node's external-semantics client
+// (src/segmenter.cpp:446-514) sends the RGB8 image and, as "depth", the RECTIFIED CLOUD it computes at :463-488
+//     p = (extrinsic.linear() * intrinsic_inverse) * (d x, d y, d)^T + t,  d = depth_mm / 1000.f,  NaN where d < 0.5 or > 15
+// (TYPE_32FC3, world frame), and expects float32[] label_distribution = [layer][y][x][class] (:497-500, the layout
+// scripts/single_frame_segmentation_server.py:47 builds).  The raw depth is recovered exactly: the camera-frame z of p is
+// d itself (the last row of the inverse intrinsics is (0, 0, 1)), and 1000 d is within 0.02 of the integer it came from.
+// ---------------------------------------------------------------------------------------------------
+extern "C" rss_status rss_service_single_frame(rss_ctx* ctx, const uint8_t* rgb, const float* depth3d, int W, int H,
+                                               const float Kinv[9], const float R[9], const float t[3],
+                                               float* label_distribution) {
+    if (!ctx) return RSS_ERR_INVALID;
+    if (!rgb || !depth3d || !Kinv || !R || !t) return ctx->fail(RSS_ERR_INVALID, "null request field");
+    if (W <= 0 || H <= 0) return ctx->fail(RSS_ERR_INVALID, "bad image size");
+    try {
+        std::vector<uint16_t>& depth = ctx->service_depth;
+        depth.resize((size_t)W * H);
+        const double r20 = R[2], r21 = R[5], r22 = R[8];  // third row of R^T = third column of R (row-major)
+        for (size_t i = 0, n = (size_t)W * H; i < n; i++) {
+            const float* p = depth3d + 3 * i;
+            uint16_t d = 0;  // NaN (the node's invalid marker) -> depth 0 = invalid for the feature extractor
+            if (p[0] == p[0] && p[1] == p[1] && p[2] == p[2]) {
+                const double z = r20 * ((double)p[0] - (double)t[0]) + r21 * ((double)p[1] - (double)t[1]) +
+                                 r22 * ((double)p[2] - (double)t[2]);
+                const double mm = std::nearbyint(z * 1000.0);
+                d = mm <= 0.0 ? 0 : (mm >= 65535.0 ? 65535 : (uint16_t)mm);
+            }
+            depth[i] = d;
+        }
+        return rss_segment_frame(ctx, rgb, depth.data(), W, H, Kinv, R, t, 0.0f, label_distribution);  // node: fill 0 (:357-362)
+    } catch (const std::exception& e) {
+        return ctx->fail(RSS_ERR_INVALID, e.what());
+    }
+}

@@ -166,6 +166,7 @@ struct rss_ctx {
     rss::DevBuf pose_dev;             // PoseParams
     struct KeyframeGraph* kf_graph = nullptr;  // captured device part of rss_segment_keyframe (crf.cu)
     bool graph_enabled = true;
+    std::vector<uint16_t> service_depth;  // raw depth recovered from a service request's rectified cloud (api.cu)
     bool counted_live = false;        // this context is counted in live_contexts(device)
     bool capturing = false;           // the device part of a keyframe is being captured: no per-stage timing events
     void mark(int i) {                // per-stage timing event on s0 (eager runs only)

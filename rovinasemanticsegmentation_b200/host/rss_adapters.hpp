@@ -351,3 +351,57 @@ class DenseCRF2D : public DenseCRF {
    protected:
     int W_, H_;
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// semantic_segmentation::SingleFrameSegmentation (srv/SingleFrameSegmentation.srv)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace semantic_segmentation {
+// srv/SingleFrameSegmentation.srv with plain structs in place of sensor_msgs/Image (same fields the node fills at
+// src/segmenter.cpp:490-497: height, width, encoding, step, data).  In a ROS build, `call` is the body of the callback
+// registered with advertiseService("/semantic_segmentation/SingleFrameSegmentation", ...): INTEGRATION.md.
+struct ImageMsg {
+    uint32_t height = 0, width = 0;
+    std::string encoding;  // "rgb8" for Request::rgb, "32FC3" for Request::depth
+    uint32_t step = 0;     // bytes per row
+    std::vector<uint8_t> data;
+};
+struct SingleFrameSegmentationRequest { ImageMsg rgb, depth; };
+struct SingleFrameSegmentationResponse { std::vector<float> label_distribution; };
+class SingleFrameSegmentationService {
+   public:
+    SingleFrameSegmentationService(rss::Session& s, const float Kinv[9], const float R[9], const float t[3]) : s_(s) {
+        std::memcpy(Kinv_, Kinv, sizeof Kinv_); std::memcpy(R_, R, sizeof R_); std::memcpy(t_, t, sizeof t_);
+    }
+    // returns false like a ROS service callback that fails (the node then throws, src/segmenter.cpp:502-504)
+    bool call(const SingleFrameSegmentationRequest& req, SingleFrameSegmentationResponse& resp) {
+        const uint32_t W = req.rgb.width, H = req.rgb.height;
+        if (W == 0 || H == 0 || req.depth.width != W || req.depth.height != H) return false;
+        if (req.rgb.encoding != "rgb8" || req.depth.encoding != "32FC3") return false;
+        if (req.rgb.step < 3 * W || req.depth.step < 12 * W) return false;
+        if (req.rgb.data.size() < (size_t)req.rgb.step * H || req.depth.data.size() < (size_t)req.depth.step * H) return false;
+        const uint8_t* rgb = req.rgb.data.data();
+        const float* cloud = reinterpret_cast<const float*>(req.depth.data.data());
+        std::vector<uint8_t> rgb_packed;
+        std::vector<float> cloud_packed;
+        if (req.rgb.step != 3 * W) {  // padded rows: pack
+            rgb_packed.resize((size_t)3 * W * H);
+            for (uint32_t y = 0; y < H; y++) std::memcpy(&rgb_packed[(size_t)3 * W * y], rgb + (size_t)req.rgb.step * y, 3 * W);
+            rgb = rgb_packed.data();
+        }
+        if (req.depth.step != 12 * W) {
+            cloud_packed.resize((size_t)3 * W * H);
+            for (uint32_t y = 0; y < H; y++)
+                std::memcpy(&cloud_packed[(size_t)3 * W * y], req.depth.data.data() + (size_t)req.depth.step * y, 12 * W);
+            cloud = cloud_packed.data();
+        }
+        resp.label_distribution.resize((size_t)s_.info().total_classes * W * H);
+        return rss_service_single_frame(s_.handle(), rgb, cloud, (int)W, (int)H, Kinv_, R_, t_,
+                                        resp.label_distribution.data()) == RSS_OK;
+    }
+
+   private:
+    rss::Session& s_;
+    float Kinv_[9], R_[9], t_[3];
+};
+
+}  // namespace semantic_segmentation

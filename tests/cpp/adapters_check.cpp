@@ -4,6 +4,7 @@
 //   adapters_check <config> <forest> <frame.raw> <calib.raw> <W> <H> <outdir>
 #include <cstdio>
 #include <fstream>
+#include <limits>
 
 #include "../../rovinasemanticsegmentation_b200/host/rss_adapters.hpp"
 
@@ -86,6 +87,42 @@ int main(int argc, char** argv) {
         dump(out + "/gated.bin", gated.data(), gated.size());
         dump(out + "/feats3.bin", feats.data(), (size_t)3 * N);
         dump(out + "/unary.bin", unary.data(), (size_t)M * N);
+        // semantic_segmentation::SingleFrameSegmentation: the request the node builds at src/segmenter.cpp:463-497
+        // (rectified cloud = (R * Kinv) * (d x, d y, d) + t, NaN outside [0.5, 15] m), rows padded by 16 bytes
+        {
+            using namespace semantic_segmentation;
+            float M3[9];
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    float acc = 0.f;
+                    for (int k = 0; k < 3; k++) acc += cal.extrinsic_linear[3 * i + k] * cal.intrinsic_inverse[3 * k + j];
+                    M3[3 * i + j] = acc;
+                }
+            SingleFrameSegmentationRequest req;
+            req.rgb.height = req.depth.height = H; req.rgb.width = req.depth.width = W;
+            req.rgb.encoding = "rgb8"; req.depth.encoding = "32FC3";
+            req.rgb.step = 3 * W + 16; req.depth.step = 12 * W + 16;
+            req.rgb.data.assign((size_t)req.rgb.step * H, 0);
+            req.depth.data.assign((size_t)req.depth.step * H, 0);
+            for (int y = 0; y < H; y++) {
+                memcpy(&req.rgb.data[(size_t)req.rgb.step * y], &rgb[(size_t)3 * W * y], 3 * W);
+                float* row = reinterpret_cast<float*>(&req.depth.data[(size_t)req.depth.step * y]);
+                for (int x = 0; x < W; x++) {
+                    const float d = static_cast<float>(depth[(size_t)y * W + x]) / 1000.0f;
+                    for (int i = 0; i < 3; i++) {
+                        const float v[3] = {d * x, d * y, d};
+                        row[3 * x + i] = (d < 0.5 || d > 15.0) ? std::numeric_limits<float>::quiet_NaN()
+                                         : M3[3 * i] * v[0] + M3[3 * i + 1] * v[1] + M3[3 * i + 2] * v[2] + cal.extrinsic_translation[i];
+                    }
+                }
+            }
+            SingleFrameSegmentationService service(session, cal.intrinsic_inverse, cal.extrinsic_linear, cal.extrinsic_translation);
+            SingleFrameSegmentationResponse resp;
+            if (!service.call(req, resp)) throw std::runtime_error("SingleFrameSegmentation service call failed");
+            dump(out + "/service.bin", resp.label_distribution.data(), resp.label_distribution.size());
+            req.depth.encoding = "mono16";
+            if (service.call(req, resp)) throw std::runtime_error("a wrong encoding must make the service call fail");
+        }
         printf("adapters ok: %d samples, D=%d\n", n, D);
     } catch (const std::exception& e) {
         fprintf(stderr, "adapters_check: %s\n", e.what());

@@ -42,6 +42,9 @@ def test_reference_named_adapters(orc, tmp_path):
     assert ld("post.bin", np.float32).tobytes() == post0.tobytes()
     n = f0.shape[0]
     assert ld("post_single.bin", np.float32).tobytes() == post0[::n // 7 + 1].tobytes()
+    # SingleFrameSegmentation service adapter == the frame worker (fill 0), bit for bit
+    post_frame = orc.segment_frame(orc.default_config(), orc.Forest(FOREST), 2, rgb, depth, Kinv, R, t, 0.5, 15.0, 0.0)
+    assert ld("service.bin", np.float32).tobytes() == post_frame.tobytes()
     # DenseCRF2D / DenseCRF
     M, N = 5, W * H
     U = ld("unary.bin", np.float32).reshape(N, M)
