@@ -122,6 +122,37 @@ rss_status rss_segment_frame(rss_ctx* ctx, const uint8_t* rgb, const uint16_t* d
                              const float Kinv[9], const float R[9], const float t[3], float fill, float* posteriors);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Forest training on the GPU: libf::DecisionTreeLearner::learn + updateMultiHistograms and RandomForestLearner::learn
+ * (third-party/libforest/src/learning.cpp:410-916, 963-1012, 1031-1073) with the learner set-up of src/train.cpp:225-249.
+ * feats [n][D] and labels [n][n_layers] are host buffers (the DataStorage of train.cpp: rss_extract_features with
+ * RSS_WITH_POSITIVE_LABEL produces both); class_counts[l] = classes of layer l.  The model is written to out_dat_path in
+ * the libforest binary format (RandomForest::write, classifier.cpp:210-220) - the file rss_load_forest and the
+ * reference's RandomForest::read accept.  Defaults of rss_train_params_default = train.cpp + DecisionTreeLearner():
+ * bootstrap of n examples, ceil(sqrt(D)) features per node, min_child_split_examples 1, smoothing 1.
+ * The learner is seeded and deterministic (the reference draws from std::random_device).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct rss_train_params {
+    int num_trees;                 /* config num_trees */
+    int max_depth;                 /* config max_depth (a node splits while depth <= max_depth, learning.cpp:525) */
+    int min_split_examples;        /* config min_split_sample */
+    int min_child_split_examples;  /* 1 */
+    int num_features;              /* 0 = ceil(sqrt(D)) (autoconf, learning.cpp:363-368) */
+    int use_bootstrap;             /* 1 */
+    int num_bootstrap_examples;    /* 0 = n */
+    float smoothing;               /* 1 */
+    uint64_t seed;
+} rss_train_params;
+typedef struct rss_train_stats {
+    int trees, features_per_node, bootstrap_examples;
+    long long nodes, levels;
+    double train_ms;               /* device + host time of the whole call */
+} rss_train_stats;
+void rss_train_params_default(rss_train_params* p);
+rss_status rss_forest_train(rss_ctx* ctx, const float* feats, int n, int D, const int32_t* labels, int n_layers,
+                            const int* class_counts, const rss_train_params* params, const char* out_dat_path,
+                            rss_train_stats* stats /* may be NULL */);
+
+/* ---------------------------------------------------------------------------------------------------
  * srv/SingleFrameSegmentation.srv (the node's external-semantics service, client side src/segmenter.cpp:446-514,
  * stub server scripts/single_frame_segmentation_server.py:12-52): request = the RGB8 image and, as "depth", the
  * rectified world-frame cloud the node computes at :463-488 (TYPE_32FC3, NaN where the raw depth is outside

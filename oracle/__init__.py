@@ -351,6 +351,57 @@ def ref_forest_train(feats, labels, out_path, num_trees=4, max_depth=30, min_spl
         raise IOError("reference learner could not write " + out_path)
 
 
+def ref_forest_train_opts(feats, labels, out_path, num_trees=1, max_depth=30, min_split=50, min_child_split=1,
+                          num_features=0, use_bootstrap=True, smoothing=1.0, threads=1):
+    """The unmodified reference learner with its options exposed (0 features = autoconf's ceil(sqrt(D)))."""
+    feats = np.ascontiguousarray(feats, np.float32)
+    labels = np.ascontiguousarray(labels, np.int32)
+    n, D = feats.shape
+    L = ref()
+    L.ref_forest_train_opts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_float, C.c_int, C.c_char_p]
+    rc = L.ref_forest_train_opts(feats.ctypes.data, n, D, labels.ctypes.data, labels.shape[1], num_trees, max_depth, min_split,
+                                 min_child_split, num_features, 1 if use_bootstrap else 0, smoothing, threads, out_path.encode())
+    if rc:
+        raise IOError("reference learner could not write " + out_path)
+
+
+def ref_forest_update_histograms(in_path, feats, labels, out_path, smoothing=1.0):
+    """DecisionTreeLearner::updateMultiHistograms of the unmodified reference on every tree of the forest file in_path."""
+    feats = np.ascontiguousarray(feats, np.float32)
+    labels = np.ascontiguousarray(labels, np.int32)
+    n, D = feats.shape
+    L = ref()
+    L.ref_forest_update_histograms.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_char_p]
+    rc = L.ref_forest_update_histograms(in_path.encode(), feats.ctypes.data, n, D, labels.ctypes.data, labels.shape[1], smoothing,
+                                        out_path.encode())
+    if rc:
+        raise IOError("reference histogram update failed (%d)" % rc)
+
+
+def read_forest_dat(path):
+    """libforest binary model (RandomForest::write, classifier.cpp:210-220) -> list of trees
+    {feat, thr, left: arrays; multi: per node list of per-layer float arrays}."""
+    b = open(path, "rb").read()
+    o = [0]
+    def i32():
+        v = int(np.frombuffer(b, np.int32, 1, o[0])[0]); o[0] += 4; return v
+    def arr(dt, n):
+        v = np.frombuffer(b, dt, n, o[0]).copy(); o[0] += 4 * n; return v
+    trees = []
+    for _ in range(i32()):
+        n = i32(); feat = arr(np.int32, n)
+        assert i32() == n; thr = arr(np.float32, n)
+        assert i32() == n; left = arr(np.int32, n)
+        assert i32() == n
+        single = [arr(np.float32, i32()) for _ in range(n)]
+        assert i32() == n
+        multi = [[arr(np.float32, i32()) for _ in range(i32())] for _ in range(n)]
+        trees.append({"feat": feat, "thr": thr, "left": left, "single": single, "multi": multi})
+    assert o[0] == len(b)
+    return trees
+
+
 class RefForest:
     def __init__(self, path):
         self.h = ref().ref_forest_load(path.encode())

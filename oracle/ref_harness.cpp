@@ -51,6 +51,70 @@ int ref_forest_train(const float* feats, int n, int D, const int* labels, int L,
     return 0;
 }
 
+// The same learner with its options exposed (src/train.cpp:225-249 sets bootstrap on, class frequency off, multi-label
+// layers on).  With use_bootstrap = 0, num_features = D and one label layer nothing random is left in
+// DecisionTreeLearner::learn, so the tree is a deterministic function of the data: the GPU learner is compared with it.
+int ref_forest_train_opts(const float* feats, int n, int D, const int* labels, int L, int num_trees, int max_depth,
+                          int min_split, int min_child_split, int num_features, int use_bootstrap, float smoothing,
+                          int num_threads, const char* out_path) {
+    libf::DataStorage storage(L);
+    for (int i = 0; i < n; i++) {
+        libf::DataPoint* p = new libf::DataPoint(D);
+        for (int k = 0; k < D; k++) p->at(k) = feats[(size_t)i * D + k];
+        std::vector<int> lab(labels + (size_t)i * L, labels + (size_t)(i + 1) * L);
+        storage.addDataPointMulti(p, lab);
+    }
+    libf::DecisionTreeLearner treeLearner;
+    treeLearner.autoconf(&storage);
+    treeLearner.setUseBootstrap(use_bootstrap != 0);
+    if (num_features > 0) treeLearner.setNumFeatures(num_features);
+    treeLearner.setMaxDepth(max_depth);
+    treeLearner.setMinSplitExamples(min_split);
+    treeLearner.setMinChildSplitExamples(min_child_split);
+    treeLearner.setSmoothingParameter(smoothing);
+    treeLearner.setUseClassFrequency(false);
+    treeLearner.useMultiLabelLayers(true);
+    libf::RandomForestLearner forestLearner;
+    forestLearner.setTreeLearner(&treeLearner);
+    forestLearner.setNumTrees(num_trees);
+    forestLearner.setNumThreads(num_threads);
+    libf::RandomForest* forest = forestLearner.learn(&storage);
+    std::filebuf fb;
+    if (!fb.open(out_path, std::ios::out | std::ios::binary)) return 1;
+    std::ostream os(&fb);
+    forest->write(os);
+    fb.close();
+    delete forest;
+    return 0;
+}
+// DecisionTreeLearner::updateMultiHistograms (learning.cpp:963-1012) applied to every tree of an existing forest file:
+// the leaf histograms the reference computes for THAT tree structure from the given training set.
+int ref_forest_update_histograms(const char* in_path, const float* feats, int n, int D, const int* labels, int L,
+                                 float smoothing, const char* out_path) {
+    std::filebuf fi;
+    if (!fi.open(in_path, std::ios::in | std::ios::binary)) return 1;
+    std::istream is(&fi);
+    libf::RandomForest forest;
+    forest.read(is);
+    fi.close();
+    libf::DataStorage storage(L);
+    for (int i = 0; i < n; i++) {
+        libf::DataPoint* p = new libf::DataPoint(D);
+        for (int k = 0; k < D; k++) p->at(k) = feats[(size_t)i * D + k];
+        std::vector<int> lab(labels + (size_t)i * L, labels + (size_t)(i + 1) * L);
+        storage.addDataPointMulti(p, lab);
+    }
+    libf::DecisionTreeLearner treeLearner;
+    treeLearner.setSmoothingParameter(smoothing);
+    for (int t = 0; t < forest.getSize(); t++) treeLearner.updateMultiHistograms(dynamic_cast<libf::DecisionTree*>(forest.getTree(t)), &storage);
+    std::filebuf fb;
+    if (!fb.open(out_path, std::ios::out | std::ios::binary)) return 2;
+    std::ostream os(&fb);
+    forest.write(os);
+    fb.close();
+    return 0;
+}
+
 void* ref_forest_load(const char* path) {
     std::filebuf fb;
     if (!fb.open(path, std::ios::in | std::ios::binary)) return nullptr;

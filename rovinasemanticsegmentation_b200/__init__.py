@@ -50,6 +50,17 @@ class Timings(C.Structure):
 _lib = None
 
 
+class TrainParams(C.Structure):  # rss_train_params
+    _fields_ = [("num_trees", C.c_int), ("max_depth", C.c_int), ("min_split_examples", C.c_int),
+                ("min_child_split_examples", C.c_int), ("num_features", C.c_int), ("use_bootstrap", C.c_int),
+                ("num_bootstrap_examples", C.c_int), ("smoothing", C.c_float), ("seed", C.c_uint64)]
+
+
+class TrainStats(C.Structure):  # rss_train_stats
+    _fields_ = [("trees", C.c_int), ("features_per_node", C.c_int), ("bootstrap_examples", C.c_int),
+                ("nodes", C.c_longlong), ("levels", C.c_longlong), ("train_ms", C.c_double)]
+
+
 def load_library():
     """Loads librss.so; raises (never falls back) when it has not been built."""
     global _lib
@@ -187,6 +198,13 @@ class Context:
         return a, b, c
 
     # ---- RandomForest::multiClassLogPosterior
+    def load_forest(self, path):
+        """RandomForest::read (classifier.cpp:222-235) into this context; refreshes the model-derived info."""
+        self._check(self._lib.rss_load_forest(self.h, os.fsencode(path)))
+        self._check(self._lib.rss_get_info(self.h, C.byref(self.info)))
+        self.classes = list(self.info.class_counts[:self.info.layer_count])
+        self.sumC = self.info.total_classes
+
     def forest_predict(self, feats=None, n=None):
         if feats is not None:
             feats = np.ascontiguousarray(feats, np.float32)
@@ -210,6 +228,25 @@ class Context:
                                                 _ptr(Kinv, C.c_float), _ptr(R, C.c_float), _ptr(t, C.c_float),
                                                 C.c_float(fill), _ptr(out, C.c_float)))
         return out
+
+    # ---- GPU forest training (rss_forest_train)
+    def forest_train(self, feats, labels, class_counts, out_path, num_trees=4, max_depth=30, min_split_examples=50,
+                     min_child_split_examples=1, num_features=0, use_bootstrap=True, num_bootstrap_examples=0,
+                     smoothing=1.0, seed=1):
+        """feats [n][D] f32, labels [n][L] i32 -> libforest .dat at out_path; returns TrainStats."""
+        feats = np.ascontiguousarray(feats, np.float32)
+        labels = np.ascontiguousarray(labels, np.int32)
+        if labels.ndim == 1:
+            labels = labels[:, None]
+        n, D = feats.shape
+        L = labels.shape[1]
+        cc = np.ascontiguousarray(class_counts, np.int32)
+        prm = TrainParams(num_trees, max_depth, min_split_examples, min_child_split_examples, num_features,
+                          1 if use_bootstrap else 0, num_bootstrap_examples, smoothing, seed)
+        stats = TrainStats()
+        self._check(self._lib.rss_forest_train(self.h, _ptr(feats, C.c_float), n, D, _ptr(labels, C.c_int32), L,
+                                               _ptr(cc, C.c_int), C.byref(prm), os.fsencode(out_path), C.byref(stats)))
+        return stats
 
     # ---- srv/SingleFrameSegmentation.srv payloads (rss_service_single_frame)
     def service_single_frame(self, rgb, depth3d, Kinv, R, t):

@@ -905,3 +905,33 @@ extern "C" rss_status rss_service_single_frame(rss_ctx* ctx, const uint8_t* rgb,
         return ctx->fail(RSS_ERR_INVALID, e.what());
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// GPU forest training (train.cu)
+// ---------------------------------------------------------------------------------------------------
+extern "C" void rss_train_params_default(rss_train_params* p) {
+    if (!p) return;
+    p->num_trees = 4; p->max_depth = 30; p->min_split_examples = 50; p->min_child_split_examples = 1;
+    p->num_features = 0; p->use_bootstrap = 1; p->num_bootstrap_examples = 0; p->smoothing = 1.0f; p->seed = 1;
+}
+extern "C" rss_status rss_forest_train(rss_ctx* ctx, const float* feats, int n, int D, const int32_t* labels, int n_layers,
+                                       const int* class_counts, const rss_train_params* params, const char* out_dat_path,
+                                       rss_train_stats* stats) {
+    if (!ctx) return RSS_ERR_INVALID;
+    if (!feats || !labels || !class_counts || !params) return ctx->fail(RSS_ERR_INVALID, "train: null argument");
+    if (n <= 0 || D <= 0 || n_layers <= 0 || n_layers > RSS_MAX_LAYERS) return ctx->fail(RSS_ERR_INVALID, "train: bad sizes");
+    if (params->num_trees <= 0 || params->num_trees > 4096) return ctx->fail(RSS_ERR_INVALID, "train: bad tree count");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    RSS_CU(ctx, cudaEventCreate(&e0));
+    RSS_CU(ctx, cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->s0);
+    const rss_status st = forest_train(ctx, feats, n, D, labels, n_layers, class_counts, *params, out_dat_path, stats);
+    cudaEventRecord(e1, ctx->s0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats && st == RSS_OK) stats->train_ms = ms;
+    return st;
+}
