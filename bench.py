@@ -751,6 +751,8 @@ def run_gpu(args, rank, world, local_rank):
             line["local_map_15m"] = [
                 local_map_bench(ctx, synth, 15_000_000, 0.5, 4.0, peak, "node scales (xyz*0.5, rgb*4): few vertices"),
                 local_map_bench(ctx, synth, 15_000_000, 20.0, 40.0, peak, "fine scales (xyz*20, rgb*40): millions of vertices")]
+        if world == 1 and not args.quick:
+            line["forest_train"] = forest_train_bench(ctx, synth, not args.no_cpu)
         if world == 1 and not args.no_cpu and not args.quick:
             import oracle
             oracle.build(ref=False)
@@ -770,6 +772,42 @@ def run_gpu(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def forest_train_bench(ctx, synth, with_cpu):
+    """Side measurement of SURVEY 8(f) rank 2: training the 4-tree forest of the benchmark (src/train.cpp:225-249 set-up) on the
+    features of synthetic frames at training_sample_stride 5 - rss_forest_train on the GPU next to the unmodified reference
+    learner (oracle/_ref, all host cores) on the same DataStorage."""
+    import tempfile
+    Kinv, R, t = synth.calibration(W, H)
+    fs = []
+    for seed in range(900, 908):
+        rgb, depth = synth.frame(seed, W, H)
+        fs.append(ctx.extract_features(rgb, depth, Kinv, R, t, 5, 0.5, 15.0)[0].copy())
+    feats = np.concatenate(fs)
+    labels = synth.labels_from_features(feats, synth.label_thresholds(feats))
+    cc = [int(labels[:, 0].max()) + 1, int(labels[:, 1].max()) + 1]
+    out = {"samples": int(feats.shape[0]), "features": int(feats.shape[1]), "trees": 4, "max_depth": 30, "min_split": 50}
+    with tempfile.TemporaryDirectory() as tmp:
+        best = None
+        for _ in range(3):
+            st = ctx.forest_train(feats, labels, cc, os.path.join(tmp, "gpu.dat"), num_trees=4, max_depth=30,
+                                  min_split_examples=50, seed=1)
+            best = st.train_ms if best is None else min(best, st.train_ms)
+        out.update({"gpu_ms": best, "nodes": int(st.nodes), "levels": int(st.levels), "features_per_node": int(st.features_per_node),
+                    "note": "rss_forest_train incl. the H2D copy of the feature matrix and the host-side leaf histograms, best of 3"})
+        if with_cpu:
+            import oracle
+            oracle.build(ref=True)
+            if oracle.ref_available():
+                threads = max(1, min(os.cpu_count() or 1, 4))  # RandomForestLearner::learn: one OpenMP task per tree
+                t0 = time.perf_counter()
+                oracle.ref_forest_train(feats, labels, os.path.join(tmp, "ref.dat"), num_trees=4, max_depth=30, min_split=50,
+                                        threads=threads)
+                out["cpu_reference_ms"] = 1000.0 * (time.perf_counter() - t0)
+                out["cpu_threads"] = threads
+                out["cpu_kind"] = "reference (third-party/libforest/src/learning.cpp compiled in place, oracle/_ref)"
+    return out
 
 
 def main():

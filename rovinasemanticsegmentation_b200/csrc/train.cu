@@ -141,14 +141,36 @@ __global__ void __launch_bounds__(256) tr_block_hist_kernel(const uint8_t* __res
     __syncthreads();
     if (threadIdx.x < TR_CM) blockhist[blockIdx.x * TR_CM + threadIdx.x] = h[threadIdx.x];
 }
-// exclusive scan over the blocks, one thread per class (a few hundred blocks)
-__global__ void tr_block_scan_kernel(int* __restrict__ blockhist, int nblocks) {
-    const int c = threadIdx.x;
-    if (c >= TR_CM) return;
-    int run = 0;
-    for (int b = 0; b < nblocks; b++) {
-        const int v = blockhist[b * TR_CM + c];
-        blockhist[b * TR_CM + c] = run;
+// exclusive scan over the blocks: one CTA per class, a thread owns a run of consecutive blocks
+__global__ void __launch_bounds__(1024) tr_block_scan_kernel(int* __restrict__ blockhist, int nblocks) {
+    __shared__ int wsum[32];
+    const int c = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int per = (nblocks + 1023) / 1024, b0 = min(nblocks, (int)threadIdx.x * per), b1 = min(nblocks, b0 + per);
+    int sum = 0;
+    for (int b = b0; b < b1; b++) sum += blockhist[(size_t)b * TR_CM + c];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int v = wsum[lane];
+        int iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    int run = wsum[w] + inc - sum;
+    for (int b = b0; b < b1; b++) {
+        const int v = blockhist[(size_t)b * TR_CM + c];
+        blockhist[(size_t)b * TR_CM + c] = run;
         run += v;
     }
 }
@@ -490,7 +512,7 @@ rss_status forest_train(rss_ctx* ctx, const float* feats_h, int n, int D, const 
                                                                                       d_boot.as<int>(), d_labels.as<int>(), L,
                                                                                       d_slayer.as<int>(), d_cls.as<uint8_t>());
                 tr_block_hist_kernel<<<nblk, 256, 0, st>>>(d_cls.as<uint8_t>(), Qs, d_blockhist.as<int>());
-                tr_block_scan_kernel<<<1, 32, 0, st>>>(d_blockhist.as<int>(), nblk);
+                tr_block_scan_kernel<<<TR_CM, 1024, 0, st>>>(d_blockhist.as<int>(), nblk);
                 tr_node_base_kernel<<<rss_div_up((long long)S * F * 32, 256), 256, 0, st>>>(d_cls.as<uint8_t>(), d_blockhist.as<int>(),
                                                                                             d_sstart.as<int>(), S, F, n_active,
                                                                                             d_nodebase.as<int>());
