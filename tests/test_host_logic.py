@@ -1,0 +1,65 @@
+"""Host-side logic that needs no GPU: service message marshalling (srv/SingleFrameSegmentation.srv), training defaults,
+the libforest model parser used by the training tests."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import rovinasemanticsegmentation_b200 as rss
+from rovinasemanticsegmentation_b200 import service, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FOREST = os.path.join(ROOT, "tests", "golden", "forest_shared.dat")
+
+
+def test_train_params_default_follow_the_reference_learner():
+    lib = rss.load_library()
+    p = rss.TrainParams()
+    lib.rss_train_params_default(C.byref(p))
+    # DecisionTreeLearner() defaults (learning.h:109-118) + src/train.cpp:225-249 + resources/config.json
+    assert (p.num_trees, p.max_depth, p.min_split_examples, p.min_child_split_examples) == (4, 30, 50, 1)
+    assert p.num_features == 0 and p.use_bootstrap == 1 and p.num_bootstrap_examples == 0 and p.smoothing == 1.0
+
+
+def test_rectified_cloud_is_the_nodes_request_payload():
+    """src/segmenter.cpp:463-488: (R * Kinv) * (d x, d y, d) + t, NaN outside [0.5, 15] m; the camera-frame z of a valid point
+    is the raw depth (what rss_service_single_frame relies on)."""
+    W, H = 64, 48
+    rgb, depth = synth.frame(5, W, H)
+    Kinv, R, t = synth.calibration(W, H)
+    cloud = service.rectified_cloud(depth, Kinv, R, t)
+    assert cloud.shape == (H, W, 3) and cloud.dtype == np.float32
+    d = depth.astype(np.float32) / np.float32(1000.0)
+    bad = (d < 0.5) | (d > 15.0)
+    assert np.isnan(cloud[bad]).all() and np.isfinite(cloud[~bad]).all() and bad.any() and (~bad).any()
+    Rm = np.asarray(R, np.float64).reshape(3, 3)
+    z = (cloud[~bad].astype(np.float64) - np.asarray(t, np.float64)) @ Rm[:, 2]
+    assert np.array_equal(np.rint(z * 1000.0).astype(np.int64), depth[~bad].astype(np.int64))
+
+
+def test_image_message_marshalling():
+    H, W = 5, 7
+    a = np.arange(H * W * 3, dtype=np.uint8).reshape(H, W, 3)
+    packed = service.ImageMsg(H, W, "rgb8", 3 * W, a.tobytes())
+    assert np.array_equal(service.image_to_array(packed), a)
+    padded_rows = np.concatenate([a.reshape(H, -1), np.zeros((H, 5), np.uint8)], 1)
+    padded = service.ImageMsg(H, W, "rgb8", 3 * W + 5, padded_rows.tobytes())
+    assert np.array_equal(service.image_to_array(padded), a)
+    f = np.linspace(0, 1, H * W * 3, dtype=np.float32).reshape(H, W, 3)
+    assert np.array_equal(service.image_to_array(service.ImageMsg(H, W, "32FC3", 12 * W, f.tobytes())), f)
+    with pytest.raises(ValueError):
+        service.image_to_array(service.ImageMsg(H, W, "bgr8", 3 * W, a.tobytes()))
+    with pytest.raises(ValueError):
+        service.image_to_array(service.ImageMsg(H, W, "rgb8", 3 * W, a.tobytes()[:-1]))
+
+
+def test_forest_dat_parser_matches_the_oracle_loader(orc):
+    trees = orc.read_forest_dat(FOREST)
+    F = orc.Forest(FOREST)
+    assert len(trees) == F.T and [len(t["feat"]) for t in trees] == F.nodes
+    for t in trees:
+        leaves = t["left"] == 0
+        assert leaves.sum() == (~leaves).sum() + 1  # a binary tree
+        for i in np.flatnonzero(leaves)[:20]:
+            assert [len(h) for h in t["multi"][i]] == F.classes
