@@ -21,7 +21,7 @@ namespace rss {
 float lattice_alpha(int d);
 rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* feat, int N, int d, uint32_t hcap, int Mp,
                          bool want_csr);
-rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h);
+rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h, const int* perm = nullptr);
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
                           int Mp);
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
@@ -331,6 +331,37 @@ __global__ void __launch_bounds__(256) zbuffer_to_index_kernel(const unsigned lo
     const unsigned long long k = zbuf[p];
     index_image[p] = k == ~0ull ? -1 : (int)(unsigned)(k & 0xffffffffull);
 }
+// Sorting an incoherent point set for the fused path: key = (vertex of simplex corner 0, vertex of corner 1), so that
+// consecutive sorted points share most of their lattice vertices
+__global__ void __launch_bounds__(256) sort_key_kernel(const int* __restrict__ offsets, int N, int d1, uint64_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ vals) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const uint32_t v0 = (uint32_t)offsets[(size_t)p * d1], v1 = d1 > 1 ? (uint32_t)offsets[(size_t)p * d1 + 1] : 0u;
+    keys[p] = ((uint64_t)v0 << 32) | v1;
+    vals[p] = (uint32_t)p;
+}
+// the run statistic of run_count_kernel (lattice.cu) over the sorted order: counts[6] += (position, corner) pairs whose
+// vertex differs from the same corner of the previous sorted point
+__global__ void __launch_bounds__(256) run_count_perm_kernel(const int* __restrict__ offsets, const int* __restrict__ perm, int N,
+                                                             int d1, uint32_t* __restrict__ counts) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool differs = false;
+    if (k < (size_t)N * d1) {
+        const size_t q = k / d1, j = k - q * d1;
+        differs = q == 0 || offsets[(size_t)perm[q] * d1 + j] != offsets[(size_t)perm[q - 1] * d1 + j];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, differs);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counts + 6, (uint32_t)__popc(m));
+}
+// rows of Mp floats in sorted order: dst[q] = src[perm[q]]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ src, const int* __restrict__ perm, int N, int G,
+                                                          float4* __restrict__ dst) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (size_t)N * G) return;
+    const size_t q = k / G, g = k - q * G;
+    dst[k] = src[(size_t)perm[q] * G + g];
+}
 // feature builders: DenseCRF2D::addPairwiseGaussian / Bilateral (densecrf.cpp:61-81), segmenter.cpp:629-637
 __global__ void __launch_bounds__(256) feat_gaussian_kernel(int W, int H, float sx, float sy, float* __restrict__ f) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,10 +475,19 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     const int d1a = Ls[0]->d + 1, d1b = K > 1 ? Ls[1]->d + 1 : 0;
     int phases_of[FUSED_MAX_LAT] = {0};
     const int blur_phases = blur_multi_plan(ba, G, phases_of);
-    const float* U = crf->unary.as<float>();
+    const float* U = crf->unary.as<float>();  // (replaced by the sorted copy for incoherent point sets, below)
     float* Q = crf->Q.as<float>();
     Lattice& L0 = *Ls[0];
-    const TileMap tm = fused_tile_map(N, crf->grid_w, crf->grid_h);
+    TileMap tm = fused_tile_map(N, crf->grid_w, crf->grid_h);
+    if (crf->sorted && tm.W == 0) {
+        // incoherent point set: tiles run over the sorted order; the unary rows are copied into that order once per
+        // inference (one gather), Q and the labels are written through the permutation by the last point kernel
+        tm.perm = crf->perm.as<int>();
+        RSS_CU(ctx, crf->unary_sorted.reserve((size_t)N * Mp * 4));
+        RSS_LAUNCH(ctx, gather_rows_kernel, rss_div_up((long long)N * G, 256), 256, 0, s0, crf->unary.as<float4>(), tm.perm, N, G,
+                   crf->unary_sorted.as<float4>());
+        U = crf->unary_sorted.as<float>();
+    }
     // pass 0: Q0 = expAndNormalize(-unary) and its splat
     for (int k = 0; k < K; k++) { fa.lat[k].vin = nullptr; fa.lat[k].vout = tgt[k]->as<float>(); }
     RSS_CU(ctx, launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, nullptr, tm, G, ls, 2));
@@ -550,6 +590,38 @@ static uint32_t next_pow2(uint64_t v) {
     return p;
 }
 
+// sorted position -> point of an incoherent point set (crf->perm): one 64-bit radix sort of (vertex 0, vertex 1) keys
+static rss_status crf_sort_points(rss_crf* crf, cudaStream_t st, Lattice& L) {
+    rss_ctx* ctx = crf->ctx;
+    const int N = crf->N, d1 = L.d + 1;
+    RSS_CU(ctx, crf->sort_keys.reserve((size_t)N * 8));
+    RSS_CU(ctx, crf->sort_keys2.reserve((size_t)N * 8));
+    RSS_CU(ctx, crf->sort_vals.reserve((size_t)N * 4));
+    RSS_CU(ctx, crf->perm.reserve((size_t)N * 4));
+    RSS_LAUNCH(ctx, sort_key_kernel, rss_div_up(N, 256), 256, 0, st, L.offsets.as<int>(), N, d1, crf->sort_keys.as<uint64_t>(),
+               crf->sort_vals.as<uint32_t>());
+    int vbits = 1;
+    while (vbits < 32 && (1ull << vbits) <= (uint64_t)L.vcap) vbits++;
+    RSS_CU(ctx, sort_pairs_u64(st, crf->sort_tmp, crf->sort_keys.as<uint64_t>(), crf->sort_keys2.as<uint64_t>(),
+                               crf->sort_vals.as<uint32_t>(), crf->perm.as<uint32_t>(), (size_t)N, 32 + vbits));
+    return RSS_OK;
+}
+// is the lattice coherent over the sorted order?  (same rule as for the points' own order: on average a vertex run
+// spans more than two points)
+static rss_status crf_sorted_run_stat(rss_crf* crf, cudaStream_t st, Lattice& L, uint64_t maxv, bool* ordered) {
+    rss_ctx* ctx = crf->ctx;
+    uint32_t* counts = L.counts.as<uint32_t>();
+    RSS_CU(ctx, cudaMemsetAsync(counts + 6, 0, 4, st));
+    RSS_LAUNCH(ctx, run_count_perm_kernel, rss_div_up((long long)maxv, 256), 256, 0, st, L.offsets.as<int>(), crf->perm.as<int>(),
+               crf->N, L.d + 1, counts);
+    uint32_t runs = 0;
+    RSS_CU(ctx, cudaMemcpyAsync(&runs, counts + 6, 4, cudaMemcpyDeviceToHost, st));
+    RSS_CU(ctx, cudaStreamSynchronize(st));
+    L.runs = (long long)runs;
+    *ordered = 2 * (uint64_t)runs <= maxv;
+    return RSS_OK;
+}
+
 // Builds one more lattice from device-resident features on stream `st`.
 // sync = true : waits, checks the overflow flag and regrows the hash table until it fits (reference-shaped API).
 // sync = false: only enqueues; the caller checks crf_lattice_overflow() later (keyframe path, no host sync).
@@ -610,6 +682,26 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
             L->runs = (long long)h[5];
             // coherent point order: on average every vertex run spans more than two points
             L->ordered = raster || 2 * L->runs <= (long long)maxv;
+            const bool grid = crf->grid_w > 0 && (long long)crf->grid_w * crf->grid_h == crf->N;
+            if (crf->sorted && !grid) {
+                // the CRF's points already run in sorted order on the fused path: this lattice joins if it is coherent there
+                L->ordered = false;
+                rc = crf_sorted_run_stat(crf, st, *L, maxv, &L->ordered);
+                if (rc != RSS_OK) return fail_build(rc);
+                if (L->ordered && tile_ok) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, 0, 0, crf->perm.as<int>());
+                return RSS_OK;
+            }
+            if (!L->ordered && tile_ok && !grid && crf->kernels.size() == 1 && !getenv("RSS_NO_POINT_SORT")) {
+                // an incoherent point set (a local map): sort the points by their first two lattice vertices and take the
+                // fused path over the sorted order when that makes consecutive points share their vertices
+                rc = crf_sort_points(crf, st, *L);
+                if (rc != RSS_OK) return fail_build(rc);
+                rc = crf_sorted_run_stat(crf, st, *L, maxv, &L->ordered);
+                if (rc != RSS_OK) return fail_build(rc);
+                crf->sorted = L->ordered;
+                if (L->ordered) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, 0, 0, crf->perm.as<int>());
+                return RSS_OK;
+            }
             if (L->ordered && tile_ok && L->tile_TP == 0) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, crf->grid_w, crf->grid_h);
             return RSS_OK;
         }
@@ -644,6 +736,8 @@ void crf_free(rss_crf* crf) {
     crf->kernels.clear();
     crf->pool.clear();
     crf->unary.release(); crf->Q.release(); crf->scratch.release(); crf->labels.release(); crf->feat_stage.release();
+    crf->perm.release(); crf->unary_sorted.release(); crf->sort_keys.release(); crf->sort_keys2.release();
+    crf->sort_vals.release(); crf->sort_tmp.release();
     crf->cloud_xyz.release(); crf->cloud_rgb.release(); crf->zbuf.release(); crf->index_dev.release();
     for (int k = 0; k < 4; k++) {
         if (crf->side[k]) cudaStreamDestroy(crf->side[k]);
@@ -936,6 +1030,7 @@ extern "C" rss_status rss_crf_clear_pairwise(rss_crf* crf) {
     RSS_CU(ctx, cudaSetDevice(ctx->device));
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
     while (!crf->kernels.empty()) { crf->pool.push_back(crf->kernels.back()); crf->kernels.pop_back(); }
+    crf->sorted = false;
     return RSS_OK;
 }
 

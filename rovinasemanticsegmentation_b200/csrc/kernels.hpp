@@ -57,6 +57,10 @@ void launch_lowres_scatter(rss_ctx* c, cudaStream_t st, const float* post, int s
 void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, int gh, int W, int H, int L,
                      const int* C, float* posteriors, int unary_stride = 0);
 
+// sort.cu: radix sort of (u64 key, u32 value) pairs (CUB); tmp = caller-owned scratch
+cudaError_t sort_pairs_u64(cudaStream_t st, DevBuf& tmp, const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                           uint32_t* vals_out, size_t n, int bits);
+
 // train.cu: GPU forest training (learning.cpp:410-916, 963-1012, 1031-1073)
 rss_status forest_train(rss_ctx* ctx, const float* feats, int n, int D, const int32_t* labels, int L, const int* class_counts,
                         const rss_train_params& prm, const char* out_path, rss_train_stats* stats);

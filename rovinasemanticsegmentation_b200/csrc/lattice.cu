@@ -780,8 +780,9 @@ rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L) {
 
 // per-tile data of the fused mean-field kernel (after the normalisation: pre- / post-scale, Potts weight and slice scale
 // are folded into the weights)
-rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h) {
-    const TileMap tm = fused_tile_map(L.N, grid_w, grid_h);
+rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h, const int* perm) {
+    TileMap tm = fused_tile_map(L.N, grid_w, grid_h);
+    tm.perm = tm.W == 0 ? perm : nullptr;
     const int d1 = L.d + 1;
     const size_t ntiles = (size_t)tm.ntiles, cap = ntiles * tm.TP * d1;
     RSS_CU(ctx, L.tile_pairs.reserve(cap * sizeof(uint2)));

@@ -111,4 +111,10 @@ struct rss_crf {
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // per-lattice streams
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     bool unary_set = false;
+    // Point sets whose own order is not coherent (local maps): points sorted by their first two lattice vertices; the fused
+    // mean-field path runs over this order (meanfield.cuh, TileMap::perm).  Everything else stays in the caller's order.
+    rss::DevBuf perm;              // int[N]   sorted position -> point
+    rss::DevBuf unary_sorted;      // float[N][Mp] copy of the unary rows in sorted order (made at the start of an inference)
+    rss::DevBuf sort_keys, sort_keys2, sort_vals, sort_tmp;  // scratch of the sort
+    bool sorted = false;
 };

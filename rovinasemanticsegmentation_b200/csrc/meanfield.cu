@@ -732,6 +732,7 @@ TileMap fused_tile_map(int N, int W, int H) {
     TileMap m;
     m.N = N;
     m.TP = TILE_POINTS;
+    m.perm = nullptr;
     if (W > 0 && H > 0 && (long long)W * H == N) {
         m.W = W; m.H = H; m.TW = TILE_W; m.TH = TILE_H;
         m.tiles_x = (W + m.TW - 1) / m.TW;

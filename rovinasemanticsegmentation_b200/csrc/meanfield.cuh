@@ -18,6 +18,11 @@ constexpr int TILE_ROW_CAP = RSS_TILE_ROW_CAP;  // value rows per lattice a tile
 // times fewer distinct vertices than a strip of the same size (fewer splat atomics, fewer value rows to stage).
 struct TileMap {
     int N, TP, W, H, TW, TH, tiles_x, ntiles;  // TW is a power of two
+    // 1-D tiles only: tile t owns the SORTED positions [t * TP, (t + 1) * TP) of a point set whose own order is not
+    // coherent, and position q is the point perm[q] (crf.cu: points sorted by their first two lattice vertices); NULL =
+    // the points' own order.  Per-point lattice data is read, and Q / labels are written, through the indirection; the
+    // unary rows arrive as a copy in sorted order, so their staging stays one contiguous bulk copy per tile.
+    const int* perm;
 };
 // per-CTA constants of the mapping (the divisions happen once per CTA, not once per point)
 struct TileOrigin {
@@ -44,7 +49,7 @@ __device__ __forceinline__ int tile_point(const TileMap& m, const TileOrigin& o,
     if (lp >= m.TP) return -1;
     if (m.W == 0) {
         const long long p = o.base + lp;
-        return p < m.N ? (int)p : -1;
+        return p < m.N ? (m.perm ? __ldg(m.perm + p) : (int)p) : -1;
     }
     const int ly = lp >> o.tw_shift, lx = lp & (m.TW - 1);
     const int x = o.x0 + lx, y = o.y0 + ly;
