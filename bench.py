@@ -484,12 +484,20 @@ def local_map_bench(ctx, synth, NM, wxyz, wrgb, peak, regime):
         builds.append(time.perf_counter() - t0)
     crf.inference(10, unknown=[7, 8], want_Q=False, want_labels=True)
     ms_iter = ctx.timings()["meanfield_ms"] / 10
-    V, M, d = crf.lattice_size(0), 17, 6
-    # one iteration, generic path: splat (Q rows + vertex-major CSR in, value rows out), d+1 blur axes (rows in/out +
-    # neighbour pairs), slice + soft-max (offsets + weights + norm + unique rows + unary in, Q out)
-    ab = (4 * M * NM + 8 * (d + 1) * NM + 4 * NM + 4 * M * V) + (d + 1) * (8 * M * V + 8 * V) + \
-         (8 * (d + 1) * NM + 4 * NM + 4 * M * V + 8 * M * NM)
+    V, M, Mp, d = crf.lattice_size(0), 17, 20, 6
+    fused, sorted_ = crf.path()
+    if fused:
+        # fused path over the sorted point order: per iteration one point kernel (unary rows in sorted order + per (point,
+        # corner) slice weight, row slot and splat pair + the distinct value rows in and out) and the blur
+        ab = (4 * Mp * NM + 14 * (d + 1) * NM + 8 * M * V) + (d + 1) * (8 * M * V + 8 * V) + 4 * M * V
+    else:
+        # generic path: splat (Q rows + vertex-major CSR in, value rows out), d+1 blur axes (rows in/out + neighbour pairs),
+        # slice + soft-max (offsets + weights + norm + unique rows + unary in, Q out)
+        ab = (4 * M * NM + 8 * (d + 1) * NM + 4 * NM + 4 * M * V) + (d + 1) * (8 * M * V + 8 * V) + \
+             (8 * (d + 1) * NM + 4 * NM + 4 * M * V + 8 * M * NM)
     out = {"points": NM, "labels": 17, "regime": regime, "vertices": V, "ms_per_meanfield_iter": ms_iter,
+           "path": ("fused point kernel over the sorted point order" if sorted_ else "fused point kernel") if fused
+                   else "generic splat / blur / slice kernels",
            "lattice_build_ms_incl_h2d": 1000.0 * builds[-1], "first_build_ms_incl_allocation": 1000.0 * builds[0],
            "algorithmic_bytes_per_iter": int(ab), "achieved_gbs": ab / (ms_iter / 1000.0) / 1e9,
            "frac_of_hbm_peak": ab / (ms_iter / 1000.0) / 1e9 / peak}

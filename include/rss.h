@@ -191,6 +191,9 @@ rss_status rss_crf_step_inference(rss_crf* crf, int steps);
 rss_status rss_crf_current(rss_crf* crf, int layer, float* Q, uint8_t* labels, const int* unknown_label);
 /* number of lattice vertices of pairwise term k (diagnostics) */
 rss_status rss_crf_lattice_size(rss_crf* crf, int k, int* vertices);
+/* Diagnostics: the mean-field path of the next inference - fused point kernel or generic kernels; sorted = the fused path
+ * runs over the sorted order of a point set whose own order is not coherent (local maps).  No reference counterpart. */
+rss_status rss_crf_path(rss_crf* crf, int* fused, int* sorted);
 /* Permutohedral::compute on pairwise term k without normalisation (permutohedral.cpp:596-604):
  * in/out host M x N with M = total labels of the CRF; for parity tests of splat/blur/slice. */
 rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float* out);

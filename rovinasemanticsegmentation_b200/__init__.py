@@ -347,6 +347,12 @@ class DenseCRF:
                                                               C.c_float(wxyz), C.c_float(wrgb), C.c_float(potts_w)))
         self.n_kernels += 1
 
+    def path(self):
+        """(fused, sorted) of the next inference: rss_crf_path."""
+        f, s = C.c_int(0), C.c_int(0)
+        self.ctx._check(self._lib.rss_crf_path(self.h, C.byref(f), C.byref(s)))
+        return bool(f.value), bool(s.value)
+
     def lattice_size(self, k=0):
         v = C.c_int(0)
         self.ctx._check(self._lib.rss_crf_lattice_size(self.h, k, C.byref(v)))

@@ -890,6 +890,17 @@ extern "C" rss_status rss_crf_add_pairwise_xyzrgb(rss_crf* crf, const float* xyz
     return crf_add_kernel_dev(crf, ctx->s0, stage, 6, potts_w, RSS_NORMALIZE_SYMMETRIC, true);
 }
 
+// which mean-field path the next rss_crf_inference takes: *fused = 1 the fused point kernel (meanfield.cu), 0 the generic
+// splat / blur / slice kernels; *sorted = 1 when the fused path runs over the sorted order of an incoherent point set
+extern "C" rss_status rss_crf_path(rss_crf* crf, int* fused, int* sorted) {
+    if (!crf) return RSS_ERR_INVALID;
+    int a = 0, b = -1;
+    const bool f = !crf->kernels.empty() && crf_fused_order(crf, &a, &b);
+    if (fused) *fused = f ? 1 : 0;
+    if (sorted) *sorted = (f && crf->sorted && !(crf->grid_w > 0 && (long long)crf->grid_w * crf->grid_h == crf->N)) ? 1 : 0;
+    return RSS_OK;
+}
+
 extern "C" rss_status rss_crf_lattice_size(rss_crf* crf, int k, int* vertices) {
     if (!crf || !vertices) return RSS_ERR_INVALID;
     if (k < 0 || k >= (int)crf->kernels.size()) return crf->ctx->fail(RSS_ERR_INVALID, "no such pairwise term");

@@ -81,3 +81,43 @@ def test_map_worker_on_device_vs_oracle(ctx, orc):
     with pytest.raises(rss.RssError):
         crf.project_accumulate(W, H, K, R, t, 0.3, 8.0, slot=77)
     crf.close()
+
+
+def test_sorted_fused_path_for_incoherent_point_sets(ctx, orc, monkeypatch):
+    """A local map's points come in no particular order: the library sorts them by their first two lattice vertices and
+    runs the fused point kernel over the sorted order (crf.cu, TileMap::perm).  Same marginals as the oracle and as the
+    generic kernels; a set that stays incoherent after sorting (fine scales: about as many vertices as points) keeps the
+    generic path."""
+    from rovinasemanticsegmentation_b200 import synth
+    N = 150_000
+    xyz, col = synth.local_map(seed=3, n_points=N)
+    rng = np.random.default_rng(1)
+    shuffle = rng.permutation(N)  # make sure the input order carries no coherence at all
+    xyz, col = np.ascontiguousarray(xyz[shuffle]), np.ascontiguousarray(col[shuffle])
+    U = [rng.random((N, m), dtype=np.float32) * 3 for m in (8, 9)]
+
+    def run(wxyz, wrgb):
+        crf = ctx.crf(N, [8, 9])
+        for l in range(2):
+            crf.set_unary(U[l], l)
+        crf.add_pairwise_xyzrgb(xyz, col, wxyz, wrgb, 10.0)
+        path = crf.path()
+        Q, labels = crf.inference(5, unknown=[7, 8], want_Q=True, want_labels=True)
+        V = crf.lattice_size(0)
+        crf.close()
+        return path, Q, labels, V
+
+    (fused, sorted_), Q, labels, V = run(0.5, 4.0)
+    assert fused and sorted_ and V < N // 20
+    f6 = orc.features_xyzrgb(xyz, col, 0.5, 4.0)
+    for l, (M, unk) in enumerate(((8, 7), (9, 8))):
+        Q0 = orc.crf_inference(U[l], [(f6, 10.0)], 5)
+        assert np.abs(Q0 - Q[l]).max() <= 1e-4
+        assert (orc.gated_argmax(Q0, unk) == labels[l]).mean() >= 0.999
+    monkeypatch.setenv("RSS_NO_POINT_SORT", "1")
+    (fused_g, sorted_g), Qg, labels_g, _ = run(0.5, 4.0)
+    monkeypatch.delenv("RSS_NO_POINT_SORT")
+    assert not fused_g and not sorted_g
+    assert max(np.abs(Qg[l] - Q[l]).max() for l in range(2)) <= 1e-4 and (labels_g == labels).mean() >= 0.999
+    (fused_f, sorted_f), _, _, Vf = run(20.0, 40.0)
+    assert not fused_f and not sorted_f and Vf > N // 2
