@@ -190,6 +190,14 @@ rss_status rss_crf_start_inference(rss_crf* crf);
 rss_status rss_crf_step_inference(rss_crf* crf, int steps);
 rss_status rss_crf_current(rss_crf* crf, int layer, float* Q, uint8_t* labels, const int* unknown_label);
 /* number of lattice vertices of pairwise term k (diagnostics) */
+/* DenseCRF::gradient (third-party/densecrf/src/densecrf.cpp:238-297) with the LogLikelihood objective
+ * (src/objective.cpp:36-52): runs `iters` mean-field iterations of `layer`, evaluates
+ * objective = sum_i log(max(Q(gt_i, i) + robust, 1e-20)) / N over the points with 0 <= gt_i < M (gt: host [N]),
+ * back-propagates through the iterations and returns the gradient w.r.t. the label-compatibility parameter (the Potts
+ * weight, labelcompatibility.cpp:41-61) of every pairwise term: potts_grad[K] (may be NULL).  Kernel-parameter and unary
+ * gradients (DIAG_KERNEL features, LogisticUnaryEnergy) are not part of the reference's inference path and not built. */
+rss_status rss_crf_gradient(rss_crf* crf, int layer, int iters, const int32_t* gt, float robust, double* objective,
+                            float* potts_grad);
 rss_status rss_crf_lattice_size(rss_crf* crf, int k, int* vertices);
 /* Diagnostics: the mean-field path of the next inference - fused point kernel or generic kernels; sorted = the fused path
  * runs over the sorted order of a point set whose own order is not coherent (local maps).  No reference counterpart. */

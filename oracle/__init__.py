@@ -442,6 +442,25 @@ def ref_crf_inference(unary, kernels, iters, norm_type=3, want_map=False):
     return (Q, mp) if want_map else Q
 
 
+def ref_crf_gradient(unary, kernels, iters, gt, robust=0.0, norm_type=3):
+    """DenseCRF::gradient of the UNMODIFIED reference (densecrf.cpp:238-297) with the log-likelihood objective
+    (objective.cpp:36-52): returns (objective, gradient w.r.t. the Potts weight of every pairwise term)."""
+    unary = np.ascontiguousarray(unary, np.float32)
+    N, M = unary.shape
+    keep = [np.ascontiguousarray(f, np.float32) for f, _ in kernels]
+    K = len(kernels)
+    fp = (C.POINTER(C.c_float) * max(1, K))(*[_p(f, C.c_float) for f in keep])
+    d = (C.c_int * max(1, K))(*[f.shape[1] for f in keep])
+    w = (C.c_float * max(1, K))(*[float(k[1]) for k in kernels])
+    gt = np.ascontiguousarray(gt, np.int16)
+    g = np.zeros(max(1, K), np.float32)
+    L = ref()
+    L.ref_crf_gradient.restype = C.c_double
+    r = L.ref_crf_gradient(N, M, _p(unary, C.c_float), fp, d, w, K, int(norm_type), int(iters), _p(gt, C.c_int16),
+                           C.c_float(robust), _p(g, C.c_float))
+    return float(r), g[:K]
+
+
 def ref_crf2d_inference(W, H, unary, gauss, bilateral, im, iters):
     """DenseCRF2D with addPairwiseGaussian(sx, sy, w) + addPairwiseBilateral(sx, sy, sr, sg, sb, im, w) of the reference."""
     unary = np.ascontiguousarray(unary, np.float32)

@@ -220,6 +220,27 @@ void ref_crf_inference(int N, int M, const float* unary, const float* const* fea
         for (int i = 0; i < N; i++) map[i] = m[i];
     }
 }
+// DenseCRF::gradient (densecrf.cpp:238-297) with the reference's LogLikelihood objective (objective.cpp:36-52, compiled in
+// place): objective value and the gradient w.r.t. the label-compatibility parameters (one Potts weight per pairwise term).
+double ref_crf_gradient(int N, int M, const float* unary, const float* const* feats, const int* d, const float* w, int K,
+                        int norm_type, int iters, const short* gt, float robust, float* potts_grad) {
+    DenseCRF crf(N, M);
+    Eigen::MatrixXf U(M, N);
+    memcpy(U.data(), unary, sizeof(float) * (size_t)M * N);
+    crf.setUnaryEnergy(U);
+    for (int k = 0; k < K; k++) {
+        Eigen::MatrixXf f(d[k], N);
+        memcpy(f.data(), feats[k], sizeof(float) * (size_t)d[k] * N);
+        crf.addPairwiseEnergy(f, new PottsCompatibility(w[k]), DIAG_KERNEL, (NormalizationType)norm_type);
+    }
+    VectorXs gtv(N);
+    for (int i = 0; i < N; i++) gtv[i] = gt[i];
+    LogLikelihood obj(gtv, robust);
+    VectorXf g;
+    const double r = crf.gradient(iters, obj, nullptr, &g, nullptr);
+    for (int k = 0; k < K; k++) potts_grad[k] = g[k];
+    return r;
+}
 // examples/dense_inference.cpp's model: DenseCRF2D with addPairwiseGaussian + addPairwiseBilateral (densecrf.cpp:61-81)
 void ref_crf2d_inference(int W, int H, int M, const float* unary, float gsx, float gsy, float gw, float bsx, float bsy,
                          float bsr, float bsg, float bsb, const unsigned char* im, float bw, int iters, float* Q, short* map) {

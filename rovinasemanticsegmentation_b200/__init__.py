@@ -347,6 +347,15 @@ class DenseCRF:
                                                               C.c_float(wxyz), C.c_float(wrgb), C.c_float(potts_w)))
         self.n_kernels += 1
 
+    def gradient(self, iters, gt, layer=0, robust=0.0):
+        """DenseCRF::gradient with the log-likelihood objective: (objective, d objective / d Potts weight of every term)."""
+        gt = np.ascontiguousarray(gt, np.int32)
+        obj = C.c_double(0.0)
+        g = np.zeros(max(1, self.n_kernels), np.float32)
+        self.ctx._check(self._lib.rss_crf_gradient(self.h, int(layer), int(iters), _ptr(gt, C.c_int32), C.c_float(robust),
+                                                   C.byref(obj), _ptr(g, C.c_float)))
+        return obj.value, g[:self.n_kernels]
+
     def path(self):
         """(fused, sorted) of the next inference: rss_crf_path."""
         f, s = C.c_int(0), C.c_int(0)

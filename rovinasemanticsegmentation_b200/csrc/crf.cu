@@ -23,7 +23,7 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
                          bool want_csr);
 rss_status lattice_build_tile_csr(rss_ctx* ctx, cudaStream_t st, Lattice& L, int G, int grid_w, int grid_h, const int* perm = nullptr);
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
-                          int Mp);
+                          int Mp, bool reverse = false);
 void lattice_slice(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* values, int M, int Mp, int seq, float* out,
                    int out_stride);
 rss_status lattice_normalization(rss_ctx* ctx, cudaStream_t st, Lattice& L);
@@ -934,6 +934,161 @@ extern "C" rss_status rss_crf_filter(rss_crf* crf, int k, const float* in, float
                    crf->moff[l], M, crf->hoff[l], stage);
     RSS_CU(ctx, cudaMemcpyAsync(out, stage, (size_t)N * M * 4, cudaMemcpyDeviceToHost, ctx->s0));
     RSS_CU(ctx, cudaStreamSynchronize(ctx->s0));
+    return RSS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DenseCRF::gradient (densecrf.cpp:238-297) for the label-compatibility parameters of Potts terms, with the
+// log-likelihood objective (objective.cpp:36-52).  All matrices are [N][Mp] device rows; only the channels of the
+// requested layer carry non-zero "b", so the other layers drop out of every sum.
+// ---------------------------------------------------------------------------------------------------------------
+// LogLikelihood::evaluate: r += log(QQ) / N, d_mul_Q(gt, i) = Q / QQ / N with QQ = max(Q(gt, i) + robust, 1e-20)
+__global__ void __launch_bounds__(256) grad_loglik_kernel(const float* __restrict__ Q, const int* __restrict__ gt, int N, int Mp,
+                                                          int off, int Ml, float robust, float* __restrict__ b,
+                                                          double* __restrict__ objective) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double r = 0.0;
+    if (i < N) {
+        const int g = gt[i];
+        if (g >= 0 && g < Ml) {
+            const float q = Q[(size_t)i * Mp + off + g];
+            const float QQ = fmaxf(__fadd_rn(q, robust), 1e-20f);
+            r = (double)__fdiv_rn(logf(QQ), (float)N);
+            b[(size_t)i * Mp + off + g] = __fdiv_rn(__fdiv_rn(q, QQ), (float)N);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0 && r != 0.0) atomicAdd(objective, r);
+}
+// sumAndNormalize (densecrf.cpp:107-114) of in (.* mul when given): out = sum(b) * q - b per point, over one layer
+__global__ void __launch_bounds__(256) grad_sum_normalize_kernel(const float* __restrict__ in, const float* __restrict__ mul,
+                                                                 const float* __restrict__ Q, int N, int Mp, int off, int Ml,
+                                                                 float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t o = (size_t)i * Mp + off;
+    float v[32];
+    float s = 0.f;
+    for (int c = 0; c < Ml; c++) {
+        v[c] = mul ? __fmul_rn(in[o + c], mul[o + c]) : in[o + c];
+        s = __fadd_rn(s, v[c]);
+    }
+    for (int c = 0; c < Ml; c++) out[o + c] = __fsub_rn(__fmul_rn(s, Q[o + c]), v[c]);
+}
+// out[i][c] (op)= scale * in[i][c] * (norm ? norm[i] : 1) on one layer's channels
+__global__ void __launch_bounds__(256) grad_axpy_kernel(const float* __restrict__ in, const float* __restrict__ norm, float scale,
+                                                        int N, int Mp, int off, int Ml, int accumulate, float* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)N * Ml) return;
+    const int i = (int)(gid / Ml), c = (int)(gid - (long long)i * Ml);
+    const size_t o = (size_t)i * Mp + off + c;
+    float v = in[o];
+    if (norm) v = __fmul_rn(v, norm[i]);
+    v = __fmul_rn(scale, v);
+    out[o] = accumulate ? __fadd_rn(out[o], v) : v;
+}
+// sum over the layer's channels of a .* b (PottsCompatibility::gradient = -(b .* filtered Q).sum(), labelcompatibility.cpp:57-61)
+__global__ void __launch_bounds__(256) grad_dot_kernel(const float* __restrict__ a, const float* __restrict__ bb,
+                                                       const float* __restrict__ norm, int N, int Mp, int off, int Ml,
+                                                       double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double r = 0.0;
+    if (i < N) {
+        const size_t o = (size_t)i * Mp + off;
+        const float nv = norm ? norm[i] : 1.f;
+        for (int c = 0; c < Ml; c++) r += (double)__fmul_rn(__fmul_rn(a[o + c], nv), bb[o + c]);
+    }
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    if ((threadIdx.x & 31) == 0 && r != 0.0) atomicAdd(acc, r);
+}
+// DenseKernel::filter (pairwise.cpp:40-62) without the trailing normalisation: pre-normalisation + lattice filter
+// (reversed axis order when transposed) + slice.  Returns whether the caller still has to multiply by norm (post).
+static rss_status grad_filter(rss_crf* crf, Lattice& L, const float* in, bool transpose, float* out, bool* post) {
+    rss_ctx* ctx = crf->ctx;
+    const int nt = L.norm_type;
+    const bool pre = nt == RSS_NORMALIZE_SYMMETRIC || (nt == RSS_NORMALIZE_BEFORE && !transpose) || (nt == RSS_NORMALIZE_AFTER && transpose);
+    *post = nt == RSS_NORMALIZE_SYMMETRIC || (nt == RSS_NORMALIZE_BEFORE && transpose) || (nt == RSS_NORMALIZE_AFTER && !transpose);
+    float* vals = lattice_splat_blur(ctx, ctx->s0, L, in, crf->Mp, pre ? L.norm.as<float>() : nullptr, crf->Mp, transpose);
+    if (!vals) return ctx->fail(RSS_ERR_CUDA, std::string("cooperative blur launch: ") + cudaGetErrorString(cudaGetLastError()));
+    lattice_slice(ctx, ctx->s0, L, vals, crf->Mp, crf->Mp, crf->Mtot <= 2 ? 1 : 0, out, crf->Mp);
+    return RSS_OK;
+}
+extern "C" rss_status rss_crf_gradient(rss_crf* crf, int layer, int iters, const int32_t* gt, float robust, double* objective,
+                                       float* potts_grad) {
+    if (!crf) return RSS_ERR_INVALID;
+    rss_ctx* ctx = crf->ctx;
+    if (layer < 0 || layer >= crf->n_layers || iters < 0 || !gt || !objective)
+        return ctx->fail(RSS_ERR_INVALID, "gradient: bad layer, iteration count or null argument");
+    for (Lattice* L : crf->kernels)
+        if (!L->have_csr) return ctx->fail(RSS_ERR_STATE, "gradient: needs pairwise terms added through rss_crf_add_pairwise*");
+    RSS_CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s0 = ctx->s0;
+    const int N = crf->N, Mp = crf->Mp, K = (int)crf->kernels.size();
+    const int off = crf->moff[layer], Ml = crf->M[layer];
+    const size_t rows = (size_t)N * Mp;
+    DevBuf hist, bbuf, t1, t2, gt_dev, acc;
+    struct Free { DevBuf* b[6]; ~Free() { for (DevBuf* p : b) p->release(); } } guard{{&hist, &bbuf, &t1, &t2, &gt_dev, &acc}};
+    RSS_CU(ctx, hist.reserve(rows * 4 * (size_t)(iters + 1)));
+    RSS_CU(ctx, bbuf.reserve(rows * 4));
+    RSS_CU(ctx, t1.reserve(rows * 4));
+    RSS_CU(ctx, t2.reserve(rows * 4));
+    RSS_CU(ctx, gt_dev.reserve((size_t)N * 4));
+    RSS_CU(ctx, acc.reserve(8 * (size_t)(K + 1)));
+    RSS_CU(ctx, cudaMemcpyAsync(gt_dev.ptr, gt, (size_t)N * 4, cudaMemcpyHostToDevice, s0));
+    RSS_CU(ctx, cudaMemsetAsync(acc.ptr, 0, 8 * (size_t)(K + 1), s0));
+    // forward: Q[0] = expAndNormalize(-unary), Q[it + 1] = one mean-field step (generic kernels), every Q kept
+    rss_status st = crf_run(crf, 0, nullptr, nullptr, true);
+    if (st != RSS_OK) return st;
+    RSS_CU(ctx, cudaMemcpyAsync(hist.ptr, crf->Q.ptr, rows * 4, cudaMemcpyDeviceToDevice, s0));
+    for (int it = 0; it < iters; it++) {
+        st = crf_run(crf, 1, nullptr, nullptr, false);
+        if (st != RSS_OK) return st;
+        RSS_CU(ctx, cudaMemcpyAsync(hist.as<float>() + rows * (size_t)(it + 1), crf->Q.ptr, rows * 4, cudaMemcpyDeviceToDevice, s0));
+    }
+    float* b = bbuf.as<float>();
+    float* tmp1 = t1.as<float>();
+    float* tmp2 = t2.as<float>();
+    double* accd = acc.as<double>();
+    const float* Qn = hist.as<float>() + rows * (size_t)iters;
+    const int gN = rss_div_up(N, 256), gNM = rss_div_up((long long)N * Ml, 256);
+    // objective and b = sumAndNormalize(d_mul_Q, Q[n])
+    RSS_CU(ctx, cudaMemsetAsync(tmp1, 0, rows * 4, s0));
+    RSS_LAUNCH(ctx, grad_loglik_kernel, gN, 256, 0, s0, Qn, gt_dev.as<int>(), N, Mp, off, Ml, robust, tmp1, accd);
+    RSS_CU(ctx, cudaMemsetAsync(b, 0, rows * 4, s0));
+    RSS_LAUNCH(ctx, grad_sum_normalize_kernel, gN, 256, 0, s0, (const float*)tmp1, (const float*)nullptr, Qn, N, Mp, off, Ml, b);
+    for (int it = iters - 1; it >= 0; it--) {
+        const float* Qi = hist.as<float>() + rows * (size_t)it;
+        RSS_CU(ctx, cudaMemsetAsync(tmp1, 0, rows * 4, s0));
+        for (int k = 0; k < K; k++) {
+            Lattice& L = *crf->kernels[k];
+            bool post = false;
+            if (potts_grad) {  // PairwisePotential::gradient (pairwise.cpp:190-195): -(b .* kernel(Q[it])).sum()
+                st = grad_filter(crf, L, Qi, false, tmp2, &post);
+                if (st != RSS_OK) return st;
+                RSS_LAUNCH(ctx, grad_dot_kernel, gN, 256, 0, s0, (const float*)tmp2, (const float*)b,
+                           post ? L.norm.as<float>() : (const float*)nullptr, N, Mp, off, Ml, accd + 1 + k);
+            }
+            // PairwisePotential::applyTranspose (pairwise.cpp:179-183): kernel^T(b), then Potts: out = -w * out
+            st = grad_filter(crf, L, b, true, tmp2, &post);
+            if (st != RSS_OK) return st;
+            RSS_LAUNCH(ctx, grad_axpy_kernel, gNM, 256, 0, s0, (const float*)tmp2, post ? L.norm.as<float>() : (const float*)nullptr,
+                       -L.potts_w, N, Mp, off, Ml, 1, tmp1);
+        }
+        // b = sumAndNormalize(tmp1 .* Q[it], Q[it])
+        RSS_LAUNCH(ctx, grad_sum_normalize_kernel, gN, 256, 0, s0, (const float*)tmp1, Qi, Qi, N, Mp, off, Ml, b);
+    }
+    std::vector<double> h(K + 1);
+    RSS_CU(ctx, cudaMemcpyAsync(h.data(), accd, 8 * (size_t)(K + 1), cudaMemcpyDeviceToHost, s0));
+    RSS_CU(ctx, cudaStreamSynchronize(s0));
+    RSS_CU(ctx, cudaGetLastError());
+    *objective = h[0];
+    if (potts_grad)
+        for (int k = 0; k < K; k++) potts_grad[k] = (float)(-h[1 + k]);
+    for (Lattice* L : crf->kernels) {
+        uint32_t hh[2];
+        RSS_CU(ctx, cudaMemcpy(hh, L->counts.ptr, sizeof(hh), cudaMemcpyDeviceToHost));
+        if (hh[1]) return ctx->fail(RSS_ERR_CAPACITY, "lattice hash table overflow");
+    }
     return RSS_OK;
 }
 

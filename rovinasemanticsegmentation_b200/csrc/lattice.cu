@@ -471,14 +471,15 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float4* __restrict__ p, 
 __global__ void __launch_bounds__(512) blur_coop_kernel(float4* __restrict__ a, float4* __restrict__ b,
                                                         const int2* __restrict__ nbr, const uint32_t* __restrict__ counts,
                                                         int G, int d1, uint32_t vcap, unsigned int* barrier,
-                                                        unsigned int barrier_base) {
+                                                        unsigned int barrier_base, int reverse) {
     const uint32_t V = counts[1] ? 0u : counts[0];
     const uint32_t items = V * (uint32_t)G;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     float4* src = a;
     float4* dst = b;
     for (int j = 0; j < d1; j++) {
-        const int2* nb_j = nbr + (size_t)j * vcap;
+        // reverse: axes d .. 0, the transposed filter (Permutohedral::compute(out, in, true), permutohedral.cpp:555)
+        const int2* nb_j = nbr + (size_t)(reverse ? d1 - 1 - j : j) * vcap;
         for (uint32_t it = tid; it < items; it += nthr) {
             const uint32_t v = it / (uint32_t)G, g = it - v * (uint32_t)G;
             const int2 nb = __ldg(nb_j + v);
@@ -666,7 +667,7 @@ rss_status lattice_build(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float*
 
 // blur_coop_kernel on tables a (input) / b with G float4 items per vertex: result in a when d+1 is even, else in b; the
 // other table comes out all zero
-static cudaError_t launch_blur_coop(rss_ctx* ctx, cudaStream_t st, Lattice& L, float4* pa, float4* pb, int G) {
+static cudaError_t launch_blur_coop(rss_ctx* ctx, cudaStream_t st, Lattice& L, float4* pa, float4* pb, int G, int reverse = 0) {
     const int2* pn = L.nbr.as<int2>();
     const uint32_t* pc = L.counts.as<uint32_t>();
     int Garg = G, d1arg = L.d + 1;
@@ -675,7 +676,7 @@ static cudaError_t launch_blur_coop(rss_ctx* ctx, cudaStream_t st, Lattice& L, f
     const int grid = ctx->sm_count;
     unsigned int base = L.barrier_base;
     L.barrier_base += (unsigned int)d1arg * (unsigned int)grid;
-    void* args[] = {&pa, &pb, &pn, &pc, &Garg, &d1arg, &vc, &bar, &base};
+    void* args[] = {&pa, &pb, &pn, &pc, &Garg, &d1arg, &vc, &bar, &base, &reverse};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (ctx->profile) { ea = ctx->prof_event(); eb = ctx->prof_event(); cudaEventRecord(ea, st); }
     const cudaError_t e = cudaLaunchCooperativeKernel((const void*)blur_coop_kernel, dim3(grid), dim3(512), args, 0, st);
@@ -687,7 +688,7 @@ static cudaError_t launch_blur_coop(rss_ctx* ctx, cudaStream_t st, Lattice& L, f
 // splat -> (d+1) blurs; returns the table holding the blurred values (NULL when the launch failed).  in: [N][in_stride] (in_stride % 4 == 0).
 // Invariant: L.splat_target is all zero on entry; on exit the other table is (or becomes) the next target.
 float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float* in, int in_stride, const float* norm,
-                          int Mp) {
+                          int Mp, bool reverse) {
     const int G = Mp / 4, d1 = L.d + 1;
     float* a = L.splat_target ? L.val_b.as<float>() : L.val_a.as<float>();
     float* b = L.splat_target ? L.val_a.as<float>() : L.val_b.as<float>();
@@ -696,14 +697,14 @@ float* lattice_splat_blur(rss_ctx* ctx, cudaStream_t st, Lattice& L, const float
                L.csr_w.as<float>(), in, in_stride, norm, G, Mp, a);
     const bool small = (size_t)L.vcap * G <= (size_t)BLUR_COOP_MAX_ITEMS;
     if (small) {
-        if (launch_blur_coop(ctx, st, L, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), G) != cudaSuccess) return nullptr;
+        if (launch_blur_coop(ctx, st, L, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), G, reverse ? 1 : 0) != cudaSuccess) return nullptr;
     } else {
         float* s = a;
         float* d = b;
         for (int j = 0; j < d1; j++) {
             RSS_LAUNCH(ctx, blur_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st,
-                       reinterpret_cast<const float4*>(s), reinterpret_cast<float4*>(d), L.nbr.as<int2>() + (size_t)j * L.vcap,
-                       L.counts.as<uint32_t>(), G, (int)L.vcap);
+                       reinterpret_cast<const float4*>(s), reinterpret_cast<float4*>(d),
+                       L.nbr.as<int2>() + (size_t)(reverse ? d1 - 1 - j : j) * L.vcap, L.counts.as<uint32_t>(), G, (int)L.vcap);
             float* t = s; s = d; d = t;
         }
         RSS_LAUNCH(ctx, zero_rows_kernel, rss_div_up((long long)L.vcap * G, 256), 256, 0, st, reinterpret_cast<float4*>(d),

@@ -63,3 +63,20 @@ def test_forest_dat_parser_matches_the_oracle_loader(orc):
         assert leaves.sum() == (~leaves).sum() + 1  # a binary tree
         for i in np.flatnonzero(leaves)[:20]:
             assert [len(h) for h in t["multi"][i]] == F.classes
+
+
+def test_reference_gradient_harness_is_consistent(orc):
+    """oracle/_ref's DenseCRF::gradient (the checker of rss_crf_gradient): its Potts-weight gradient is the derivative of its
+    own objective (central finite differences), for the symmetric normalisation of the reference's path."""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref is not built here")
+    rng = np.random.default_rng(0)
+    N, M = 3000, 5
+    f = np.stack([rng.uniform(0, 30, N), rng.uniform(0, 30, N), rng.uniform(0, 8, N)], 1).astype(np.float32)
+    U = rng.random((N, M), dtype=np.float32) * 2
+    gt = rng.integers(-1, M, N).astype(np.int16)
+    r, g = orc.ref_crf_gradient(U, [(f, 3.0), (f[:, :2] * np.float32(0.5), 1.5)], 3, gt)
+    eps = 1e-2
+    r1, _ = orc.ref_crf_gradient(U, [(f, 3.0 + eps), (f[:, :2] * np.float32(0.5), 1.5)], 3, gt)
+    r0, _ = orc.ref_crf_gradient(U, [(f, 3.0 - eps), (f[:, :2] * np.float32(0.5), 1.5)], 3, gt)
+    assert r < 0 and abs((r1 - r0) / (2 * eps) - g[0]) <= 0.01 * abs(g[0])
