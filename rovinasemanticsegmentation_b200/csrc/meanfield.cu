@@ -48,6 +48,9 @@
 #define RSS_BLUR_FUSE 2  // lattice axes blurred per phase of the cooperative blur (1 = one grid barrier per axis); measured on
                          // the keyframe workload: 30.4 us (1), 28.0 us (2), 29.9 us (3) per launch
 #endif
+#ifndef RSS_BLUR_FU
+#define RSS_BLUR_FU 1  // independent items per thread and trip in a 2-axis phase
+#endif
 #ifndef RSS_BLUR_FUSE3_ITEMS
 #define RSS_BLUR_FUSE3_ITEMS (400u << 10)  // float4 items (vcap * G) up to which 3 axes are fused (27 row reads per item) ...
 #endif
@@ -656,12 +659,24 @@ __device__ __forceinline__ float4 blur_value(const float4* __restrict__ src, con
         return blur_item(o, x, y);
     }
 }
-template <int F>
+template <int F, int U>
 __device__ __forceinline__ void blur_axes(const float4* __restrict__ src, float4* __restrict__ dst, const int2* __restrict__ nbr,
                                           int j0, uint32_t items, int G, int vcap, uint32_t tid, uint32_t nthr) {
-    for (uint32_t it = tid; it < items; it += nthr) {
-        const uint32_t v = it / (uint32_t)G, g = it - v * (uint32_t)G;
-        __stcg(dst + it, blur_value<F>(src, nbr, j0, vcap, G, (int)v, (int)g));
+    for (uint32_t base = tid; base < items; base += U * nthr) {  // U independent items per trip: their load chains overlap
+        float4 r[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t it = base + u * nthr;
+            if (it < items) {
+                const uint32_t v = it / (uint32_t)G, g = it - v * (uint32_t)G;
+                r[u] = blur_value<F>(src, nbr, j0, vcap, G, (int)v, (int)g);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t it = base + u * nthr;
+            if (it < items) __stcg(dst + it, r[u]);
+        }
     }
 }
 __global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __grid_constant__ BlurMultiArgs a, int G,
@@ -681,8 +696,8 @@ __global__ void __launch_bounds__(RSS_BLUR_MAXT) blur_multi_coop_kernel(const __
             float4* dst = (p & 1) ? a.ping[k] : a.pong[k];
             const uint32_t items = V[k] * (uint32_t)G;
             if (f == 1) blur_axis<RSS_BLUR_U>(src, dst, a.nbr[k] + (size_t)j0[k] * a.vcap[k], items, G, (int)a.vcap[k], tid, nthr);
-            else if (f == 2) blur_axes<2>(src, dst, a.nbr[k], j0[k], items, G, (int)a.vcap[k], tid, nthr);
-            else blur_axes<3>(src, dst, a.nbr[k], j0[k], items, G, (int)a.vcap[k], tid, nthr);
+            else if (f == 2) blur_axes<2, RSS_BLUR_FU>(src, dst, a.nbr[k], j0[k], items, G, (int)a.vcap[k], tid, nthr);
+            else blur_axes<3, 1>(src, dst, a.nbr[k], j0[k], items, G, (int)a.vcap[k], tid, nthr);
             j0[k] += f;
             if (p == 0 && a.zero[k])
                 for (uint32_t it = tid; it < items; it += nthr) __stcg(a.zero[k] + it, make_float4(0.f, 0.f, 0.f, 0.f));

@@ -57,9 +57,9 @@ __global__ void __launch_bounds__(1024) k_blur(unsigned* counter, unsigned base,
     }
 }
 template <int U, bool PF, bool RED>
-void run(const char* name, int sms, int block, unsigned* counter, float4* a, float4* b, int2* nbr, int hi, int lo, int stride) {
+void run(const char* name, int sms, int block, unsigned* counter, float4* a, float4* b, int2* nbr, int hi, int lo, int stride, int nphase = 6) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int reps = 200; unsigned base = 0; int nphase = 6;
+    const int reps = 200; unsigned base = 0;
     cudaMemset(counter, 0, 4); cudaDeviceSynchronize();
     for (int pass = 0; pass < 2; pass++) {
         cudaEventRecord(e0);
@@ -71,7 +71,7 @@ void run(const char* name, int sms, int block, unsigned* counter, float4* a, flo
         cudaEventRecord(e1); cudaEventSynchronize(e1);
     }
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    printf("%-28s block %4d: %6.2f us/launch (%s)\n", name, block, 1000 * ms / reps, cudaGetErrorString(cudaGetLastError()));
+    printf("%-28s block %4d phases %d: %6.2f us/launch (%s)\n", name, block, nphase, 1000 * ms / reps, cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -82,6 +82,8 @@ int main() {
     int2* h = new int2[(size_t)6 * stride];
     for (int j = 0; j < 6; j++) for (int i = 0; i < stride; i++) { const int n = j < 4 ? hi : lo; h[(size_t)j * stride + i].x = (int)(((long long)i * 7919 + j * 31) % n); h[(size_t)j * stride + i].y = (int)(((long long)i * 104729 + 13 + j) % n); }
     cudaMemcpy(nbr, h, (size_t)6 * stride * 8, cudaMemcpyHostToDevice);
+    // fixed cost vs per-phase cost: the same kernel with 0..6 phases (0 = an empty cooperative launch)
+    for (int np = 0; np <= 6; np++) run<2, false, false>("U2 atom", sms, 512, counter, a, b, nbr, hi, lo, stride, np);
     for (int block : {128, 256, 512, 1024}) {
         run<1, false, false>("U1 atom", sms, block, counter, a, b, nbr, hi, lo, stride);
         run<2, false, false>("U2 atom", sms, block, counter, a, b, nbr, hi, lo, stride);
