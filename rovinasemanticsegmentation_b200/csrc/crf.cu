@@ -691,7 +691,10 @@ rss_status crf_add_kernel_dev(rss_crf* crf, cudaStream_t st, const float* feat_d
                 if (L->ordered && tile_ok) return lattice_build_tile_csr(ctx, st, *L, crf->Mp / 4, 0, 0, crf->perm.as<int>());
                 return RSS_OK;
             }
-            if (!L->ordered && tile_ok && !grid && crf->kernels.size() == 1 && !getenv("RSS_NO_POINT_SORT")) {
+            // (not for NO_NORMALIZATION: un-normalised messages saturate the marginals and amplify the run-to-run float noise of
+            // the fused path's atomic splat beyond the 1e-4 bar; that type is never used on the reference's path)
+            if (!L->ordered && tile_ok && !grid && crf->kernels.size() == 1 && norm_type != RSS_NO_NORMALIZATION &&
+                !getenv("RSS_NO_POINT_SORT")) {
                 // an incoherent point set (a local map): sort the points by their first two lattice vertices and take the
                 // fused path over the sorted order when that makes consecutive points share their vertices
                 rc = crf_sort_points(crf, st, *L);
