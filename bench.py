@@ -209,6 +209,10 @@ def algo_bytes(name, env):
         "fill_kernel": 4 * M * (N // 4), "lowres_scatter_kernel": 8 * M * Ns + 8 * Ns,
         "upsample_kernel": 4 * M * (N // 4) + 4 * M * N, "upsample_kernel<true>": 4 * M * (N // 4) + 4 * M * N,
         "upsample_kernel<false>": 4 * M * (N // 4) + 4 * M * N,
+        "upsample_unary_groups_kernel": 4 * M * (N // 4) + 4 * M * N,
+        # fused frame kernel: Lab image, depth + cloud + distance / integral images at the samples,
+        # the model, the low-res posterior image out
+        "forest_frame_lowres_kernel": 3 * Wb * Hb + 18 * N + 16 * env["nodes"] + 4 * M * env["leaves"] + 4 * M * (N // 4),
         "unary_from_posteriors_kernel": 8 * M * N,
         # C0 lattice construction (permutohedral.cpp:140-321)
         "lattice_embed_kernel<D>": mean(lambda d, V: 4 * d * N + 8 * (d + 1) * N + 2 * d * V),

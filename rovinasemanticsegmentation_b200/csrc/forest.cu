@@ -170,6 +170,48 @@ __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__
         }
     }
 }
+// The keyframe path's variant: one thread per (pixel, float4 channel group) of the CRF's [pixel][Mp] unary matrix, so a warp
+// stores 512 contiguous bytes (the per-pixel kernel above stores 17 scalars per thread at an 80-byte stride: 6.9e6 L2
+// sectors for 26 MB).  Same arithmetic per value; the padding channels of a layer get +inf like unary_init_kernel.
+__global__ void __launch_bounds__(256) upsample_unary_groups_kernel(const float* __restrict__ lowres, int gw, int gh, int W, int H,
+                                                                    LayerDims ld, int G, double scale_x, double scale_y,
+                                                                    float4* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)W * H * G) return;
+    const int p = (int)(gid / G), g = (int)(gid - (long long)p * G);
+    const int y = p / W, x = p - y * W;
+    float fx = (float)(((double)x + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= gw - 1) { sx = gw - 1; fx = 0.f; }
+    const int sx1 = min(sx + 1, gw - 1);
+    float fy = (float)(((double)y + 0.5) * scale_y - 0.5);
+    const int sy = (int)floorf(fy);
+    fy = __fsub_rn(fy, (float)sy);
+    const int y0 = min(max(sy, 0), gh - 1), y1 = min(max(sy + 1, 0), gh - 1);
+    const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
+    int l = 0;
+    while (l + 1 < ld.L && 4 * g >= ld.uoff[l + 1]) l++;
+    const int C = ld.C[l], c0 = 4 * g - ld.uoff[l];
+    const float* src = lowres + (size_t)gw * gh * ld.coff[l];
+    const float* r00 = src + ((size_t)y0 * gw + sx) * C;
+    const float* r01 = src + ((size_t)y0 * gw + sx1) * C;
+    const float* r10 = src + ((size_t)y1 * gw + sx) * C;
+    const float* r11 = src + ((size_t)y1 * gw + sx1) * C;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int cl = c0 + k;
+        v[k] = INFINITY;
+        if (cl < C) {
+            const float h0 = __fadd_rn(__fmul_rn(__ldg(r00 + cl), a0), __fmul_rn(__ldg(r01 + cl), a1));
+            const float h1 = __fadd_rn(__fmul_rn(__ldg(r10 + cl), a0), __fmul_rn(__ldg(r11 + cl), a1));
+            v[k] = -__fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+        }
+    }
+    out[gid] = make_float4(v[0], v[1], v[2], v[3]);
+}
 void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, int gh, int W, int H, int L,
                      const int* C, float* posteriors, int unary_stride) {
     LayerDims d = make_dims(L, C);
@@ -177,7 +219,10 @@ void launch_upsample(rss_ctx* c, cudaStream_t st, const float* lowres, int gw, i
     for (int l = 0; l < L; l++) sumC += C[l];
     const double scale_x = 1.0 / ((double)W / (double)gw), scale_y = 1.0 / ((double)H / (double)gh);
     const long long total = (long long)W * H;  // one thread per output pixel
-    if (unary_stride > 0)
+    if (unary_stride > 0 && unary_stride % 4 == 0 && d.uoff[L - 1] + ((C[L - 1] + 3) & ~3) == unary_stride)
+        RSS_LAUNCH(c, upsample_unary_groups_kernel, rss_div_up(total * (unary_stride / 4), 256), 256, 0, st, lowres, gw, gh, W, H, d,
+                   unary_stride / 4, scale_x, scale_y, reinterpret_cast<float4*>(posteriors));
+    else if (unary_stride > 0)
         RSS_LAUNCH(c, upsample_kernel<true>, rss_div_up(total, 256), 256, 0, st, lowres, gw, gh, W, H, d, sumC, unary_stride,
                    scale_x, scale_y, posteriors);
     else

@@ -44,6 +44,9 @@
 #ifndef RSS_TILE_SEG
 #define RSS_TILE_SEG 32
 #endif
+#ifndef RSS_SPLAT_REV
+#define RSS_SPLAT_REV 1  // the splat walks the second lattice's segments in reverse thread order (gather_entries)
+#endif
 #ifndef RSS_BLUR_FUSE
 #define RSS_BLUR_FUSE 2  // lattice axes blurred per phase of the cooperative blur (1 = one grid barrier per axis); measured on
                          // the keyframe workload: 30.4 us (1), 28.0 us (2), 29.9 us (3) per launch
@@ -145,10 +148,12 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1];
     extern __shared__ int tile_smem[];  // above the 48 KB static limit for large d
     int* hkeys = tile_smem;  // HC slots (power of two, > pairs per tile)
-    int* hcnt = tile_smem + HC;
-    int* hrow = tile_smem + 2 * HC;
-    int* hcur = tile_smem + 3 * HC;
-    unsigned short* pslot = reinterpret_cast<unsigned short*>(tile_smem + 4 * HC);
+    // per slot: pair count in the low half, fill cursor of the slot's pair list in the high half (both <= TP * D1 <
+    // 65536) - one word instead of two, and 16-bit row slots: 10 instead of 16 bytes per hash slot, which is what lets
+    // 5 (d = 5) / 6 (d = 3) CTAs share an SM instead of 4 - 1200 tiles are then two waves of CTAs instead of three
+    unsigned* hcc = reinterpret_cast<unsigned*>(tile_smem + HC);
+    unsigned short* hrow = reinterpret_cast<unsigned short*>(tile_smem + 2 * HC);
+    unsigned short* pslot = hrow + HC;
     uint2* spairs = reinterpret_cast<uint2*>(pslot + TILE_POINTS * D1);  // the tile's pair lists, ordered here, written out at the end
     int* segs = reinterpret_cast<int*>(spairs + TILE_POINTS * D1);      // start | length << 16 of every segment
     const int hshift = 32 - (31 - __clz(HC));
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         if (threadIdx.x == 0) out.tile_info[tile] = make_int2(0, 0);
         return;
     }
-    for (int i = threadIdx.x; i < HC; i += 256) { hkeys[i] = -1; hcnt[i] = 0; }
+    for (int i = threadIdx.x; i < HC; i += 256) { hkeys[i] = -1; hcc[i] = 0u; }
     if (threadIdx.x <= TILE_SEG) hist[threadIdx.x] = 0;
     __syncthreads();
     // pair i = (corner j, local point lp), lp fastest: the point-major outputs are written coalesced
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
             h = (h + 1) & (HC - 1);
         }
         pslot[i] = (unsigned short)h;
-        atomicAdd(&hcnt[h], 1);
+        atomicAdd(&hcc[h], 1u);
     }
     __syncthreads();
     // Lists are cut into segments of at most TILE_SEG pairs and the segments are ordered by length (longest first), so
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     const int spt = HC / 256, s0 = threadIdx.x * spt;  // slots per thread
 #pragma unroll 4
     for (int k = 0; k < spt; k++) {
-        const int c = hcnt[s0 + k];
+        const int c = (int)(hcc[s0 + k] & 0xffffu);
         if (c > 0) {
             const int full = c / TILE_SEG, rem = c - full * TILE_SEG;
             if (full) atomicAdd(&hist[TILE_SEG], full);
@@ -208,12 +213,12 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     }
     __syncthreads();
     for (int k = 0; k < spt; k++) {
-        const int c = hcnt[s0 + k];
+        const int c = (int)(hcc[s0 + k] & 0xffffu);
         if (c > 0) {
-            hrow[s0 + k] = pre3.z;             // the vertex's row slot in the tile
+            hrow[s0 + k] = (unsigned short)pre3.z;  // the vertex's row slot in the tile
             out.tile_vert[tb + pre3.z] = hkeys[s0 + k];
             pre3.z++;
-            hcur[s0 + k] = pre3.y;             // fill cursor of the slot's pair list
+            hcc[s0 + k] = (unsigned)c | ((unsigned)pre3.y << 16);  // fill cursor of the slot's pair list
             pre3.y += c;
         }
     }
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         int slot = 0;
         if (p >= 0) {
             const int h = pslot[i];
-            const int pos = atomicAdd(&hcur[h], 1);
+            const int pos = (int)(atomicAdd(&hcc[h], 0x10000u) >> 16);
             const float b = bary[(size_t)p * D1 + j];
             const float nv = (pre | post) ? norm[p] : 1.f;
             spairs[pos] = make_uint2((unsigned)lp, __float_as_uint(pre ? __fmul_rn(b, nv) : b));
@@ -242,9 +247,10 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     // (e + k) mod 8 whenever the list still has one - a vertex covers a blob of pixels, so all classes occur about equally.
     const int G = row_bytes / 16;
     for (int k = 0; k < spt; k++) {
-        const int c = hcnt[s0 + k];
+        const unsigned cc = hcc[s0 + k];
+        const int c = (int)(cc & 0xffffu);
         if (c > 0) {
-            const int key = hkeys[s0 + k], start = hcur[s0 + k] - c;
+            const int key = hkeys[s0 + k], start = (int)(cc >> 16) - c;
             for (int o = 0; o < c; o += TILE_SEG) {
                 const int len = min(TILE_SEG, c - o);
                 const int idx = binstart[len] + atomicAdd(&hist[len], 1);
@@ -261,25 +267,28 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     for (int idx = threadIdx.x; idx < tot.x; idx += 256) {
         const int m = segs[idx], len = m >> 16, start = m & 0xffff;
         const uint2* lst = spairs + start;
-        unsigned long long cls[2] = {~0ull, ~0ull};
+        unsigned long long c0 = ~0ull, c1 = ~0ull;  // two registers, never indexed dynamically (that would be local memory)
         for (int f = 0; f < len; f++) {
-            const unsigned long long c = (unsigned long long)((G * lst[f].x) & 7u);
-            cls[f >> 4] = (cls[f >> 4] & ~(0xFull << (4 * (f & 15)))) | (c << (4 * (f & 15)));
+            const int sh = 4 * (f & 15);
+            const unsigned long long keep = ~(0xFull << sh), val = (unsigned long long)((G * lst[f].x) & 7u) << sh;
+            if (f < 16) c0 = (c0 & keep) | val;
+            else c1 = (c1 & keep) | val;
         }
         for (int q = 0; q < len; q++) {
             const unsigned long long want = (unsigned long long)((unsigned)(G * (idx + q)) & 7u) * 0x1111111111111111ull;
-            int f = -1;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const unsigned long long x = cls[h] ^ want;  // zero nibble <=> unused pair of the wanted class
-                const unsigned long long z = (x - 0x1111111111111111ull) & ~x & 0x8888888888888888ull;
-                if (f < 0 && z) f = 16 * h + ((__ffsll((long long)z) - 1) >> 2);
-            }
-            if (f < 0) {  // the class is exhausted: any unused pair (bit 3 of its nibble is clear)
-                const unsigned long long u0 = ~cls[0] & 0x8888888888888888ull, u1 = ~cls[1] & 0x8888888888888888ull;
+            // zero nibble of c ^ want <=> unused pair of the wanted class
+            const unsigned long long x0 = c0 ^ want, x1 = c1 ^ want;
+            const unsigned long long z0 = (x0 - 0x1111111111111111ull) & ~x0 & 0x8888888888888888ull;
+            const unsigned long long z1 = (x1 - 0x1111111111111111ull) & ~x1 & 0x8888888888888888ull;
+            int f;
+            if (z0) f = (__ffsll((long long)z0) - 1) >> 2;
+            else if (z1) f = 16 + ((__ffsll((long long)z1) - 1) >> 2);
+            else {  // the class is exhausted: any unused pair (bit 3 of its nibble is clear)
+                const unsigned long long u0 = ~c0 & 0x8888888888888888ull, u1 = ~c1 & 0x8888888888888888ull;
                 f = u0 ? ((__ffsll((long long)u0) - 1) >> 2) : 16 + ((__ffsll((long long)u1) - 1) >> 2);
             }
-            cls[f >> 4] |= 0xFull << (4 * (f & 15));
+            if (f < 16) c0 |= 0xFull << (4 * f);
+            else c1 |= 0xFull << (4 * (f - 16));
             const uint2 v = lst[f];
             out.pairs[tb + start + q] = make_uint2(v.x * (unsigned)row_bytes, v.y);
         }
@@ -386,12 +395,17 @@ __device__ __forceinline__ void stage_rows(const FusedLat& L, size_t tb, int nro
 }
 
 // one thread = one splat segment, all channels in registers; pairs[].x = byte offset of the point's row in the Q tile
-template <int G>
+// REV: the threads take the segments in reverse order (thread TP-1 the first = longest one).  The segments of a lattice are
+// ordered longest first, so when the second lattice of a tile is walked in reverse, the threads that had the long
+// segments of the first lattice get the short ones of the second: the serial chain per thread is ~(longest + shortest)
+// instead of 2 x longest.  The bank-conflict ordering of the pairs (tile_csr_build_kernel) only needs the eight lanes of a
+// quarter-warp to hold eight consecutive segments, in either direction.
+template <int G, bool REV>
 __device__ __forceinline__ void gather_entries(const uint2* pr, const int2* meta, int cap, const int2* __restrict__ meta_g,
                                                int ne, float* __restrict__ vout, const float4* qtile) {
     constexpr int MP = 4 * G;
     const char* qbytes = reinterpret_cast<const char*>(qtile);
-    for (int e = threadIdx.x; e < ne; e += TILE_POINTS) {
+    for (int e = REV ? TILE_POINTS - 1 - (int)threadIdx.x : (int)threadIdx.x; e < ne; e += TILE_POINTS) {
         const int2 m = e < cap ? meta[e] : __ldg(meta_g + e);
         const uint2* pp = pr + (m.x & 0xffff);
         const int len = m.x >> 16;
@@ -592,8 +606,9 @@ __global__ void __launch_bounds__(TILE_POINTS, RSS_TILE_MINB)
     __syncthreads();  // the tile's marginals are complete
     mbar_wait(bar1, 0);
     // ---- phase 2: tile-local gather splat out of shared memory
-    gather_entries<G>(spairsA, metaA, capA, a.lat[0].ent_meta + tbA, neA, a.lat[0].vout, qtile);
-    if constexpr (D1B > 0) gather_entries<G>(spairsB, metaB, capB, a.lat[1].ent_meta + tbB, neB, a.lat[1].vout, qtile);
+    gather_entries<G, false>(spairsA, metaA, capA, a.lat[0].ent_meta + tbA, neA, a.lat[0].vout, qtile);
+    if constexpr (D1B > 0)
+        gather_entries<G, RSS_SPLAT_REV != 0>(spairsB, metaB, capB, a.lat[1].ent_meta + tbB, neB, a.lat[1].vout, qtile);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -822,12 +837,15 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
     const int grid = tm.ntiles, TP = TILE_POINTS;
     int HC = 1024;  // power of two with load factor <= 0.8 even when every pair of the tile hits a different vertex
     while (HC * 4 < TP * d1 * 5) HC *= 2;
-    const size_t tsm = (size_t)4 * HC * 4 + (size_t)TP * d1 * (2 + 8 + 4);
+    const size_t tsm = (size_t)HC * (4 + 4 + 2) + (size_t)TP * d1 * (2 + 8 + 4);
     const int ipre = pre ? 1 : 0, ipost = post ? 1 : 0;
 #define RSS_TCB(D)                                                                                                      \
     do {                                                                                                                \
-        if (c->smem_attr_done.insert((const void*)tile_csr_build_kernel<D>).second)  /* once per context (= per device) */ \
+        if (c->smem_attr_done.insert((const void*)tile_csr_build_kernel<D>).second) { /* once per context (= per device) */ \
             cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);     \
+            cudaFuncSetAttribute(tile_csr_build_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout,               \
+                                 cudaSharedmemCarveoutMaxShared);                                                       \
+        }                                                                                                               \
         RSS_LAUNCH(c, tile_csr_build_kernel<D>, grid, 256, tsm, st, offsets, bary, norm, ipre, ipost, slice_scale, tm,  \
                    row_bytes, HC, counts, out);                                                                         \
     } while (0)
