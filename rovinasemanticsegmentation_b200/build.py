@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librss.so")
-SOURCES = ["api.cu", "features.cu", "normals.cu", "forest.cu", "lattice.cu", "meanfield.cu", "crf.cu", "train.cu", "sort.cu"]
+SOURCES = ["api.cu", "features.cu", "normals.cu", "forest.cu", "lattice.cu", "meanfield.cu", "meanfield_shared.cu", "crf.cu", "train.cu", "sort.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]

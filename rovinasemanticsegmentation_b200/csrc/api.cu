@@ -152,6 +152,7 @@ static rss_status load_forest_bytes_impl(rss_ctx* ctx, const unsigned char* data
     std::vector<Node> nodes;
     std::vector<float> leaves;
     std::vector<int> tree_off(T + 1, 0);
+    size_t true_nodes = 0;  // without the alignment padding
     int L = -1, sumC = 0;
     int C[RSS_MAX_LAYERS] = {0};
     for (int t = 0; t < T; t++) {
@@ -164,7 +165,11 @@ static rss_status load_forest_bytes_impl(rss_ctx* ctx, const unsigned char* data
         if (!rd.raw(feat.data(), nb)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated splitFeatures");
         if (rd.i32() != n || !rd.raw(thr.data(), nb)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated thresholds");
         if (rd.i32() != n || !rd.raw(left.data(), nb)) return ctx->fail(RSS_ERR_MODEL, "forest: truncated leftChild");
+        // roots at ODD node indices: a libforest tree's sibling pairs start at odd local indices (root 0, children 1|2, 3|4,
+        // ...), so they then start at even global ones and the two 16-byte nodes share one 32-byte sector (features.cu)
+        if (nodes.size() % 2 == 0) nodes.push_back(Node{0, 0.f, 0, -1});
         const size_t base = nodes.size();
+        true_nodes += (size_t)n;
         tree_off[t] = (int)base;
         nodes.resize(base + n);
         for (int i = 0; i < n; i++) {
@@ -225,7 +230,7 @@ static rss_status load_forest_bytes_impl(rss_ctx* ctx, const unsigned char* data
             return ctx->fail(RSS_ERR_MODEL, "forest: split feature index exceeds the configured feature length");
     F.T = T; F.L = L; F.sumC = sumC;
     for (int k = 0; k < RSS_MAX_LAYERS; k++) F.C[k] = C[k];
-    F.total_nodes = (int)nodes.size();
+    F.total_nodes = (int)true_nodes;
     F.total_leaves = (int)(leaves.size() / (size_t)sumC);
     F.tree_off = tree_off;
     RSS_CU(ctx, F.nodes.reserve(nodes.size() * sizeof(Node)));

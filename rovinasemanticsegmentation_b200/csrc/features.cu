@@ -258,6 +258,11 @@ __device__ __forceinline__ int traverse_frame(const Node* __restrict__ tree, con
     float normal_feature = 0.f;
     Node nd = load_node_ro(tree);
     while (nd.left != 0) {
+        // both children are fetched BEFORE the feature value is known: the node load leaves the dependent chain (feature
+        // offset -> taps -> four pixels -> compare -> node).  Siblings are adjacent, and the loader places every root at an
+        // odd node index, so the pair (left, left + 1) - left is odd inside a libforest tree - is one aligned 32-byte sector.
+        const int4* ch = reinterpret_cast<const int4*>(tree + nd.left);
+        const int4 cl = __ldg(ch), cr = __ldg(ch + 1);
         float v;
         const int f = nd.feat;
         if (f < F.ncolor) {
@@ -281,7 +286,8 @@ __device__ __forceinline__ int traverse_frame(const Node* __restrict__ tree, con
             }
             v = normal_feature;
         }
-        nd = load_node_ro(tree + (v < nd.thr ? nd.left : nd.left + 1));
+        const int4 nx = v < nd.thr ? cl : cr;
+        nd.feat = nx.x; nd.thr = __int_as_float(nx.y); nd.left = nx.z; nd.leaf = nx.w;
     }
     return nd.leaf;
 }

@@ -118,6 +118,20 @@ struct TileCsrOut {
     uint16_t* pt_slot;
 };
 
+#ifndef RSS_TILE_SEG
+#define RSS_TILE_SEG 32  // pairs per splat segment (one thread walks one segment serially)
+#endif
+#ifndef RSS_SPLAT_REV
+#define RSS_SPLAT_REV 1  // the splat walks the second lattice's segments in reverse thread order (gather_entries)
+#endif
+#ifndef RSS_TILE_MINB
+#define RSS_TILE_MINB 3  // resident CTAs per SM the "alone" build of the point kernel is compiled for (register budget)
+#endif
+constexpr int TILE_SEG = RSS_TILE_SEG;
+// the 64-register build of the point kernel (meanfield_shared.cu), for SMs shared with the cooperative blur
+cudaError_t launch_meanfield_fused_shared(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary,
+                                          float* Q, uint8_t* labels, const TileMap& tm, int G, const FusedLayers& ls, int mode);
+
 bool fused_group_supported(int G);  // channel-group counts the point kernel is instantiated for
 bool fused_signature_supported(int G, int d1a, int d1b);
 TileMap fused_tile_map(int N, int W, int H);  // W = H = 0 for point sets without an image grid

@@ -30,35 +30,62 @@ __device__ __forceinline__ bool depth_change(float z, float zn) {
     return fabsf(__fsub_rn(z, zn)) > thr || !isfinite(z) || !isfinite(zn);
 }
 
+// One CTA per 32 x 32 pixel tile.  The cloud tile (+ a one-pixel halo) is staged in shared memory with coalesced loads; the
+// gradient planes and finite flags live in the SKEWED layout the wavefront kernel reads, where consecutive rows of one
+// anti-diagonal are contiguous - so a warp walks an anti-diagonal of the tile (lane = row) and stores 128 contiguous bytes
+// per plane (a thread-per-pixel, row-major kernel scatters every 4-byte store into its own 32-byte sector: 4.5e6 L2
+// sectors for 8 MB of output).  Shared-memory reads at lane stride 33 float4 are conflict-free.  The row-major initial
+// distance map is written in a second, row-major sweep over the same tile.
+constexpr int GM_T = 32;
 __global__ void __launch_bounds__(256) gradient_mask_kernel(const float4* __restrict__ xyz, int W, int H,
                                                             float* __restrict__ grad, uint8_t* __restrict__ fin,
                                                             float* __restrict__ dist_init) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= W) return;
-    const size_t i = (size_t)r * W + c;
-    const size_t SP = skew_elems(W, H), si = skew_index(r, c, skew_pitch(H));
-    float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f};
-    if (r >= 1 && r < H - 1 && c >= 1 && c < W - 1) {
-        const float4 L = xyz[i - 1], Rr = xyz[i + 1], U = xyz[i - W], Dn = xyz[i + W];
-        gx[0] = __fsub_rn(Rr.x, L.x); gx[1] = __fsub_rn(Rr.y, L.y); gx[2] = __fsub_rn(Rr.z, L.z);
-        gy[0] = __fsub_rn(Dn.x, U.x); gy[1] = __fsub_rn(Dn.y, U.y); gy[2] = __fsub_rn(Dn.z, U.z);
+    __shared__ float4 tile[(GM_T + 2) * (GM_T + 2)];
+    constexpr int TPITCH = GM_T + 2;
+    const int c0 = blockIdx.x * GM_T, r0 = blockIdx.y * GM_T;
+    for (int k = threadIdx.x; k < TPITCH * TPITCH; k += 256) {
+        const int rr = k / TPITCH, cc = k - rr * TPITCH;
+        const int r = r0 - 1 + rr, c = c0 - 1 + cc;
+        tile[k] = (r >= 0 && r < H && c >= 0 && c < W) ? xyz[(size_t)r * W + c] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const bool fx = isfinite(__fadd_rn(__fadd_rn(gx[0], gx[1]), gx[2]));
-    const bool fy = isfinite(__fadd_rn(__fadd_rn(gy[0], gy[1]), gy[2]));
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t SP = skew_elems(W, H);
+    const int HP = skew_pitch(H);
+    for (int dl = warp; dl < 2 * GM_T - 1; dl += 8) {  // anti-diagonal dl of the tile, lane = local row
+        const int rl = lane, cl = dl - rl;
+        const int r = r0 + rl, c = c0 + cl;
+        if (cl < 0 || cl >= GM_T || r >= H || c >= W) continue;
+        const float4* t = tile + (rl + 1) * TPITCH + cl + 1;
+        float gx[3] = {0.f, 0.f, 0.f}, gy[3] = {0.f, 0.f, 0.f};
+        if (r >= 1 && r < H - 1 && c >= 1 && c < W - 1) {
+            const float4 L = t[-1], Rr = t[1], U = t[-TPITCH], Dn = t[TPITCH];
+            gx[0] = __fsub_rn(Rr.x, L.x); gx[1] = __fsub_rn(Rr.y, L.y); gx[2] = __fsub_rn(Rr.z, L.z);
+            gy[0] = __fsub_rn(Dn.x, U.x); gy[1] = __fsub_rn(Dn.y, U.y); gy[2] = __fsub_rn(Dn.z, U.z);
+        }
+        const bool fx = isfinite(__fadd_rn(__fadd_rn(gx[0], gx[1]), gx[2]));
+        const bool fy = isfinite(__fadd_rn(__fadd_rn(gy[0], gy[1]), gy[2]));
+        const size_t si = skew_index(r, c, HP);
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        grad[(size_t)k * SP + si] = fx ? gx[k] : 0.f;
-        grad[(size_t)(3 + k) * SP + si] = fy ? gy[k] : 0.f;
+        for (int k = 0; k < 3; k++) {
+            grad[(size_t)k * SP + si] = fx ? gx[k] : 0.f;
+            grad[(size_t)(3 + k) * SP + si] = fy ? gy[k] : 0.f;
+        }
+        fin[si] = fx ? 1 : 0;
+        fin[SP + si] = fy ? 1 : 0;
     }
-    fin[si] = fx ? 1 : 0;
-    fin[SP + si] = fy ? 1 : 0;
     // depth-change map, gathered: a pixel is cleared by its own tests and by its left / upper neighbour's
-    const float z = xyz[i].z;
-    bool cleared = false;
-    if (r < H - 1 && c < W - 1) cleared = depth_change(z, xyz[i + 1].z) || depth_change(z, xyz[i + W].z);
-    if (!cleared && c >= 1 && r < H - 1) cleared = depth_change(xyz[i - 1].z, z);
-    if (!cleared && r >= 1 && c < W - 1) cleared = depth_change(xyz[i - W].z, z);
-    dist_init[i] = cleared ? 0.0f : (float)(W + H);
+    for (int rl = warp; rl < GM_T; rl += 8) {
+        const int cl = lane, r = r0 + rl, c = c0 + cl;
+        if (r >= H || c >= W) continue;
+        const float4* t = tile + (rl + 1) * TPITCH + cl + 1;
+        const float z = t[0].z;
+        bool cleared = false;
+        if (r < H - 1 && c < W - 1) cleared = depth_change(z, t[1].z) || depth_change(z, t[TPITCH].z);
+        if (!cleared && c >= 1 && r < H - 1) cleared = depth_change(t[-1].z, z);
+        if (!cleared && r >= 1 && c < W - 1) cleared = depth_change(t[-TPITCH].z, z);
+        dist_init[(size_t)r * W + c] = cleared ? 0.0f : (float)(W + H);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -237,7 +264,7 @@ __global__ void __launch_bounds__(MAXT) integral_wavefront_kernel(const float* _
 
 void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int W, int H, float* dist_a,
                             float* dist_b, double* integ, int* integ_cnt, float* grad, uint8_t* fin) {
-    dim3 grid(rss_div_up(W, 256), H);
+    dim3 grid(rss_div_up(W, GM_T), rss_div_up(H, GM_T));
     RSS_LAUNCH(c, gradient_mask_kernel, grid, 256, 0, st, xyz, W, H, grad, fin, dist_b);
     // distance map: init (dist_b) -> forward (dist_a) -> backward (dist_b)
     const int band = 8;

@@ -7,7 +7,7 @@ i=0
 for defs in "$@"; do
   echo "=== [$i] $defs"
   RSS_NVCC_DEFS="$defs" python -m rovinasemanticsegmentation_b200.build --force > /dev/null 2>&1 || echo BUILD FAILED
-  if [ $i -eq 0 ]; then timeout 600 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; tail -2 $OUT/pytest_$TAG.log; fi
+  if [ $i -eq 0 ] && [ -z "$NOTEST" ]; then timeout 600 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; tail -2 $OUT/pytest_$TAG.log; fi
   timeout 300 python bench.py --steps 16 --warmup 3 --quick --repeats 3 > $OUT/bench_${TAG}_$i.json 2> $OUT/bench_${TAG}_$i.err; echo "bench rc=$?"
   python profiles/show_bench.py $OUT/bench_${TAG}_$i.json 2>/dev/null | sed -n 2,20p | cut -c1-130
   i=$((i+1))
