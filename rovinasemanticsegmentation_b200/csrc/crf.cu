@@ -475,6 +475,7 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
     const int d1a = Ls[0]->d + 1, d1b = K > 1 ? Ls[1]->d + 1 : 0;
     int phases_of[FUSED_MAX_LAT] = {0};
     const int blur_phases = blur_multi_plan(ba, G, phases_of);
+    const BlurShape blur_shape = blur_multi_shape(ctx);  // once per inference: the barrier targets depend on the grid
     const float* U = crf->unary.as<float>();  // (replaced by the sorted copy for incoherent point sets, below)
     float* Q = crf->Q.as<float>();
     Lattice& L0 = *Ls[0];
@@ -495,8 +496,8 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
         for (int k = 0; k < K; k++) {
             ba.ping[k] = tgt[k]->as<float4>(); ba.pong[k] = spare[k]->as<float4>(); ba.zero[k] = res[k]->as<float4>();
         }
-        RSS_CU(ctx, launch_blur_multi(ctx, s0, ba, G, L0.counts.as<unsigned int>() + 8, L0.barrier_base));
-        L0.barrier_base += (unsigned int)(blur_phases - 1) * (unsigned int)blur_multi_grid(ctx);
+        RSS_CU(ctx, launch_blur_multi(ctx, s0, ba, G, L0.counts.as<unsigned int>() + 8, L0.barrier_base, blur_shape));
+        L0.barrier_base += (unsigned int)(blur_phases - 1) * (unsigned int)blur_shape.grid;
         for (int k = 0; k < K; k++) {
             DevBuf* X = (phases_of[k] % 2 == 0) ? tgt[k] : spare[k];  // blurred result
             DevBuf* Y = (phases_of[k] % 2 == 0) ? spare[k] : tgt[k];
@@ -506,7 +507,10 @@ static rss_status crf_run_fused(rss_crf* crf, int iters, const int* unknown, uin
             fa.lat[k].vout = tgt[k]->as<float>();
         }
         const bool last = it == iters - 1;
-        RSS_CU(ctx, launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, Q, last ? labels_dev : nullptr, tm, G, ls, last ? (1 | 4) : (1 | 2)));
+        // the last pass writes the marginals unless the caller only wants the label maps (rss_segment_keyframe with Q = NULL)
+        float* Qlast = (crf->skip_q_store && labels_dev) ? nullptr : Q;
+        RSS_CU(ctx, launch_meanfield_fused(ctx, s0, fa, d1a, d1b, U, last ? Qlast : Q, last ? labels_dev : nullptr, tm, G, ls,
+                                           last ? (1 | 4) : (1 | 2)));
     }
     // restore the two-table convention of the generic path: val_a = the all-zero table, splat_target = 0
     for (int k = 0; k < K; k++) {
@@ -1330,6 +1334,7 @@ struct KeyframeGraph {
     rss_keyframe_params prm{};
     uint64_t launches = 0;       // kernel launches inside the graph
     bool shared_gpu = false;     // captured while other contexts were alive on the device (smaller blur CTAs)
+    bool want_q = false;         // captured with the marginals stored by the last point kernel
     // stability detection: the previous eager call's signature and the allocation counter after it
     int prev_W = 0, prev_H = 0;
     rss_keyframe_params prev_prm{};
@@ -1449,12 +1454,13 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
     if (st != RSS_OK) return st;
     const bool want_graph = ctx->graph_enabled && !ctx->profile && !G.broken && !getenv("RSS_NO_GRAPH");
     bool staged = false;  // per-stage events recorded (eager runs only)
+    crf->skip_q_store = Qout == nullptr;
     for (int attempt = 0;; attempt++) {
         const uint64_t gen = device_alloc_events().load();
         bool ran = false;
         const bool shared_gpu = live_contexts(ctx->device).load() > 1;
         if (want_graph && attempt == 0 && G.exec && G.W == W && G.H == H && same_params(G.prm, *prm) && G.alloc_gen == gen &&
-            G.shared_gpu == shared_gpu) {
+            G.shared_gpu == shared_gpu && G.want_q == (Qout != nullptr)) {
             // steady state: replay.  The frame-state flags the eager path maintains:
             ctx->fr.have_cloud = ctx->cfg.use_height || ctx->cfg.use_normal;
             ctx->fr.have_lab = ctx->cfg.use_color;
@@ -1483,7 +1489,7 @@ extern "C" rss_status rss_segment_keyframe(rss_ctx* ctx, const uint8_t* rgb, con
                 e = cudaErrorUnknown;
             if (graph) cudaGraphDestroy(graph);
             if (e == cudaSuccess) {
-                G.W = W; G.H = H; G.prm = *prm; G.alloc_gen = gen; G.shared_gpu = shared_gpu;
+                G.W = W; G.H = H; G.prm = *prm; G.alloc_gen = gen; G.shared_gpu = shared_gpu; G.want_q = Qout != nullptr;
                 G.launches = ctx->launches - l0;
                 RSS_CU(ctx, cudaGraphLaunch(G.exec, ctx->s0));
                 ran = true;

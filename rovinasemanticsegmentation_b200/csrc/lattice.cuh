@@ -89,6 +89,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 
 struct rss_crf {
     rss_ctx* ctx = nullptr;
+    bool skip_q_store = false;     // fused path: the last point kernel writes only the label maps (keyframes without Q output)
     int N = 0, n_layers = 0;
     int M[RSS_MAX_LAYERS] = {0};
     // Device channel layout: layer l owns channels [moff[l], moff[l] + M[l]) of a point's row; every layer starts at a

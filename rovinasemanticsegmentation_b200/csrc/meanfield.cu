@@ -37,6 +37,9 @@
 #ifndef RSS_BLUR_SHARED_T
 #define RSS_BLUR_SHARED_T (RSS_BLUR_MAXT / 2)  // CTA size of the cooperative blur while several keyframes share the GPU
 #endif
+#ifndef RSS_BLUR_SHARED_GRID_DIV
+#define RSS_BLUR_SHARED_GRID_DIV 1  // the shared-GPU blur runs on sm_count / this many SMs
+#endif
 #ifndef RSS_BLUR_U
 #define RSS_BLUR_U 2      // independent (vertex, channel group) items a blur thread keeps in flight
 #endif
@@ -507,7 +510,20 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
 #undef RSS_TCB
 }
 
-int blur_multi_grid(const rss_ctx* c) { return c->sm_count; }  // one CTA per SM
+// Launch shape of the cooperative blur.  Alone on the GPU: one CTA of RSS_BLUR_MAXT threads per SM.  Sharing the GPU with
+// other keyframes in flight: RSS_BLUR_SHARED_T threads per CTA on sm_count / RSS_BLUR_SHARED_GRID_DIV SMs - the blur is
+// resident most of the time then, and what it costs the other keyframes' kernels is the CTA slots its registers block.
+BlurShape blur_multi_shape(const rss_ctx* c) {
+    BlurShape s;
+    if (live_contexts(c->device).load() > 1) {
+        s.grid = std::max(1, c->sm_count / RSS_BLUR_SHARED_GRID_DIV);
+        s.block = RSS_BLUR_SHARED_T;
+    } else {
+        s.grid = c->sm_count;
+        s.block = RSS_BLUR_MAXT;
+    }
+    return s;
+}
 // Splits the d+1 axes of every lattice into phases of up to `RSS_BLUR_FUSE` fused axes (fewer grid barriers, more L2
 // reads): 3 axes per phase for tables of at most RSS_BLUR_FUSE3_ITEMS float4 items, 2 up to RSS_BLUR_FUSE2_ITEMS, else 1.
 // Returns the number of phases of the launch; phases_of[k] = phases lattice k takes part in (the blurred table is `ping`
@@ -530,10 +546,9 @@ int blur_multi_plan(BlurMultiArgs& a, int G, int* phases_of) {
     }
     return a.phases;
 }
-cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base) {
-    // alone on the GPU: 512 threads per SM (the phases are L2-latency/throughput-bound); sharing it with other keyframes in
-    // flight: 256, which leaves room for their kernels while this one waits at its barriers
-    const int grid = blur_multi_grid(c), block = live_contexts(c->device).load() > 1 ? RSS_BLUR_SHARED_T : RSS_BLUR_MAXT;
+cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base,
+                              const BlurShape& shape) {
+    const int grid = shape.grid, block = shape.block;
     void* args[] = {&a, &G, &barrier, &barrier_base};
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (c->profile) { ea = c->prof_event(); eb = c->prof_event(); cudaEventRecord(ea, st); }

@@ -141,9 +141,11 @@ cudaError_t launch_meanfield_fused(rss_ctx* c, cudaStream_t st, const FusedArgs&
 void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, const float* norm, bool pre,
                            bool post, float slice_scale, const TileMap& tm, int d1, int row_bytes, const uint32_t* counts,
                            const TileCsrOut& out);
-int blur_multi_grid(const rss_ctx* c);  // CTAs of the cooperative blur (one barrier arrival each)
+struct BlurShape { int grid, block; };  // CTAs (one barrier arrival each) and threads per CTA of the cooperative blur
+BlurShape blur_multi_shape(const rss_ctx* c);  // read ONCE per inference: the barrier targets depend on the grid
 int blur_multi_plan(BlurMultiArgs& a, int G, int* phases_of);  // fills a.phases / a.fuse; phases per lattice -> phases_of
-cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base);
+cudaError_t launch_blur_multi(rss_ctx* c, cudaStream_t st, BlurMultiArgs a, int G, unsigned int* barrier, unsigned int barrier_base,
+                              const BlurShape& shape);
 void launch_splat_ones_runs(rss_ctx* c, cudaStream_t st, const int* offsets, const float* bary, int N, int d1,
                             const uint32_t* counts, float* values);
 

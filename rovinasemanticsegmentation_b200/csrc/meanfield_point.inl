@@ -307,7 +307,7 @@ __global__ void RSS_POINT_BOUNDS
             const float4 v = make_float4(t[4 * g] * gs[g], t[4 * g + 1] * gs[g], t[4 * g + 2] * gs[g], t[4 * g + 3] * gs[g]);
             t[4 * g] = v.x; t[4 * g + 1] = v.y; t[4 * g + 2] = v.z; t[4 * g + 3] = v.w;
             if (do_splat) qtile[lp * G + g] = v;
-            if (store_q) reinterpret_cast<float4*>(Q + (size_t)p * MP)[g] = v;
+            if (store_q && Q) reinterpret_cast<float4*>(Q + (size_t)p * MP)[g] = v;
         }
         if (labels) {
             // gated argmax (segmenter.cpp:645-657) / plain argmax (densecrf.cpp:200-208); strict '>' keeps the first maximum
