@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
                                                              const float* __restrict__ norm, int pre, int post,
                                                              float slice_scale, const TileMap tm, int row_bytes, int HC,
                                                              const uint32_t* __restrict__ counts, const TileCsrOut out) {
-    __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1];
+    __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1], cumstart[TILE_SEG + 1];
     extern __shared__ int tile_smem[];  // above the 48 KB static limit for large d
     int* hkeys = tile_smem;  // HC slots (power of two, > pairs per tile)
     // per slot: pair count in the low half, fill cursor of the slot's pair list in the high half (both <= TP * D1 <
@@ -212,8 +212,12 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     int3 tot;
     int3 pre3 = block_excl_scan3(nseg, ncnt, nvert, &tot);  // ends with a barrier: hist is complete
     if (threadIdx.x == 0) {
-        int pos = 0;
-        for (int len = TILE_SEG; len >= 1; len--) { binstart[len] = pos; pos += hist[len]; hist[len] = 0; }
+        int pos = 0, cpos = 0;  // segments / pairs before the first segment of this length, in the sorted segment order
+        for (int len = TILE_SEG; len >= 1; len--) {
+            binstart[len] = pos; cumstart[len] = cpos;
+            pos += hist[len]; cpos += hist[len] * len;
+            hist[len] = 0;
+        }
         out.tile_info[tile] = make_int2(tot.x, tot.z);
     }
     __syncthreads();
@@ -260,17 +264,28 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
                 const int len = min(TILE_SEG, c - o);
                 const int idx = binstart[len] + atomicAdd(&hist[len], 1);
                 const int m = (start + o) | (len << 16);
-                out.ent_meta[tb + idx] = make_int2(m, key);
+                reinterpret_cast<int*>(out.ent_meta + tb + idx)[1] = key;  // .x follows in the ordering loop
                 segs[idx] = m;
             }
         }
     }
     __syncthreads();
     // one segment per thread: the classes of its <= 32 pairs packed as nibbles in two 64-bit registers (a used pair
-    // becomes 0xF, which matches no class), so "the first unused pair of class c" is a zero-nibble search, not a scan
+    // becomes 0xF, which matches no class), so "the first unused pair of class c" is a zero-nibble search, not a scan.
+    // STORAGE: the 32 consecutive segments a warp of the gather walks form a group, stored COLUMN-major - first pair 0 of
+    // every segment of the group, then pair 1 of every segment that has one, ... (segments are ordered longest first, so
+    // the segments that still have a pair q are a prefix of the group and a column is compact).  At step q the lanes of a
+    // warp then read consecutive 8-byte pairs: no bank conflicts (row-major lists with arbitrary starts: 3.6 wavefronts
+    // per 8-byte read).  ent_meta.x = first pair of the segment's GROUP | length << 16.
     static_assert(TILE_SEG <= 32, "the segment ordering packs 32 classes into 128 bits");
-    for (int idx = threadIdx.x; idx < tot.x; idx += 256) {
-        const int m = segs[idx], len = m >> 16, start = m & 0xffff;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = threadIdx.x - lane; i0 < tot.x; i0 += 256) {
+        const int idx = i0 + lane;
+        int len = 0, start = 0;
+        if (idx < tot.x) { const int m = segs[idx]; len = m >> 16; start = m & 0xffff; }
+        const int len0 = __shfl_sync(0xffffffffu, len, 0);  // the group's longest segment
+        int col = cumstart[len0] + (i0 - binstart[len0]) * len0;  // pairs before the group
+        if (idx < tot.x) reinterpret_cast<int*>(out.ent_meta + tb + idx)[0] = col | (len << 16);
         const uint2* lst = spairs + start;
         unsigned long long c0 = ~0ull, c1 = ~0ull;  // two registers, never indexed dynamically (that would be local memory)
         for (int f = 0; f < len; f++) {
@@ -279,23 +294,28 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
             if (f < 16) c0 = (c0 & keep) | val;
             else c1 = (c1 & keep) | val;
         }
-        for (int q = 0; q < len; q++) {
-            const unsigned long long want = (unsigned long long)((unsigned)(G * (idx + q)) & 7u) * 0x1111111111111111ull;
-            // zero nibble of c ^ want <=> unused pair of the wanted class
-            const unsigned long long x0 = c0 ^ want, x1 = c1 ^ want;
-            const unsigned long long z0 = (x0 - 0x1111111111111111ull) & ~x0 & 0x8888888888888888ull;
-            const unsigned long long z1 = (x1 - 0x1111111111111111ull) & ~x1 & 0x8888888888888888ull;
-            int f;
-            if (z0) f = (__ffsll((long long)z0) - 1) >> 2;
-            else if (z1) f = 16 + ((__ffsll((long long)z1) - 1) >> 2);
-            else {  // the class is exhausted: any unused pair (bit 3 of its nibble is clear)
-                const unsigned long long u0 = ~c0 & 0x8888888888888888ull, u1 = ~c1 & 0x8888888888888888ull;
-                f = u0 ? ((__ffsll((long long)u0) - 1) >> 2) : 16 + ((__ffsll((long long)u1) - 1) >> 2);
+        for (int q = 0; q < len0; q++) {
+            const bool act = q < len;
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const unsigned long long want = (unsigned long long)((unsigned)(G * (idx + q)) & 7u) * 0x1111111111111111ull;
+                // zero nibble of c ^ want <=> unused pair of the wanted class
+                const unsigned long long x0 = c0 ^ want, x1 = c1 ^ want;
+                const unsigned long long z0 = (x0 - 0x1111111111111111ull) & ~x0 & 0x8888888888888888ull;
+                const unsigned long long z1 = (x1 - 0x1111111111111111ull) & ~x1 & 0x8888888888888888ull;
+                int f;
+                if (z0) f = (__ffsll((long long)z0) - 1) >> 2;
+                else if (z1) f = 16 + ((__ffsll((long long)z1) - 1) >> 2);
+                else {  // the class is exhausted: any unused pair (bit 3 of its nibble is clear)
+                    const unsigned long long u0 = ~c0 & 0x8888888888888888ull, u1 = ~c1 & 0x8888888888888888ull;
+                    f = u0 ? ((__ffsll((long long)u0) - 1) >> 2) : 16 + ((__ffsll((long long)u1) - 1) >> 2);
+                }
+                if (f < 16) c0 |= 0xFull << (4 * f);
+                else c1 |= 0xFull << (4 * (f - 16));
+                const uint2 v = lst[f];
+                out.pairs[tb + col + lane] = make_uint2(v.x * (unsigned)row_bytes, v.y);
             }
-            if (f < 16) c0 |= 0xFull << (4 * f);
-            else c1 |= 0xFull << (4 * (f - 16));
-            const uint2 v = lst[f];
-            out.pairs[tb + start + q] = make_uint2(v.x * (unsigned)row_bytes, v.y);
+            col += __popc(bal);
         }
     }
 }
@@ -529,20 +549,27 @@ BlurShape blur_multi_shape(const rss_ctx* c) {
 // Returns the number of phases of the launch; phases_of[k] = phases lattice k takes part in (the blurred table is `ping`
 // when that is even, else `pong`).
 int blur_multi_plan(BlurMultiArgs& a, int G, int* phases_of) {
+    // phases of the launch = the most any lattice needs at its own fusion limit ...
+    int fmax[FUSED_MAX_LAT] = {0};
     a.phases = 0;
+    for (int k = 0; k < a.K; k++) {
+        const size_t items = (size_t)a.vcap[k] * G;
+        fmax[k] = std::min(RSS_BLUR_FUSE, items <= RSS_BLUR_FUSE3_ITEMS ? 3 : (items <= RSS_BLUR_FUSE2_ITEMS ? 2 : 1));
+        a.phases = std::max(a.phases, (a.d1[k] + fmax[k] - 1) / fmax[k]);
+    }
+    // ... and every lattice spreads its axes over ALL of them, as evenly as possible with the larger chunks first: a lattice
+    // with fewer axes then fuses fewer per phase (4 axes over 3 phases: 2 + 1 + 1 instead of 2 + 2 + idle), which reads
+    // 3^F rows per item less often - the phases are L2-throughput-bound - and evens the phases out.
     for (int k = 0; k < FUSED_MAX_LAT; k++) {
         for (int p = 0; p < BLUR_MAX_PHASES; p++) a.fuse[k][p] = 0;
         if (k >= a.K) continue;
-        const size_t items = (size_t)a.vcap[k] * G;
-        const int fmax = std::min(RSS_BLUR_FUSE, items <= RSS_BLUR_FUSE3_ITEMS ? 3 : (items <= RSS_BLUR_FUSE2_ITEMS ? 2 : 1));
-        const int np = (a.d1[k] + fmax - 1) / fmax;
-        for (int p = 0, left = a.d1[k]; p < np; p++) {  // as even as possible, larger chunks first
+        const int np = std::min(a.phases, a.d1[k]);
+        for (int p = 0, left = a.d1[k]; p < np; p++) {
             const int f = (left + (np - p) - 1) / (np - p);
             a.fuse[k][p] = f;
             left -= f;
         }
         phases_of[k] = np;
-        a.phases = std::max(a.phases, np);
     }
     return a.phases;
 }

@@ -115,52 +115,56 @@ __device__ __forceinline__ void stage_rows(const FusedLat& L, size_t tb, int nro
 }
 
 // one thread = one splat segment, all channels in registers; pairs[].x = byte offset of the point's row in the Q tile
-// REV: the threads take the segments in reverse order (thread TP-1 the first = longest one).  The segments of a lattice are
-// ordered longest first, so when the second lattice of a tile is walked in reverse, the threads that had the long
-// segments of the first lattice get the short ones of the second: the serial chain per thread is ~(longest + shortest)
-// instead of 2 x longest.  The bank-conflict ordering of the pairs (tile_csr_build_kernel) only needs the eight lanes of a
-// quarter-warp to hold eight consecutive segments, in either direction.
+// A warp walks a GROUP of 32 consecutive segments, lane <-> segment; the group's pairs are stored column-major
+// (tile_csr_build_kernel): at step k the lanes that still have a pair - a prefix of the group, the segments are ordered
+// longest first - read consecutive 8-byte pairs.  The column starts follow from ballots, no per-column metadata.
+// REV: the lanes AND the warps take the segments in reverse order (thread TP-1 the first = longest one).  When the second
+// lattice of a tile is walked in reverse, the threads that had the long segments of the first lattice get the short ones
+// of the second: the serial chain per thread is ~(longest + shortest) instead of 2 x longest.  The bank-conflict ordering
+// of the pairs only needs the eight lanes of a quarter-warp to hold eight consecutive segments, in either direction.
 template <int G, bool REV>
 __device__ __forceinline__ void gather_entries(const uint2* pr, const int2* meta, int cap, const int2* __restrict__ meta_g,
                                                int ne, float* __restrict__ vout, const float4* qtile) {
     constexpr int MP = 4 * G;
     const char* qbytes = reinterpret_cast<const char*>(qtile);
-    for (int e = REV ? TILE_POINTS - 1 - (int)threadIdx.x : (int)threadIdx.x; e < ne; e += TILE_POINTS) {
-        const int2 m = e < cap ? meta[e] : __ldg(meta_g + e);
-        const uint2* pp = pr + (m.x & 0xffff);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int li = REV ? 31 - lane : lane;  // position of this lane's segment in its group
+    for (int e0 = 32 * (REV ? TILE_POINTS / 32 - 1 - w : w); e0 < ne; e0 += TILE_POINTS) {
+        const int e = e0 + li;
+        int2 m = make_int2(0, 0);
+        if (e < ne) m = e < cap ? meta[e] : __ldg(meta_g + e);
         const int len = m.x >> 16;
+        const int2 m0 = make_int2(__shfl_sync(0xffffffffu, m.x, REV ? 31 : 0), 0);  // the group's first (longest) segment
+        const int len0 = m0.x >> 16;
+        const uint2* col = pr + (m0.x & 0xffff) + li;
         float4 acc[G];
 #pragma unroll
         for (int g = 0; g < G; g++) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int k = 0;
-        for (; k + 2 <= len; k += 2) {  // two pairs per trip: the second pair's loads overlap the first pair's multiply-adds
-            const uint2 p0 = pp[k], p1 = pp[k + 1];
-            const float w0 = __uint_as_float(p0.y), w1 = __uint_as_float(p1.y);
-            const float4* q0 = reinterpret_cast<const float4*>(qbytes + p0.x);
-            const float4* q1 = reinterpret_cast<const float4*>(qbytes + p1.x);
+        for (int k = 0; k < len0; k += 2) {  // two pairs per trip: the second pair's loads overlap the first pair's multiply-adds
+            const bool a0 = k < len, a1 = k + 1 < len;
+            const int n0 = __popc(__ballot_sync(0xffffffffu, a0)), n1 = __popc(__ballot_sync(0xffffffffu, a1));
+            if (a0) {
+                const uint2 p0 = col[0];
+                const uint2 p1 = a1 ? col[n0] : make_uint2(p0.x, 0u);  // no second pair: weight 0 on the same row
+                const float w0 = __uint_as_float(p0.y), w1 = __uint_as_float(p1.y);
+                const float4* q0 = reinterpret_cast<const float4*>(qbytes + p0.x);
+                const float4* q1 = reinterpret_cast<const float4*>(qbytes + p1.x);
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const float4 a = q0[g], b = q1[g];
-                acc[g].x = fmaf(w0, a.x, acc[g].x); acc[g].y = fmaf(w0, a.y, acc[g].y);
-                acc[g].z = fmaf(w0, a.z, acc[g].z); acc[g].w = fmaf(w0, a.w, acc[g].w);
-                acc[g].x = fmaf(w1, b.x, acc[g].x); acc[g].y = fmaf(w1, b.y, acc[g].y);
-                acc[g].z = fmaf(w1, b.z, acc[g].z); acc[g].w = fmaf(w1, b.w, acc[g].w);
+                for (int g = 0; g < G; g++) {
+                    const float4 a = q0[g], b = q1[g];
+                    acc[g].x = fmaf(w0, a.x, acc[g].x); acc[g].y = fmaf(w0, a.y, acc[g].y);
+                    acc[g].z = fmaf(w0, a.z, acc[g].z); acc[g].w = fmaf(w0, a.w, acc[g].w);
+                    acc[g].x = fmaf(w1, b.x, acc[g].x); acc[g].y = fmaf(w1, b.y, acc[g].y);
+                    acc[g].z = fmaf(w1, b.z, acc[g].z); acc[g].w = fmaf(w1, b.w, acc[g].w);
+                }
             }
+            col += n0 + n1;
         }
-        if (k < len) {
-            const uint2 p0 = pp[k];
-            const float w0 = __uint_as_float(p0.y);
-            const float4* q0 = reinterpret_cast<const float4*>(qbytes + p0.x);
+        if (len > 0) {
+            float* dst = vout + (size_t)m.y * MP;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const float4 a = q0[g];
-                acc[g].x = fmaf(w0, a.x, acc[g].x); acc[g].y = fmaf(w0, a.y, acc[g].y);
-                acc[g].z = fmaf(w0, a.z, acc[g].z); acc[g].w = fmaf(w0, a.w, acc[g].w);
-            }
+            for (int g = 0; g < G; g++) red_add_v4(dst + 4 * g, acc[g]);
         }
-        float* dst = vout + (size_t)m.y * MP;
-#pragma unroll
-        for (int g = 0; g < G; g++) red_add_v4(dst + 4 * g, acc[g]);
     }
 }
 
