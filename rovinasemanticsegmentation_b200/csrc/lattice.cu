@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
                                                             int* __restrict__ offsets, float* __restrict__ bary_out,
                                                             uint32_t* __restrict__ first_ref,
                                                             uint32_t* __restrict__ counts) {
+    __shared__ int s_off[256 * (D + 1)];
+    __shared__ float s_bary[256 * (D + 1)];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // no early exit: the lanes of a warp agree on duplicate vertices below (full-mask match / shuffle)
     const bool live = i < Next && !*reinterpret_cast<volatile uint32_t*>(counts + 1);  // overflow: the build is void anyway
@@ -192,9 +194,22 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
             else atomicMin(first_ref + slot, (uint32_t)i * (D + 1) + rem);  // first (point, corner) pair that touches the vertex
         }
         slot = __shfl_sync(0xffffffffu, slot, leader);
-        if (live) {
-            offsets[(size_t)i * (D + 1) + rem] = slot;
-            bary_out[(size_t)i * (D + 1) + rem] = bary[rem];
+        // staged in shared memory and written out below: a thread's D+1 values are 4 (D+1) bytes apart from its neighbour's,
+        // so storing them one corner at a time scatters every 4-byte store into its own sector (9e6 L2 sectors for D = 5)
+        s_off[threadIdx.x * (D + 1) + rem] = slot;
+        s_bary[threadIdx.x * (D + 1) + rem] = bary[rem];
+    }
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * blockDim.x * (D + 1);
+    const size_t end = (size_t)Next * (D + 1);
+    if (!*reinterpret_cast<volatile uint32_t*>(counts + 1)) {
+#pragma unroll
+        for (int k = 0; k <= D; k++) {
+            const int q = k * 256 + threadIdx.x;
+            if (base + q < end) {
+                offsets[base + q] = s_off[q];
+                bary_out[base + q] = s_bary[q];
+            }
         }
     }
 }
