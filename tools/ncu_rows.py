@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One line per profiled launch from an exported `ncu --page raw --csv` file.  usage: python tools/ncu_rows.py raw.csv [--json out.json]"""
-import csv, json, sys
+import csv, json, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
@@ -17,7 +17,8 @@ agg = {}
 def tobytes(metric, v):
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(units[idx[metric]].lower(), 1)
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("rss::", "")
+    # "void rss::point_alone::meanfield_point_kernel<5, 4, 6, 3>(..." -> "meanfield_point_kernel<5, 4, 6, 3>"
+    name = re.sub(r"^(?:\w+::)+", "", r[idx["Kernel Name"]].split("(")[0].replace("void ", ""))
     vals = []
     for m, n in want:
         try:

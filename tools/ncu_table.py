@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an ncu report: one row per profiled launch with the metrics that matter for HBM/L2-bound kernels.
 usage: python tools/ncu_table.py report.ncu-rep [--json out.json]"""
-import csv, json, subprocess, sys
+import csv, json, re, subprocess, sys
 rep = sys.argv[1]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -18,7 +18,7 @@ print("%-34s" % "kernel" + "".join("%10s" % n for _, n in want))
 print("%-34s" % "" + "".join("%10s" % units[idx[m]][:9] for m, _ in want))
 agg = {}
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("rss::", "")
+    name = re.sub(r"^(?:\w+::)+", "", r[idx["Kernel Name"]].split("(")[0].replace("void ", ""))
     vals = []
     for m, n in want:
         v = r[idx[m]].replace(",", "")
