@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
             const int pos = (int)(atomicAdd(&hcc[h], 0x10000u) >> 16);
             const float b = bary[(size_t)p * D1 + j];
             const float nv = (pre | post) ? norm[p] : 1.f;
-            spairs[pos] = make_uint2((unsigned)lp, __float_as_uint(pre ? __fmul_rn(b, nv) : b));
+            spairs[pos] = make_uint2((unsigned)q_row(lp), __float_as_uint(pre ? __fmul_rn(b, nv) : b));  // row in the Q tile
             ws = __fmul_rn(post ? __fmul_rn(b, nv) : b, slice_scale);
             slot = hrow[h];
         }

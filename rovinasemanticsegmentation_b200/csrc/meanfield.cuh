@@ -127,6 +127,18 @@ struct TileCsrOut {
 #ifndef RSS_TILE_MINB
 #define RSS_TILE_MINB 3  // resident CTAs per SM the "alone" build of the point kernel is compiled for (register budget)
 #endif
+#ifndef RSS_POINT_ALIAS
+#define RSS_POINT_ALIAS 0  // the point kernel's splat lists reuse the shared memory of the staged value rows (4 CTAs per SM)
+#endif
+#ifndef RSS_QROW_SKEW
+#define RSS_QROW_SKEW 3
+#endif
+// Row of local point lp in the point kernel's shared Q tile: the 32 rows of every warp (= one image row of a 32-pixel-wide
+// tile) are rotated by RSS_QROW_SKEW * warp index.  The bank group of a row is (G * row + g) mod 8, i.e. - G odd - the row
+// mod 8; unrotated that is x mod 8 for every image row, so a vertex whose pixel blob is narrower than 8 pixels only offers
+// the splat a few of the eight classes however tall it is (the eight lanes of a quarter-warp read eight different rows
+// conflict-free only if these differ mod 8).  With the skew the class is (x + 3 y) mod 8: a 2 x 8 blob covers all eight.
+__host__ __device__ __forceinline__ int q_row(int lp) { return (lp & ~31) | ((lp + RSS_QROW_SKEW * (lp >> 5)) & 31); }
 constexpr int TILE_SEG = RSS_TILE_SEG;
 // the 64-register build of the point kernel (meanfield_shared.cu), for SMs shared with the cooperative blur
 cudaError_t launch_meanfield_fused_shared(rss_ctx* c, cudaStream_t st, const FusedArgs& a, int d1a, int d1b, const float* unary,

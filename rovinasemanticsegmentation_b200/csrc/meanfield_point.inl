@@ -181,7 +181,15 @@ __global__ void RSS_POINT_BOUNDS
     float4* qtile = smem_f4;            // [TP][G]  unary rows on arrival, marginals after phase 1
     float4* rowsA = qtile + TP * G;     // [RC][G]  staged value rows of lattice A ...
     float4* rowsB = rowsA + RC * G;     //          ... and B
+#if RSS_POINT_ALIAS
+    // the splat lists share the shared memory of the staged value rows (phase 2 follows phase 1): ~46 instead of ~70 KB per
+    // CTA, i.e. 4 instead of 3 CTAs per SM; their bulk copy is then issued after phase 1, not at the start
+    constexpr bool alias_lists = do_slice && do_splat;
+    int2* metaA = reinterpret_cast<int2*>(alias_lists ? rowsA : rowsB + (D1B > 0 ? RC * G : 0));
+#else
+    constexpr bool alias_lists = false;
     int2* metaA = reinterpret_cast<int2*>(rowsB + (D1B > 0 ? RC * G : 0));  // 2 * TP segment slots shared by the lattices
+#endif
     int2* metaB = metaA;
     uint2* spairsA = reinterpret_cast<uint2*>(metaA + 2 * TP);
     uint2* spairsB = spairsA + TP * D1A;
@@ -225,7 +233,7 @@ __global__ void RSS_POINT_BOUNDS
                 bulk_g2s(qtile + (size_t)ly * tm.TW * G, unary + ((size_t)(org.y0 + ly) * tm.W + org.x0) * MP,
                          (unsigned)w * MP * 4, bar0);
         }
-        if (do_splat) {
+        if (do_splat && !alias_lists) {
             // sizes rounded up to 16 bytes: the arrays have TP * D1 (even) slots per tile, so the extra 8 bytes exist
             const unsigned szMA = ((unsigned)capA * 8 + 15) & ~15u, szMB = ((unsigned)capB * 8 + 15) & ~15u;
             const unsigned szPA = (unsigned)TP * D1A * 8, szPB = (unsigned)TP * D1B * 8;
@@ -251,6 +259,7 @@ __global__ void RSS_POINT_BOUNDS
     }
     // ---- phase 1: one thread = one point
     const int p = tile_point(tm, org, lp);
+    const unsigned live_lanes = __ballot_sync(0xffffffffu, p >= 0);  // the lanes that take part in phase 1
     mbar_wait(bar0, 0);
     if (p >= 0) {
         float t[MP];
@@ -306,11 +315,15 @@ __global__ void RSS_POINT_BOUNDS
             for (int g = 0; g < G; g++)
                 if ((m >> g) & 1u) gs[g] = rs;
         }
+        // the marginals go to the ROTATED row (q_row): another lane's unary row, which that lane read at the top of phase 1 -
+        // the rotation stays inside the warp's 32 rows, so a warp-level barrier orders its reads before these writes
+        const int qr = q_row(lp);
+        if (do_splat) __syncwarp(live_lanes);
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const float4 v = make_float4(t[4 * g] * gs[g], t[4 * g + 1] * gs[g], t[4 * g + 2] * gs[g], t[4 * g + 3] * gs[g]);
             t[4 * g] = v.x; t[4 * g + 1] = v.y; t[4 * g + 2] = v.z; t[4 * g + 3] = v.w;
-            if (do_splat) qtile[lp * G + g] = v;
+            if (do_splat) qtile[qr * G + g] = v;
             if (store_q && Q) reinterpret_cast<float4*>(Q + (size_t)p * MP)[g] = v;
         }
         if (labels) {
@@ -327,7 +340,21 @@ __global__ void RSS_POINT_BOUNDS
         }
     }
     if (!do_splat) return;
-    __syncthreads();  // the tile's marginals are complete
+    __syncthreads();  // the tile's marginals are complete (and nobody reads the staged value rows any more)
+    if (alias_lists && threadIdx.x == 0) {
+        // generic-proxy reads of the rows region are ordered before the async-proxy writes of the bulk copies
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // sizes rounded up to 16 bytes: the arrays have TP * D1 (even) slots per tile, so the extra 8 bytes exist
+            const unsigned szMA = ((unsigned)capA * 8 + 15) & ~15u, szMB = ((unsigned)capB * 8 + 15) & ~15u;
+            const unsigned szPA = (unsigned)TP * D1A * 8, szPB = (unsigned)TP * D1B * 8;
+            mbar_expect_tx(bar1, szMA + szMB + szPA + szPB);
+            if (szMA) bulk_g2s(metaA, a.lat[0].ent_meta + tbA, szMA, bar1);
+            bulk_g2s(spairsA, a.lat[0].pairs + tbA, szPA, bar1);
+            if constexpr (D1B > 0) {
+                if (szMB) bulk_g2s(metaB, a.lat[1].ent_meta + tbB, szMB, bar1);
+                bulk_g2s(spairsB, a.lat[1].pairs + tbB, szPB, bar1);
+            }
+    }
     mbar_wait(bar1, 0);
     // ---- phase 2: tile-local gather splat out of shared memory
     gather_entries<G, false>(spairsA, metaA, capA, a.lat[0].ent_meta + tbA, neA, a.lat[0].vout, qtile);
@@ -339,8 +366,13 @@ template <int G, int A, int B, int M>
 static cudaError_t launch_point_m(rss_ctx* c, cudaStream_t st, const FusedArgs& a, const float* unary, float* Q, uint8_t* labels,
                                   const TileMap& tm, const FusedLayers& ls) {
     auto kfn = meanfield_point_kernel<G, A, B, M>;
-    const size_t smem = (size_t)TILE_POINTS * G * sizeof(float4) + (size_t)TILE_ROW_CAP * G * sizeof(float4) * (B > 0 ? 2 : 1) +
-                        (size_t)2 * TILE_POINTS * sizeof(int2) + (size_t)TILE_POINTS * (A + B) * sizeof(uint2);
+    const size_t rows_b = (size_t)TILE_ROW_CAP * G * sizeof(float4) * (B > 0 ? 2 : 1);
+    const size_t lists_b = (size_t)2 * TILE_POINTS * sizeof(int2) + (size_t)TILE_POINTS * (A + B) * sizeof(uint2);
+#if RSS_POINT_ALIAS
+    const size_t smem = (size_t)TILE_POINTS * G * sizeof(float4) + ((M & 3) == 3 ? std::max(rows_b, lists_b) : rows_b + lists_b);
+#else
+    const size_t smem = (size_t)TILE_POINTS * G * sizeof(float4) + rows_b + lists_b;
+#endif
     if (c->smem_attr_done.insert((const void*)kfn).second) { /* once per context (= per device) and instantiation */
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
