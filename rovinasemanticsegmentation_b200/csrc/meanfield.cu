@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
                                                              float slice_scale, const TileMap tm, int row_bytes, int HC,
                                                              const uint32_t* __restrict__ counts, const TileCsrOut out) {
     __shared__ int hist[TILE_SEG + 1], binstart[TILE_SEG + 1], cumstart[TILE_SEG + 1];
+    __shared__ int colstart[8 * 32];  // per warp: column starts of the segment group it is ordering
     extern __shared__ int tile_smem[];  // above the 48 KB static limit for large d
     int* hkeys = tile_smem;  // HC slots (power of two, > pairs per tile)
     // per slot: pair count in the low half, fill cursor of the slot's pair list in the high half (both <= TP * D1 <
@@ -270,8 +271,8 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         }
     }
     __syncthreads();
-    // one segment per thread: the classes of its <= 32 pairs packed as nibbles in two 64-bit registers (a used pair
-    // becomes 0xF, which matches no class), so "the first unused pair of class c" is a zero-nibble search, not a scan.
+    // one segment per thread: the classes of its <= 32 pairs packed as nibbles in two 64-bit registers (unused nibbles are
+    // 0xF, which matches no class), so "the pairs of class c" is a zero-nibble mask, not a scan.
     // STORAGE: the 32 consecutive segments a warp of the gather walks form a group, stored COLUMN-major - first pair 0 of
     // every segment of the group, then pair 1 of every segment that has one, ... (segments are ordered longest first, so
     // the segments that still have a pair q are a prefix of the group and a column is compact).  At step q the lanes of a
@@ -287,35 +288,72 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         int col = cumstart[len0] + (i0 - binstart[len0]) * len0;  // pairs before the group
         if (idx < tot.x) reinterpret_cast<int*>(out.ent_meta + tb + idx)[0] = col | (len << 16);
         const uint2* lst = spairs + start;
-        unsigned long long c0 = ~0ull, c1 = ~0ull;  // two registers, never indexed dynamically (that would be local memory)
+        // column starts of the group: position q of every segment lies at colw[q] + lane (lane q keeps the start it sees)
+        int mycol = 0;
+        for (int q = 0; q < len0; q++) {
+            if (lane == q) mycol = col;
+            col += __popc(__ballot_sync(0xffffffffu, q < len));
+        }
+        int* colw = colstart + (threadIdx.x >> 5) * 32;
+        __syncwarp();
+        colw[lane] = mycol;
+        __syncwarp();
+        if (len == 0) continue;  // (no warp-level operation below)
+        // the classes of the pairs as nibbles in two 64-bit registers (never indexed dynamically: that would be local memory)
+        unsigned long long c0 = ~0ull, c1 = ~0ull;
         for (int f = 0; f < len; f++) {
             const int sh = 4 * (f & 15);
             const unsigned long long keep = ~(0xFull << sh), val = (unsigned long long)((G * lst[f].x) & 7u) << sh;
             if (f < 16) c0 = (c0 & keep) | val;
             else c1 = (c1 & keep) | val;
         }
-        for (int q = 0; q < len0; q++) {
-            const bool act = q < len;
-            const unsigned bal = __ballot_sync(0xffffffffu, act);
-            if (act) {
-                const unsigned long long want = (unsigned long long)((unsigned)(G * (idx + q)) & 7u) * 0x1111111111111111ull;
-                // zero nibble of c ^ want <=> unused pair of the wanted class
-                const unsigned long long x0 = c0 ^ want, x1 = c1 ^ want;
-                const unsigned long long z0 = (x0 - 0x1111111111111111ull) & ~x0 & 0x8888888888888888ull;
-                const unsigned long long z1 = (x1 - 0x1111111111111111ull) & ~x1 & 0x8888888888888888ull;
+        // the positions that want class c: want(q) = G (idx + q) mod 8 has period 8 in q
+        unsigned posmask[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) posmask[c] = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const unsigned w = (unsigned)(G * (idx + q)) & 7u;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                if (w == (unsigned)c) posmask[c] |= 0x01010101u << q;
+        }
+        const unsigned lenmask = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+        unsigned filled = 0u;
+        unsigned long long l0 = 0ull, l1 = 0ull;  // members that found no position of their class (bit 4 f' + 3 of word f / 16)
+        auto place = [&](int f, int q) {
+            const uint2 v = lst[f];
+            out.pairs[tb + colw[q] + lane] = make_uint2(v.x * (unsigned)row_bytes, v.y);
+        };
+        // class by class (static unroll: every mask stays in a register): the k-th pair of the class takes the k-th position
+        // that wants it
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const unsigned long long want = (unsigned long long)c * 0x1111111111111111ull;
+            const unsigned long long x0 = c0 ^ want, x1 = c1 ^ want;  // zero nibble <=> pair of class c
+            unsigned long long z0 = (x0 - 0x1111111111111111ull) & ~x0 & 0x8888888888888888ull;
+            unsigned long long z1 = (x1 - 0x1111111111111111ull) & ~x1 & 0x8888888888888888ull;
+            unsigned pos = posmask[c] & lenmask;
+            while (pos && (z0 | z1)) {
                 int f;
-                if (z0) f = (__ffsll((long long)z0) - 1) >> 2;
-                else if (z1) f = 16 + ((__ffsll((long long)z1) - 1) >> 2);
-                else {  // the class is exhausted: any unused pair (bit 3 of its nibble is clear)
-                    const unsigned long long u0 = ~c0 & 0x8888888888888888ull, u1 = ~c1 & 0x8888888888888888ull;
-                    f = u0 ? ((__ffsll((long long)u0) - 1) >> 2) : 16 + ((__ffsll((long long)u1) - 1) >> 2);
-                }
-                if (f < 16) c0 |= 0xFull << (4 * f);
-                else c1 |= 0xFull << (4 * (f - 16));
-                const uint2 v = lst[f];
-                out.pairs[tb + col + lane] = make_uint2(v.x * (unsigned)row_bytes, v.y);
+                if (z0) { f = (__ffsll((long long)z0) - 1) >> 2; z0 &= z0 - 1; }
+                else { f = 16 + ((__ffsll((long long)z1) - 1) >> 2); z1 &= z1 - 1; }
+                const int q = __ffs(pos) - 1;
+                pos &= pos - 1;
+                filled |= 1u << q;
+                place(f, q);
             }
-            col += __popc(bal);
+            l0 |= z0; l1 |= z1;
+        }
+        // the classes that ran out leave holes; the left-over pairs fill them in order
+        unsigned holes = lenmask & ~filled;
+        while (holes) {
+            int f;
+            if (l0) { f = (__ffsll((long long)l0) - 1) >> 2; l0 &= l0 - 1; }
+            else { f = 16 + ((__ffsll((long long)l1) - 1) >> 2); l1 &= l1 - 1; }
+            const int q = __ffs(holes) - 1;
+            holes &= holes - 1;
+            place(f, q);
         }
     }
 }
