@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
     __shared__ float s_bary[256 * (D + 1)];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // no early exit: the lanes of a warp agree on duplicate vertices below (full-mask match / shuffle)
-    const bool live = i < Next && !*reinterpret_cast<volatile uint32_t*>(counts + 1);  // overflow: the build is void anyway
+    // (an L2 read, not a system-scope volatile one: a stale 0 only means this thread still works on a build that is void)
+    const bool live = i < Next && !__ldcg(counts + 1);  // overflow: the build is void anyway
     // i == N (only when N % 4 != 0): the reference's SSE loop pads its last block of four points with ZERO features and
     // still inserts their vertices (permutohedral.cpp:192-198,268-275).  Those vertices never receive a splat, but they
     // exist for the blur and pass values on between their neighbours - so they must exist here too.
@@ -202,14 +203,12 @@ __global__ void __launch_bounds__(256) lattice_embed_kernel(const float* __restr
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * blockDim.x * (D + 1);
     const size_t end = (size_t)Next * (D + 1);
-    if (!*reinterpret_cast<volatile uint32_t*>(counts + 1)) {
 #pragma unroll
-        for (int k = 0; k <= D; k++) {
-            const int q = k * 256 + threadIdx.x;
-            if (base + q < end) {
-                offsets[base + q] = s_off[q];
-                bary_out[base + q] = s_bary[q];
-            }
+    for (int k = 0; k <= D; k++) {  // (also after an overflow: the host rebuilds everything then)
+        const int q = k * 256 + threadIdx.x;
+        if (base + q < end) {
+            offsets[base + q] = s_off[q];
+            bary_out[base + q] = s_bary[q];
         }
     }
 }

@@ -331,8 +331,11 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
         for (int c = 0; c < 8; c++) {
             const unsigned long long want = (unsigned long long)c * 0x1111111111111111ull;
             const unsigned long long x0 = c0 ^ want, x1 = c1 ^ want;  // zero nibble <=> pair of class c
-            unsigned long long z0 = (x0 - 0x1111111111111111ull) & ~x0 & 0x8888888888888888ull;
-            unsigned long long z1 = (x1 - 0x1111111111111111ull) & ~x1 & 0x8888888888888888ull;
+            // EXACT zero-nibble mask (bit 3 of every zero nibble): no carries between nibbles, unlike the (x - 0x11..) & ~x
+            // test, which is only right about the LOWEST zero nibble
+            constexpr unsigned long long N7 = 0x7777777777777777ull, N8 = 0x8888888888888888ull;
+            unsigned long long z0 = ~(((x0 & N7) + N7) | x0) & N8;
+            unsigned long long z1 = ~(((x1 & N7) + N7) | x1) & N8;
             unsigned pos = posmask[c] & lenmask;
             while (pos && (z0 | z1)) {
                 int f;
