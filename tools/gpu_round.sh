@@ -5,8 +5,10 @@
 TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
+if [ -z "$SKIPTEST" ]; then  # SKIPTEST=1: the same build was just tested by a separate call
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_$TAG.log
 tail -3 $OUT/pytest_$TAG.log
+fi
 timeout 600 python bench.py --steps 30 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 python profiles/show_bench.py $OUT/bench_$TAG.json 2>/dev/null | head -30
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "reference arm rc=$?"; cut -c1-300 $OUT/bench_ref_$TAG.json
