@@ -12,6 +12,8 @@ both label layers, gated argmax (BASELINE.json configs[1], with configs[2]'s sec
           the K steps, device-wide synchronisation on both sides)
   e2e   : the same through the C ABI with HOST buffers: pinned rgb/depth in, label maps out, copies inside the timed region
   latency: one keyframe at a time (library CUDA events), with the per-stage and per-kernel break-down
+  cpp_worker: the C++ host (host/keyframe_worker.cpp, one process driving all N GPUs, one thread per keyframe in flight) on
+          the same workload, run by rank 0 after the timed region while the ranks are idle: wall clock, end to end
 N > 1 (torchrun): every rank owns one GPU and its own keyframes (weak scaling, no collective on the data path);
 the timed region is bracketed by a barrier + synchronize and the slowest rank's time is used.
 """
@@ -779,12 +781,36 @@ def run_gpu(args, rank, world, local_rank):
             line["parity_check"] = {"label_agreement": min(agree), "per_layer": agree, "frame_seed": frame_seeds(0)[0],
                                     "bar": 0.999, "ok": bool(min(agree) >= 0.999),
                                     "what": "rss_segment_keyframe (host buffers, the e2e path) vs oracle.keyframe on the same 640x480 frame"}
-        print(json.dumps(line), flush=True)
+    # the C++ multi-GPU host (one process, all N GPUs) runs while the ranks are idle: every rank waits here, rank 0 runs it
     for c in ctxs:
         c.close()
     if dist is not None:
         dist.barrier()
+    if rank == 0:
+        if not args.quick or world > 1:
+            line["cpp_worker"] = cpp_worker_bench(world, NC, 1500 * world)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def cpp_worker_bench(n_gpus, inflight, frames):
+    """The C++ host path over the same C ABI (host/keyframe_worker.cpp: one thread per (GPU, keyframe in flight), pinned host
+    buffers in, label maps out, no Python): its own throughput figure next to the torchrun ranks, at every N."""
+    from rovinasemanticsegmentation_b200 import build as rss_build
+    import rovinasemanticsegmentation_b200 as rss
+    try:
+        exe = rss_build.build_host()
+        r = subprocess.run([exe, "--config", rss.DEFAULT_CONFIG, "--forest", FOREST, "--gpus", str(n_gpus), "--inflight",
+                            str(inflight), "--frames", str(frames)], capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            return {"error": (r.stderr or "rc=%d" % r.returncode).strip()[-200:]}
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        out["note"] = "wall clock around %d keyframes, end to end with host buffers, no L2 flush between keyframes" % frames
+        return out
+    except Exception as e:  # a missing g++ or binary is not a reason to lose the bench line
+        return {"error": str(e)[-200:]}
 
 
 def forest_train_bench(ctx, synth, with_cpu):
