@@ -21,8 +21,13 @@
 //            out of shared memory and issues G red.global.add.v4.f32.  Global atomics per iteration = (distinct vertices
 //            per tile) * G instead of (nonzeros) * G, Q is never re-read from L2, and nothing depends on how noisy the
 //            pixel order is (+-8 colour noise sends 64 % of consecutive pixels to a different bilateral vertex).
+//            The 32 segments a warp walks are stored column-major (conflict-free pair reads), and a point's row in the Q
+//            tile is rotated by 3 x its warp index (meanfield.cuh: q_row), so that narrow vertex blobs still spread over
+//            all eight 16-byte bank groups.
 // Value tables rotate through three buffers per lattice: `res` (blurred result being sliced), `tgt` (all zero, receives
 // the splat) and `spare`; the blur ping-pongs between tgt and spare and clears the old `res`, the next tgt.
+// The point kernel itself lives in meanfield_point.inl and is compiled twice (this file: up to 85 registers, the build
+// for a context that is alone on the GPU; meanfield_shared.cu: 64 registers, for SMs shared with other keyframes' blur).
 //
 // Compile-time tuning knobs (build.py: RSS_NVCC_DEFS="-DNAME=value"), defaults measured on B200:
 #include <algorithm>

@@ -65,8 +65,10 @@ __device__ __forceinline__ int tile_point(const TileMap& m, const TileOrigin& o,
 struct FusedLat {
     const float* pt_w;         // D1 * TP floats per tile, pt_index() order
     const uint16_t* pt_slot;   // D1 * TP row slots per tile, pt_index() order
-    const uint2* pairs;        // (byte offset of the local point's row in the shared Q tile, weight bits), by segment
-    const int2* ent_meta;      // per segment: x = start in the tile's pair array | length << 16, y = vertex id
+    const uint2* pairs;        // (byte offset of the local point's row in the shared Q tile - q_row(lp) - and weight bits); the 32
+                               // consecutive segments one warp walks form a group, stored column-major (pair k of every
+                               // segment of the group that has one, then pair k + 1, ...)
+    const int2* ent_meta;      // per segment: x = first pair of the segment's GROUP | length << 16, y = vertex id
     const int* tile_vert;      // row slot -> vertex id
     const int2* tile_info;     // per tile: x = segments, y = distinct vertices (row slots)
     const float* vin;          // blurred value table of the previous iteration (slice source)
