@@ -40,7 +40,11 @@
 #define RSS_POINT_MAXNREG 0  // > 0: register cap of the "alone" build of the point kernel instead of RSS_TILE_MINB
 #endif
 #ifndef RSS_BLUR_SHARED_T
-#define RSS_BLUR_SHARED_T (RSS_BLUR_MAXT / 2)  // CTA size of the cooperative blur while several keyframes share the GPU
+#define RSS_BLUR_SHARED_T 256  // CTA size of the cooperative blur while several keyframes share the GPU (128: 1027, 512: 1075
+                               // keyframes/s against 1100 at 256)
+#endif
+#ifndef RSS_BLUR_ALONE_T
+#define RSS_BLUR_ALONE_T 768   // ... and alone on the GPU: 26.1 us at 512, 23.4 us at 768, 25.2 us at 1024 threads per SM
 #endif
 #ifndef RSS_BLUR_SHARED_GRID_DIV
 #define RSS_BLUR_SHARED_GRID_DIV 1  // the shared-GPU blur runs on sm_count / this many SMs
@@ -49,8 +53,10 @@
 #define RSS_BLUR_U 2      // independent (vertex, channel group) items a blur thread keeps in flight
 #endif
 #ifndef RSS_BLUR_MAXT
-#define RSS_BLUR_MAXT 512  // CTA size of the cooperative blur: the phases are L2-throughput-bound once >= 512 threads per
-                           // SM keep loads in flight (tools/micro/blur_bench.cu: 35 us at 128, 25 us at 512 and 1024)
+#define RSS_BLUR_MAXT 1024  // launch bound of the cooperative blur = its register cap (64): a 256-thread CTA must fit next to
+                            // three 64-register point CTAs (a bound of 768 lets the compiler take more, which cost 7 % of the
+                            // shared-GPU throughput); the phases are L2-throughput-bound once >= 512 threads per SM keep loads
+                            // in flight (tools/micro/blur_bench.cu: 35 us at 128, 25 us at 512 and 1024)
 #endif
 #ifndef RSS_BLUR_FUSE
 #define RSS_BLUR_FUSE 2  // lattice axes blurred per phase of the cooperative blur (1 = one grid barrier per axis); measured on
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(256) tile_csr_build_kernel(const int* __restri
     // the segments that still have a pair q are a prefix of the group and a column is compact).  At step q the lanes of a
     // warp then read consecutive 8-byte pairs: no bank conflicts (row-major lists with arbitrary starts: 3.6 wavefronts
     // per 8-byte read).  ent_meta.x = first pair of the segment's GROUP | length << 16.
+    static_assert(RSS_BLUR_ALONE_T <= RSS_BLUR_MAXT && RSS_BLUR_SHARED_T <= RSS_BLUR_MAXT, "blur CTA sizes exceed the launch bound");
     static_assert(TILE_SEG <= 32, "the segment ordering packs 32 classes into 128 bits");
     const int lane = threadIdx.x & 31;
     for (int i0 = threadIdx.x - lane; i0 < tot.x; i0 += 256) {
@@ -576,7 +583,7 @@ void launch_tile_csr_build(rss_ctx* c, cudaStream_t st, const int* offsets, cons
 #undef RSS_TCB
 }
 
-// Launch shape of the cooperative blur.  Alone on the GPU: one CTA of RSS_BLUR_MAXT threads per SM.  Sharing the GPU with
+// Launch shape of the cooperative blur.  Alone on the GPU: one CTA of RSS_BLUR_ALONE_T threads per SM.  Sharing the GPU with
 // other keyframes in flight: RSS_BLUR_SHARED_T threads per CTA on sm_count / RSS_BLUR_SHARED_GRID_DIV SMs - the blur is
 // resident most of the time then, and what it costs the other keyframes' kernels is the CTA slots its registers block.
 BlurShape blur_multi_shape(const rss_ctx* c) {
@@ -586,7 +593,7 @@ BlurShape blur_multi_shape(const rss_ctx* c) {
         s.block = RSS_BLUR_SHARED_T;
     } else {
         s.grid = c->sm_count;
-        s.block = RSS_BLUR_MAXT;
+        s.block = RSS_BLUR_ALONE_T;
     }
     return s;
 }
