@@ -202,7 +202,6 @@ def algo_bytes(name, env):
         "gradient_mask_kernel": 12 * N + 24 * N + 2 * N + 4 * N,
         "dist_forward_kernel": 8 * N, "dist_backward_kernel": 8 * N,
         "integral_wavefront_kernel<512>": 24 * N + 2 * N + 48 * N + 8 * N,
-        "integral_warps_kernel<512>": 24 * N + 2 * N + 48 * N + 8 * N,
         "scalar_features_kernel": 8 * Ns + 2 * Ns + 12 * Ns + 12 * Ns,
         # R1, R2 (classifier.cpp, segmenter.cpp:355-431)
         "forest_traverse_kernel": 4 * D * Ns + 16 * env["nodes"] + 4 * T * Ns,

@@ -262,75 +262,6 @@ __global__ void __launch_bounds__(MAXT) integral_wavefront_kernel(const float* _
                                             reinterpret_cast<int*>(smd), W, H);
 }
 
-// ------------------------------------------------------------------------------------------------
-// (2b) the same recurrence as a pipeline of WARPS (default when the boundary rows fit in shared memory).  Thread r still
-// owns row r and the evaluation order of every element is unchanged, but
-//   * inside a warp the "up" value comes from the lane above by SHUFFLE (the lanes of a warp walk one anti-diagonal: lane l
-//     handles column j - l at the warp's local step j), so a step is shuffle + three dependent DADDs, with no barrier and
-//     no shared-memory round trip;
-//   * between warps the last row of warp w (its lane 31) goes through a shared-memory row [W], and warp w+1 runs
-//     D = ceil((K + 31) / K) ROUNDS of K steps behind warp w, so that everything its lane 0 reads in a round was written
-//     before the previous round's barrier: one __syncthreads per K = 8 steps instead of one per step.
-// The schedule is 14 * K steps longer than the anti-diagonal count (W + H - 1 + 14 K), but a step costs ~1/3.
-// ------------------------------------------------------------------------------------------------
-constexpr int WFW_K = 8;
-template <typename T, typename TIn>
-__device__ __forceinline__ void wavefront_plane_warps(const TIn* __restrict__ g, T* __restrict__ I, T* bnd, int W, int H) {
-    constexpr int K = WFW_K;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int r = threadIdx.x;
-    const bool row_ok = r < H;
-    const int HP = skew_pitch(H);
-    const int D = (K + 31 + K - 1) / K;     // rounds a warp lags the warp above it
-    const int nsteps = W + 31;              // local steps of a warp: column j - lane at step j
-    const int rounds = (nsteps + K - 1) / K + D * (nw - 1);
-    T left = T(0), upleft = T(0), vprev = T(0);
-    const T* up_row = bnd + (size_t)(w > 0 ? w - 1 : 0) * W;  // last row of the warp above
-    T* my_row = bnd + (size_t)w * W;
-    for (int t = 0; t < rounds; t++) {
-        const int j0 = K * (t - D * w);
-        if (j0 >= 0 && j0 < nsteps) {  // warp-uniform
-            TIn e[K];
-#pragma unroll
-            for (int k = 0; k < K; k++) {  // the round's inputs: K independent coalesced loads (global step 32 w + j)
-                const int j = j0 + k, c = j - lane;
-                e[k] = (row_ok && c >= 0 && c < W) ? __ldg(g + (size_t)(32 * w + j) * HP + r) : TIn(0);
-            }
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const int j = j0 + k, c = j - lane;
-                const bool act = row_ok && c >= 0 && c < W;
-                // the lane above computed column c one step ago (an inactive lane above means this lane is inactive too)
-                T up = __shfl_up_sync(0xffffffffu, vprev, 1);
-                if (lane == 0) up = (w > 0 && act) ? up_row[c] : T(0);
-                if (act) {
-                    T v;
-                    if constexpr (sizeof(T) == 8) v = __dadd_rn(__dsub_rn(__dadd_rn(up, left), upleft), (double)e[k]);
-                    else v = up + left - upleft + (T)e[k];
-                    I[(size_t)(32 * w + j) * HP + r] = v;
-                    if (lane == 31) my_row[c] = v;
-                    upleft = up;
-                    left = v;
-                    vprev = v;
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) integral_warps_kernel(const float* __restrict__ grad, const uint8_t* __restrict__ fin,
-                                                              int W, int H, double* __restrict__ integ, int* __restrict__ cnt) {
-    extern __shared__ double smd[];  // [warps][W] doubles (or ints): the last row of every warp
-    const size_t SP = skew_elems(W, H);
-    const int plane_id = blockIdx.x;
-    if (plane_id < 6)
-        wavefront_plane_warps<double, float>(grad + (size_t)plane_id * SP, integ + (size_t)plane_id * SP, smd, W, H);
-    else
-        wavefront_plane_warps<int, uint8_t>(fin + (size_t)(plane_id - 6) * SP, cnt + (size_t)(plane_id - 6) * SP,
-                                            reinterpret_cast<int*>(smd), W, H);
-}
-
 void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int W, int H, float* dist_a,
                             float* dist_b, double* integ, int* integ_cnt, float* grad, uint8_t* fin) {
     dim3 grid(rss_div_up(W, GM_T), rss_div_up(H, GM_T));
@@ -342,22 +273,6 @@ void launch_normals_prepare(rss_ctx* c, cudaStream_t st, const float4* xyz, int 
     RSS_LAUNCH(c, dist_forward_kernel, rss_div_up(H, band), threads, smem, st, dist_b, W, H, band, dist_a);
     RSS_LAUNCH(c, dist_backward_kernel, rss_div_up(H, band), threads, smem, st, dist_a, W, H, band, dist_b);
     const int wt = min(1024, rss_div_up(H, 32) * 32);
-    // warp pipeline (shuffles inside a warp, one barrier per 8 steps) when the boundary rows fit in shared memory;
-    // RSS_WF_BARRIER=1 selects the barrier-per-step kernel
-    const size_t bsmem = (size_t)(wt / 32) * W * sizeof(double);
-    static const bool wf_barrier = getenv("RSS_WF_BARRIER") != nullptr;
-    if (!wf_barrier && bsmem <= 200 * 1024) {
-        if (wt <= 512) {
-            if (c->smem_attr_done.insert((const void*)integral_warps_kernel<512>).second)
-                cudaFuncSetAttribute(integral_warps_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            RSS_LAUNCH(c, integral_warps_kernel<512>, 8, wt, bsmem, st, grad, fin, W, H, integ, integ_cnt);
-        } else {
-            if (c->smem_attr_done.insert((const void*)integral_warps_kernel<1024>).second)
-                cudaFuncSetAttribute(integral_warps_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            RSS_LAUNCH(c, integral_warps_kernel<1024>, 8, wt, bsmem, st, grad, fin, W, H, integ, integ_cnt);
-        }
-        return;
-    }
     const size_t wsmem = (size_t)2 * (H + 1) * sizeof(double);
     if (wt <= 512) RSS_LAUNCH(c, integral_wavefront_kernel<512>, 8, wt, wsmem, st, grad, fin, W, H, integ, integ_cnt);
     else RSS_LAUNCH(c, integral_wavefront_kernel<1024>, 8, wt, wsmem, st, grad, fin, W, H, integ, integ_cnt);

@@ -16,7 +16,7 @@ if [ "$2" != "noncu" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --quick --inflight 1 > $OUT/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'meanfield_point_kernel|blur_multi_coop|integral_wavefront|integral_warps|lattice_embed|tile_csr_build|forest_frame_lowres|upsample_|gradient_mask|neighbors_kernel' \
+    -k regex:'meanfield_point_kernel|blur_multi_coop|integral_wavefront|lattice_embed|tile_csr_build|forest_frame_lowres|upsample_|gradient_mask|neighbors_kernel' \
     --launch-skip 40 --launch-count 20 -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 3 --quick --inflight 1 > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ncu -i $OUT/prof_$TAG.ncu-rep --page raw --csv > $OUT/prof_${TAG}_raw.csv 2>/dev/null
 ncu -i $OUT/prof_$TAG.ncu-rep --page source --csv --kernel-name regex:meanfield_point_kernel > $OUT/prof_${TAG}_src_point.csv 2>/dev/null
