@@ -80,3 +80,23 @@ def test_reference_gradient_harness_is_consistent(orc):
     r1, _ = orc.ref_crf_gradient(U, [(f, 3.0 + eps), (f[:, :2] * np.float32(0.5), 1.5)], 3, gt)
     r0, _ = orc.ref_crf_gradient(U, [(f, 3.0 - eps), (f[:, :2] * np.float32(0.5), 1.5)], 3, gt)
     assert r < 0 and abs((r1 - r0) / (2 * eps) - g[0]) <= 0.01 * abs(g[0])
+
+
+def test_meanfield_plans_and_layout_helpers(tmp_path):
+    """Host-side logic of the fused mean-field path (csrc/meanfield.cu / meanfield.cuh), checked without a GPU by a small nvcc
+    program linked against librss.so (tests/cpp/plans_check.cu): the cooperative blur's phase plan covers every lattice axis
+    exactly once, in order, in consecutive phases (permutohedral.cpp:555-569 blurs axes 0..d in turn - the ping / pong parity
+    of the result depends on the phase count), the Q-tile row rotation is a permutation inside a warp, the point-major
+    (corner, point) index is a bijection, and the tile maps of image / 1-D point sets have the expected tile counts."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(rss.__file__))
+    lib_dir = os.path.dirname(rss.LIB_PATH)
+    assert os.path.exists(rss.LIB_PATH), "librss.so is not built"
+    exe = str(tmp_path / "plans_check")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets",
+                           "-I" + os.path.join(root, "rovinasemanticsegmentation_b200", "csrc"), "-I" + os.path.join(root, "include"),
+                           "-o", exe, os.path.join(root, "tests", "cpp", "plans_check.cu"), "-L" + lib_dir, "-lrss",
+                           "-Xlinker", "-rpath", "-Xlinker", lib_dir])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "plans_check OK" in r.stdout, r.stdout + r.stderr
