@@ -220,6 +220,12 @@ def algo_bytes(name, env):
         "lattice_embed_kernel<D>": mean(lambda d, V: 4 * d * N + 8 * (d + 1) * N + 2 * d * V),
         "remap_offsets_kernel": mean(lambda d, V: 8 * (d + 1) * N), "csr_fill_kernel": mean(lambda d, V: 16 * (d + 1) * N),
         "first_flags_kernel": mean(lambda d, V: 8 * (d + 1) * N), "assign_ids_kernel": mean(lambda d, V: 8 * (d + 1) * N),
+        # bitmap numbering (lattice.cu): hash table of ~4 V slots; one bit per (point, corner) pair; one prefix word per 32 bits
+        "first_bitmap_kernel": mean(lambda d, V: 16 * V + (d + 1) * N / 8),
+        "bitmap_chunk_sums_kernel": mean(lambda d, V: (d + 1) * N / 8),
+        "bitmap_prefix_kernel": mean(lambda d, V: (d + 1) * N / 8 + (d + 1) * N / 8),
+        "assign_ids_bitmap_kernel": mean(lambda d, V: 32 * V + 8 * V),
+        "unary_init_kernel": 4 * (M + 3) * N,
         # C1 mean-field iteration (permutohedral.cpp:529-589, densecrf.cpp:98-131)
         "softmax_init_kernel": 8 * M * N,
         "splat_kernel": mean(lambda d, V: 4 * M * N + 8 * (d + 1) * N + 4 * N + 4 * M * V),

@@ -58,3 +58,28 @@ def test_algorithmic_bytes_table():
     assert 60e6 < b < 110e6
     assert bench.algo_bytes("patch_features_kernel", env) > 4 * 363 * 70000
     assert bench.algo_bytes("no_such_kernel", env) is None
+
+
+def test_every_profiled_kernel_has_algorithmic_bytes():
+    """Every kernel of the library in the committed ncu launch list of the bench (profiles/r02z_launches.csv) has an entry in
+    bench.algo_bytes - a kernel without one reads 0 % in the per-kernel roofline table."""
+    import csv
+    import re
+    sys.path.insert(0, ROOT)
+    import bench
+    env = {"N": 640 * 480, "M": 17, "Ns": 70000, "D": 366, "T": 4, "nodes": 16000, "leaves": 8000, "P": 77,
+           "lat": [(3, 40000), (5, 11000)]}
+    lines = [l for l in open(os.path.join(ROOT, "profiles", "r02z_launches.csv")) if not l.startswith("==")]
+    names = set()
+    for row in csv.DictReader(lines):
+        if "rss::" not in row["Kernel Name"]:
+            continue  # the bench's own L2-flush fill kernel (torch)
+        n = re.sub(r"^(?:\w+::)+", "", row["Kernel Name"].split("(")[0].replace("void ", "").strip())
+        # the library's profile table names the three variants of the point kernel by their role
+        m = re.match(r"meanfield_point_kernel<\d+, \d+, \d+, (\d+)>", n)
+        if m:
+            n = {"2": "meanfield_point_kernel<first>", "3": "meanfield_point_kernel", "5": "meanfield_point_kernel<last>"}[m.group(1)]
+        names.add(n)
+    assert len(names) > 25
+    missing = [n for n in sorted(names) if not bench.algo_bytes(n, env)]
+    assert not missing, missing
