@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=6) as ex:
         list(ex.map(run, jobs))
     if jobs or not os.path.exists(OUT):
-        run([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"])
+        # (the arch on the link line too: nvcc's device-link stub otherwise targets its default, sm_52)
+        run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart"])
     return OUT
 
 
